@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the modal-synthesis path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): mode-samples/s (IIR + FFAT-weighted modal sum), whole job over N GPUs.
+Workload: SURVEY.md 8(d) cfg5 -- offline batch, 4096 objects x 512 modes x 10 s of audio at 44.1 kHz
+(1723 buffers of 256 samples), one PointForce per object in the first second, one static listener per
+object (FFAT transfer vector resident), mixed down to one track.  Objects are block-partitioned over
+the N ranks (strong scaling, total work fixed); the only exchange is one NCCL reduce (sum) of the
+441 088-sample FP64 mix.  One "step" = one full render of that job.
+
+The JSON line also carries: the FP32-FMA roofline of the synthesis kernel (peak measured in the same
+run with an FMA micro-benchmark), the CPU oracle timed on this box's host cores on a bounded sample
+(`cpu_baseline`), the end-to-end number through the host-pointer C ABI (`e2e`), and the real-time
+per-buffer latency of the second half of the metric (cfg2: 1024 modes, 256-sample buffers) under
+`realtime`.
+
+`--impl reference` times the reference's CPU path (the oracle port of modal_solver.h:181-276; the
+reference itself cannot be built here) with all host threads on bounded samples.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_OBJ, N_MODES, BUF, N_BUF = 4096, 512, 256, 1723      # cfg5: 441 088 samples = 10.0 s
+FLOP_PER_MODE_SAMPLE = 8.0                              # 4 FMA: 3 in Step (modal_integrator.h:109-110) + 1 in the dot (modal_solver.h:267-269)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--objects", type=int, default=N_OBJ, help="total objects (default cfg5: 4096)")
+    ap.add_argument("--modes", type=int, default=N_MODES)
+    ap.add_argument("--buffers", type=int, default=N_BUF)
+    ap.add_argument("--precision", default="f32_tiled", choices=["f32_tiled", "f64"])
+    ap.add_argument("--no-realtime", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def shard(n_obj, world, rank):
+    """Contiguous block of objects for `rank`."""
+    per = (n_obj + world - 1) // world
+    lo = min(rank * per, n_obj)
+    return lo, min(lo + per, n_obj)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (the ONLY place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_render_sample(n_threads, obj_per_thread, n_modes, n_buf, seed):
+    """Each host thread renders `obj_per_thread` cfg5 objects for the full 10 s with the oracle's
+    ModalSolver::step loop.  Returns (mode_samples, seconds)."""
+    from oracle import oracle as orc
+    from openpbso_b200 import synth
+    orc.lib()
+    n = n_threads * obj_per_thread
+    w = synth.batch_workload(n, n_modes, n_buf, seed)
+    mixes = [np.zeros(n_buf * BUF) for _ in range(n_threads)]
+
+    def work(t):
+        lo, hi = t * obj_per_thread, (t + 1) * obj_per_thread
+        orc.batch_render(synth.H, w["a"][lo:hi], w["b"][lo:hi], w["space"][lo:hi], w["trans"][lo:hi],
+                         w["imp_buf"][lo:hi], BUF, n_buf, mixes[t])
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    t0 = time.perf_counter()
+    for th in threads: th.start()
+    for th in threads: th.join()
+    dt = time.perf_counter() - t0
+    return float(n) * n_modes * n_buf * BUF, dt
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip(); break
+    except OSError:
+        pass
+    return model, os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, cores = cpu_info()
+    obj_per_thread = 1
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        cpu_render_sample(cores, 1, args.modes, max(args.buffers // 8, 1), 1)
+    tot_ms = 0.0; tot_dt = 0.0
+    for k in range(args.steps):
+        ms, dt = cpu_render_sample(cores, obj_per_thread, args.modes, args.buffers, 1005 + k)
+        tot_ms += ms; tot_dt += dt
+    value = tot_ms / tot_dt
+    sample = "%d objects x %d modes x %d samples per step (1 object per host thread), oracle port of ModalSolver::step" % (
+        cores * obj_per_thread, args.modes, args.buffers * BUF)
+    line = {
+        "impl": "reference", "metric": "mode-samples/s (IIR+FFAT)", "value": value, "unit": "mode-samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg5 offline batch (bounded sample): %s" % sample, "cpu": model},
+        "cpu_baseline": {"value": value, "unit": "mode-samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "mode-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index; self.rows = []; self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try: self.p.wait(timeout=2)
+        except Exception: self.p.kill()
+        sm = []; mx = None; reasons = set(); power = []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2]); power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def realtime_latency(pbso, synth, n_buffers=4000):
+    """cfg2: one 1024-mode object, 256-sample buffers, Bernoulli(0.12) impulse stream, host pointers in
+    and out through pbso_render_buffer (H2D + kernel + D2H + sync per buffer)."""
+    N = 1024
+    mat = synth.MATERIALS["low_damping"]
+    f = synth.mode_frequencies(N, 1002)
+    a, b = synth.ab_from_material(f, mat)
+    it = pbso.ModalIntegrator(N, synth.H, a, b)
+    rng = np.random.default_rng(1002)
+    it.set_transfer(np.abs(rng.standard_normal(N)) + 0.1)
+    spaces = rng.standard_normal((64, N)); zero = np.zeros(N)
+    tm_imp = np.zeros(BUF); tm_imp[0] = 1.0; tm_zero = np.zeros(BUF)
+    hits = rng.random(n_buffers) < 0.12
+    for _ in range(200):
+        it.render_buffer(zero, tm_zero)
+    lat = np.empty(n_buffers)
+    for i in range(n_buffers):
+        sp, tm = (spaces[i & 63], tm_imp) if hits[i] else (zero, tm_zero)
+        t0 = time.perf_counter()
+        it.render_buffer(sp, tm)
+        lat[i] = time.perf_counter() - t0
+    it.close()
+    us = lat * 1e6
+    return {"workload": "cfg2: 1024 modes, 1 listener, 256-sample buffers, Bernoulli(0.12) PointForce stream, host in/out",
+            "buffers": n_buffers, "p50_us": float(np.percentile(us, 50)), "p99_us": float(np.percentile(us, 99)),
+            "p999_us": float(np.percentile(us, 99.9)), "max_us": float(us.max()),
+            "mode_samples_per_s": float(N * BUF / np.mean(lat)), "dtype": "f64",
+            "budget_us": 1e6 * BUF / synth.SAMPLE_RATE}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openpbso_b200 import build
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if rank == 0:
+        build.build()                 # no-op when the in-tree .so is current
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    import openpbso_b200 as pbso
+    from openpbso_b200 import synth
+    pbso.set_device(local)
+    prec = pbso.PREC_F32_TILED if args.precision == "f32_tiled" else pbso.PREC_F64
+
+    lo, hi = shard(args.objects, world, rank)
+    n_local = hi - lo
+    # synthetic workload: generated per rank for its own shard (seeded by object range)
+    w = synth.batch_workload(args.objects, args.modes, args.buffers, 1005)
+    sl = slice(lo, hi)
+    a, b = w["a"][sl], w["b"][sl]
+    # pinned host staging for the e2e arm
+    def pinned(x):
+        t = torch.empty(x.shape, dtype=torch.float64 if x.dtype == np.float64 else torch.int32, pin_memory=True)
+        t.numpy()[...] = x
+        return t.numpy()
+    space_h = pinned(w["space"][sl]); trans_h = pinned(w["trans"][sl])
+    obj_h = pinned(np.arange(n_local, dtype=np.int32)); buf_h = pinned(w["imp_buf"][sl].astype(np.int32))
+    n_samples = args.buffers * BUF
+    br = pbso.BatchRenderer(synth.H, a, b)
+    # a dedicated (non-default) stream shared by the render kernel, the NCCL reduce and the timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    br.set_stream(stream.cuda_stream)
+    br.set_transfer(trans_h)
+    br.set_impulses(obj_h, buf_h, space_h)
+    mix = torch.zeros(n_samples, dtype=torch.float64, device="cuda")     # also the NCCL send buffer
+    mix_host = torch.empty(n_samples, dtype=torch.float64, pin_memory=True)
+
+    def step_device():
+        br.render_mix_device(BUF, args.buffers, mix.data_ptr(), prec)
+        if world > 1:
+            dist.reduce(mix, dst=0, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    # ---- timed region: exactly K steps, device-resident inputs -----------------------------
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        pbso.flush_l2(256 << 20)                       # evict L2 between timed iterations (default stream)
+        torch.cuda.synchronize()
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+        kernel_ms.append(br.last_kernel_ms()[0])       # syncs on the render kernel's own event pair
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    kms = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX); dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    ms_per_step = tot.item() / args.steps
+    mode_samples = float(args.objects) * args.modes * n_samples
+    value = mode_samples / (ms_per_step * 1e-3)
+
+    # ---- e2e: same job through the host-pointer C ABI, copies inside the timed region --------
+    def step_e2e():
+        br.set_transfer(trans_h)                       # H2D
+        br.set_impulses(obj_h, buf_h, space_h)         # H2D (+ host-side CSR build)
+        step_device()
+        if rank == 0:
+            mix_host.copy_(mix, non_blocking=True)     # D2H of the result
+        torch.cuda.synchronize()
+    step_e2e(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = mode_samples / (e2e_t.item() / args.steps)
+    h2d = (space_h.nbytes + trans_h.nbytes + obj_h.nbytes + buf_h.nbytes)
+    h2d_t = torch.tensor([float(h2d)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(h2d_t, op=dist.ReduceOp.SUM)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    # ---- rank 0 only: peaks, roofline, CPU baseline, real-time latency -----------------------
+    checksum = float(mix_host.abs().sum().item())
+    peaks, peaks_kind = measured_peaks()
+    fma = {}
+    for kind, name in ((0, "ffma_uniform"), (1, "ffma2_uniform"), (3, "ffma_3reg"), (4, "ffma2_3reg"), (2, "dfma")):
+        t, mhz = pbso.measure_fma_peak(kind)
+        fma[name] = round(t, 2)
+    fp32_peak = max(fma["ffma_uniform"], fma["ffma2_uniform"], fma["ffma_3reg"], fma["ffma2_3reg"])
+    info = pbso.device_info()
+    k_ms = kms.item()
+    achieved = (float(n_local) * args.modes * n_samples) * FLOP_PER_MODE_SAMPLE / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32_fma", "kernel": "k_batch_pow<4>" if prec == pbso.PREC_F32_TILED else "k_batch_f64",
+                "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                "traffic": None, "kernel_ms": k_ms,
+                "peak_source": "FMA micro-benchmark in this run (pbso_measure_fma_peak; MEASURED_PEAKS.json has no FP32 figure)",
+                "peak_nominal": info["sm_count"] * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12,
+                "fma_microbench_tflops": fma,
+                "algorithmic": "8 FLOP per mode-sample (reference recurrence); the kernel evaluates each sample from "
+                               "precomputed pole powers with 2 FMA, so frac can exceed the FMA-pipe utilisation"}
+    line = {
+        "metric": "mode-samples/s (IIR+FFAT)", "value": value, "unit": "mode-samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 tiles + f64 carrier" if prec == pbso.PREC_F32_TILED else "f64",
+        "data": "synthetic",
+        "config": {"workload": "cfg5 offline batch: %d objects x %d modes x %d samples (%d buffers of %d), one PointForce "
+                               "per object, static listeners, mixed down" % (args.objects, args.modes, n_samples, args.buffers, BUF),
+                   "parallelism": "objects block-partitioned over %d rank(s); one NCCL reduce(sum) of the FP64 mix" % world,
+                   "l2": "flushed with a 256 MiB write between timed steps; per-step inputs %.0f MB" % (
+                       (7 * a.size * 8 + space_h.nbytes) / 1e6),
+                   "mix_abs_sum": checksum},
+        "roofline": roofline, "clocks": clocks, "gpu_launches": args.steps * world,
+        "e2e": {"value": e2e_value, "unit": "mode-samples/s", "h2d_bytes_per_step": int(h2d_t.item()),
+                "d2h_bytes_per_step": int(mix_host.numel() * 8), "ms_per_step": 1e3 * e2e_t.item() / args.steps},
+        "wall_ms_per_step": 1e3 * t_wall / args.steps, "peaks": {"source": peaks_kind, "hbm_gbs": peaks.get("hbm_gbs")},
+    }
+    if not args.no_cpu_baseline:
+        model, cores = cpu_info()
+        ms, dt = cpu_render_sample(cores, 1, args.modes, args.buffers, 1005)
+        line["cpu_baseline"] = {"value": ms / dt, "unit": "mode-samples/s", "cores": cores, "kind": "port",
+                                "sample": "%d objects x %d modes x %d samples (1 object per host thread, %s), %.1f s" % (
+                                    cores, args.modes, n_samples, model, dt)}
+    if not args.no_realtime:
+        line["realtime"] = realtime_latency(pbso, synth)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

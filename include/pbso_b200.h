@@ -1,0 +1,193 @@
+/* =============================================================================
+ * pbso_b200.h -- C ABI of libpbso_b200.so: the B200 (sm_100a) implementation of openpbso's
+ * modal-synthesis hot path  (U^T f projection -> per-mode IIR -> FFAT-weighted modal sum).
+ *
+ * The reference (jhwang7628/openpbso) has no FFI layer: its API is a set of header-only C++
+ * templates.  include/openpbso/ mirrors those headers and forwards to the entry points
+ * below; each entry point cites the reference interface it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; host pointers unless a name ends in _device / d_*
+ *  - every function returns an int status (PBSO_OK == 0); never throws, never spins
+ *  - handles are opaque; each owns one CUDA stream and its device/pinned buffers; a handle is
+ *    bound to the device that was current (pbso_set_device) when it was created
+ *  - all arithmetic visible at this boundary is IEEE double, like the reference
+ *    (ModalSolver<double>, tools/real_time_modal_sound.cpp:188); the offline batch renderer
+ *    additionally offers an FP32-tile fast path that stays within the parity tolerance
+ *  - there is NO CPU fallback: without a CUDA device every compute entry returns
+ *    PBSO_ERR_NO_DEVICE
+ * ============================================================================= */
+#ifndef PBSO_B200_H
+#define PBSO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBSO_ABI_VERSION 1
+
+enum {
+    PBSO_OK = 0,
+    PBSO_ERR_INVALID = 1,     /* bad argument: null pointer, size mismatch (reference: assert) */
+    PBSO_ERR_CUDA = 2,        /* CUDA runtime failure; text in pbso_last_error() */
+    PBSO_ERR_IO = 3,          /* file / directory missing or unreadable */
+    PBSO_ERR_FORMAT = 4,      /* malformed .fatcube / .modes contents */
+    PBSO_ERR_RANGE = 5,       /* index or mode id out of range (reference: std::out_of_range) */
+    PBSO_ERR_NO_DEVICE = 6,   /* no CUDA device: the product has no CPU path */
+    PBSO_ERR_UNSUPPORTED = 7
+};
+
+typedef struct pbso_integrator pbso_integrator;  /* ModalIntegrator<double> + per-buffer renderer */
+typedef struct pbso_ffat pbso_ffat;              /* std::map<int, FFAT_Map<double,3>> */
+typedef struct pbso_modes pbso_modes;            /* ModeData<double>::_modes on the device */
+typedef struct pbso_batch pbso_batch;            /* many independent sound objects, offline */
+
+/* ---- library / device ----------------------------------------------------------------- */
+int pbso_abi_version(void);
+const char* pbso_last_error(void);               /* thread-local, valid until the next call */
+int pbso_device_count(int* n);
+int pbso_set_device(int device);                 /* like cudaSetDevice, per calling thread */
+int pbso_device_info(int* sm_count, int* cc_major, int* cc_minor, double* hbm_gib);
+
+/* ---- modal integrator: modal_integrator.h --------------------------------------------- */
+/* ModalIntegrator<T>::Build (modal_integrator.h:39-42, 47-70).  N < 0 means n_omega. */
+int pbso_integrator_build(double density, const double* omega_squared, int n_omega,
+                          double alpha, double beta, double h, int N, pbso_integrator** out);
+/* ModalIntegrator<T>::ModalIntegrator(N, h, a, b) (modal_integrator.h:37-38, 72-101):
+ * coefficient kernel K2 runs in FP64 on the device. */
+int pbso_integrator_create(int N, double h, const double* a, const double* b,
+                           pbso_integrator** out);
+int pbso_integrator_destroy(pbso_integrator* it);
+int pbso_integrator_size(const pbso_integrator* it, int* N);
+/* _c1/_c2/_c3 (modal_integrator.h:32-34, 95-99); any pointer may be NULL. */
+int pbso_integrator_get_coeffs(const pbso_integrator* it, double* c1, double* c2, double* c3);
+/* Step(Q) / Step() (modal_integrator.h:43-44, 103-123); Q == NULL selects Step().
+ * q_out[N] receives q_k (the reference returns a reference into its ring). */
+int pbso_integrator_step(pbso_integrator* it, const double* Q, double* q_out);
+/* Ring contents as (q_{k-1}, q_{k-2}) (modal_integrator.h:24,29): checkpoint / chunked render. */
+int pbso_integrator_get_state(const pbso_integrator* it, double* q_km1, double* q_km2);
+int pbso_integrator_set_state(pbso_integrator* it, const double* q_km1, const double* q_km2);
+
+/* ---- per-buffer synthesis: ModalSolver::step hot loop (modal_solver.h:261-272) ---------
+ * For i in [0,T):  q = Step(space * time[i]);  y[l][i] = sum_{m < n_transfer} q[m]*transfer[l][m];
+ * qnorm[m] = sqrt(sum_i q[m]^2).  Kernel K1 (FP64 direct form, state kept in registers).
+ *   space[N], time[T]; y_out[L*T] (listener-major); qnorm_out[N] or NULL.
+ * The transfer table is resident: set it with pbso_integrator_set_transfer (TransMessage,
+ * modal_solver.h:84-98, 250-252); transfer is column-major n_transfer x L like the reference's
+ * batched call site (tools/real_time_modal_sound.cpp:921-927).  L == 0 renders q only. */
+int pbso_integrator_set_transfer(pbso_integrator* it, const double* transfer, int n_transfer,
+                                 int L);
+int pbso_render_buffer(pbso_integrator* it, const double* space, const double* time, int T,
+                       double* y_out, double* qnorm_out);
+/* Same, enqueue-only on the handle's stream with device-resident inputs/outputs (no copies,
+ * no sync).  d_y must hold L*T doubles. */
+int pbso_render_buffer_device(pbso_integrator* it, const double* d_space, const double* d_time,
+                              int T, double* d_y, double* d_qnorm);
+int pbso_integrator_sync(pbso_integrator* it);
+
+/* ---- FFAT maps: ffat_solver.h runtime subset + ffat_map_serialize.h ------------------- */
+/* FFAT_Map_Serialize_Double::LoadAll (ffat_map_serialize.h:267-279) incl. ListDirFiles(dir,
+ * ".fatcube") (io.cpp:18-35).  A missing directory yields an empty set and PBSO_ERR_IO. */
+int pbso_ffat_load_dir(const char* dirname, pbso_ffat** out);
+/* FFAT_Map_Serialize_Double::Load (ffat_map_serialize.h:166-254) of a single file. */
+int pbso_ffat_load_file(const char* filename, pbso_ffat** out);
+/* Build a set from arrays (the fields ffat_map_serialize.h:55-79 keeps), one record per map:
+ * geom[32] = {cellSize, lowCorners[6][3], shell centre[3], bboxLow[3], bboxTop[3], map centre[3], k}
+ * igeom[18] = {N_elements[6][2], strides[6]};  psi = n_maps blocks of psi_len doubles (column 0). */
+int pbso_ffat_create(int n_maps, const int* mode_ids, const double* geom, const int* igeom,
+                     const double* psi, int psi_len, const unsigned char* is_compressed,
+                     pbso_ffat** out);
+int pbso_ffat_destroy(pbso_ffat* f);
+int pbso_ffat_num_maps(const pbso_ffat* f, int* n);
+int pbso_ffat_mode_ids(const pbso_ffat* f, int* ids);
+/* Field access by mode id, for FFAT_Map_Serialize_Double::Check-style comparisons
+ * (ffat_map_serialize.h:281-329).  psi may be NULL to query psi_len only. */
+int pbso_ffat_get_map(const pbso_ffat* f, int mode_id, double* geom32, int* igeom18,
+                      int* psi_len, int* psi_cols, int* is_compressed, double* psi);
+/* FFAT_Map_Serialize_Double::Save (ffat_map_serialize.h:90-164). */
+int pbso_ffat_save_file(const pbso_ffat* f, int mode_id, const char* filename);
+/* ModalSolver::computeTransfer (modal_solver.h:286-315) for L listeners at once (kernel K3):
+ * out[l*n_modes + m] = |maps.at(m).GetMapVal(pos_l, use_compressed)|, m in [0, n_modes)
+ * (ffat_solver.h:1180-1206 -> Intersect :676-712 -> Interpolate :736-803 -> Reconstruct :899-906).
+ * pos is L x 3.  A missing mode id in [0, n_modes) returns PBSO_ERR_RANGE (.at() throws). */
+int pbso_ffat_eval(const pbso_ffat* f, int n_modes, const double* pos, int L, int use_compressed,
+                   double* out);
+int pbso_ffat_eval_device(const pbso_ffat* f, int n_modes, const double* d_pos, int L,
+                          double* d_out, void* cuda_stream);
+
+/* ---- mode shapes and impulse projection U^T f ---------------------------------------- */
+/* ModeData<REAL>::_modes (ModeData.h:23-24), mode-major U[M][K]. */
+int pbso_modes_upload(const double* U, int M, int K, pbso_modes** out);
+/* ModeData<REAL>::read (ModeData.h:61-83) straight to the device; omega_squared[M] may be NULL. */
+int pbso_modes_read_file(const char* filename, pbso_modes** out, int* M, int* K);
+int pbso_modes_omega_squared(const pbso_modes* md, double* omega_squared);
+int pbso_modes_destroy(pbso_modes* md);
+/* GetModalForceVertex (tools/real_time_modal_sound.cpp:268-280): out[m] = vn . U_m[3vid..3vid+2] */
+int pbso_modes_project_vertex(const pbso_modes* md, int force_dim, int vid, const double* vn3,
+                              double* out);
+/* GetModalForceFace (tools/real_time_modal_sound.cpp:236-251). */
+int pbso_modes_project_face(const pbso_modes* md, int force_dim, const int* vids3,
+                            const double* coords3, const double* vn3, double* out);
+/* Batched sparse form: B vertex impulses at once; out is B x force_dim (row per impulse). */
+int pbso_modes_project_vertices(const pbso_modes* md, int force_dim, int B, const int* vids,
+                                const double* vn, double* out);
+/* Dense form Y = U F, U[force_dim][K] and F[K][B] row-major, Y[force_dim][B] (kernel K4 for B == 1:
+ * HBM-bound GEMV; K5 for B > 1: tensor-core contraction with 3xTF32 split, FP32 accumulate). */
+int pbso_modes_project_dense(const pbso_modes* md, int force_dim, const double* F, int B,
+                             double* Y);
+int pbso_modes_project_dense_device(const pbso_modes* md, int force_dim, const float* d_F, int B,
+                                    float* d_Y, void* cuda_stream);
+
+/* ---- offline batch renderer (many objects x long audio) ------------- */
+/* n_obj independent sound objects with n_modes each; (a,b) are n_obj x n_modes as accepted by
+ * ModalIntegrator(N,h,a,b).  Each object behaves exactly like its own ModalSolver::step loop
+ * (modal_solver.h:181-276) fed with PointForce messages (forces.h:81-90). */
+int pbso_batch_create(int n_obj, int n_modes, double h, const double* a, const double* b,
+                      pbso_batch** out);
+int pbso_batch_destroy(pbso_batch* bt);
+/* One TransMessage per object, applied from buffer 0 (static listeners): trans[n_obj][n_modes]. */
+int pbso_batch_set_transfer(pbso_batch* bt, const double* trans);
+/* Impulse script: event e = a ForceMessage{data = space[e][n_modes], PointForce} enqueued so that
+ * object obj[e] dequeues it in step #buf[e] (impulse lands on sample 0 of that buffer, forces.h:87).
+ * step() dequeues at most one message per buffer (modal_solver.h:184), so two events of one object
+ * in the same buffer are rejected with PBSO_ERR_INVALID. */
+int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const int* buf,
+                            const double* space);
+#define PBSO_PREC_F64 0        /* FP64 direct form: the reference's arithmetic */
+#define PBSO_PREC_F32_TILED 1  /* FP32 coupled-form tiles re-seeded from an FP64 carrier */
+/* Render n_buffers x buf_size samples of every object from zero state and mix them down:
+ * mix[i] = sum_obj y_obj[i]  (double, n_buffers*buf_size).  Runs on n_chunks independent time
+ * chunks (0 = choose) whose start states come from closed-form pole powers. */
+int pbso_batch_render_mix(pbso_batch* bt, int buf_size, int n_buffers, int precision,
+                          int n_chunks, double* mix);
+/* Device-resident variant: enqueue only; d_mix (double[n_buffers*buf_size]) is zeroed then
+ * accumulated on the handle's stream -- e.g. straight into an NCCL send buffer. */
+int pbso_batch_render_mix_device(pbso_batch* bt, int buf_size, int n_buffers, int precision,
+                                 int n_chunks, double* d_mix);
+/* Per-object stems: y[n_obj][n_buffers*buf_size] float32 (y as in SoundMessage, before /1e10). */
+int pbso_batch_render_stems(pbso_batch* bt, int buf_size, int n_buffers, int precision,
+                            float* stems);
+int pbso_batch_sync(pbso_batch* bt);
+/* Run this handle's work on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the
+ * handle's own stream) so that renders order with the caller's copies / NCCL calls without host syncs. */
+int pbso_batch_set_stream(pbso_batch* bt, void* cuda_stream);
+/* CUDA-event time of the last render kernel(s) on the handle's stream, and launches issued. */
+int pbso_batch_last_kernel_ms(pbso_batch* bt, float* ms, int* launches);
+
+/* ---- measurement helpers (device micro-benchmarks used by bench.py for roofline peaks) -- */
+/* kind 0: FP32 FFMA (uniform operands); 1: packed fma.rn.f32x2 (uniform operands); 2: FP64 DFMA;
+ * 3: FFMA with three distinct registers; 4: fma.rn.f32x2 with three distinct register pairs.
+ * Returns measured TFLOP/s. */
+int pbso_measure_fma_peak(int kind, double* tflops, double* sm_mhz_est);
+/* STREAM-style device copy bandwidth in GB/s (read+write bytes). */
+int pbso_measure_copy_bw(size_t bytes, double* gbs);
+/* Writes `bytes` to a scratch buffer to evict L2 between timed iterations. */
+int pbso_flush_l2(size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBSO_B200_H */

@@ -1,0 +1,280 @@
+"""Object view of the C ABI, named after the reference classes each wraps."""
+import ctypes as C
+import numpy as np
+from . import _capi as capi
+from ._capi import check, f64, dp, ip, lib
+
+
+def device_count():
+    n = C.c_int()
+    check(lib().pbso_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(dev):
+    check(lib().pbso_set_device(dev))
+
+
+def device_info():
+    sm = C.c_int(); ma = C.c_int(); mi = C.c_int(); gib = C.c_double()
+    check(lib().pbso_device_info(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(gib)))
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value), hbm_gib=gib.value)
+
+
+def measure_fma_peak(kind):
+    t = C.c_double(); mhz = C.c_double()
+    check(lib().pbso_measure_fma_peak(kind, C.byref(t), C.byref(mhz)))
+    return t.value, mhz.value
+
+
+def measure_copy_bw(nbytes):
+    g = C.c_double()
+    check(lib().pbso_measure_copy_bw(nbytes, C.byref(g)))
+    return g.value
+
+
+def flush_l2(nbytes=256 << 20):
+    check(lib().pbso_flush_l2(nbytes))
+
+
+class ModalIntegrator:
+    """ModalIntegrator<double> (modal_integrator.h:19-45) + the ModalSolver::step hot loop."""
+
+    def __init__(self, N, h, a, b):
+        a = f64(a); b = f64(b)
+        self._h = C.c_void_p()
+        check(lib().pbso_integrator_create(N, h, dp(a), dp(b), C.byref(self._h)))
+        self.N = N
+
+    @classmethod
+    def Build(cls, density, omegaSquared, alpha, beta, h, N=-1):
+        """modal_integrator.h:39-42"""
+        w2 = f64(omegaSquared)
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        check(lib().pbso_integrator_build(density, dp(w2), len(w2), alpha, beta, h, N, C.byref(self._h)))
+        n = C.c_int(); check(lib().pbso_integrator_size(self._h, C.byref(n)))
+        self.N = n.value
+        return self
+
+    def coeffs(self):
+        c1 = np.empty(self.N); c2 = np.empty(self.N); c3 = np.empty(self.N)
+        check(lib().pbso_integrator_get_coeffs(self._h, dp(c1), dp(c2), dp(c3)))
+        return c1, c2, c3
+
+    def Step(self, Q=None):
+        """modal_integrator.h:43-44"""
+        out = np.empty(self.N)
+        Qc = None if Q is None else f64(Q)
+        if Qc is not None and len(Qc) != self.N:
+            raise capi.PbsoError(capi.ERR_INVALID, "input force incorrect dimension")   # :108
+        check(lib().pbso_integrator_step(self._h, dp(Qc), dp(out)))
+        return out
+
+    def get_state(self):
+        q1 = np.empty(self.N); q2 = np.empty(self.N)
+        check(lib().pbso_integrator_get_state(self._h, dp(q1), dp(q2)))
+        return q1, q2
+
+    def set_state(self, q1, q2):
+        q1 = f64(q1); q2 = f64(q2)
+        check(lib().pbso_integrator_set_state(self._h, dp(q1), dp(q2)))
+
+    def set_transfer(self, transfer, L=1):
+        """transfer: [L][n_transfer] (= column-major n_transfer x L)."""
+        t = f64(transfer).reshape(L, -1) if L > 0 else np.zeros((0, 0))
+        self.L = L
+        check(lib().pbso_integrator_set_transfer(self._h, dp(t), t.shape[1] if L > 0 else 0, L))
+
+    def render_buffer(self, space, time, want_qnorm=True):
+        """ModalSolver::step hot loop (modal_solver.h:261-272): returns (y[L][T], qnorm[N])."""
+        space = f64(space); time = f64(time); T = len(time)
+        L = getattr(self, "L", 1)
+        y = np.empty((max(L, 1), T)); qn = np.empty(self.N) if want_qnorm else None
+        check(lib().pbso_render_buffer(self._h, dp(space), dp(time), T, dp(y), dp(qn)))
+        return (y if L > 0 else None), qn
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pbso_integrator_destroy(self._h); self._h = None
+
+    __del__ = close
+
+
+class FFATMaps:
+    """std::map<int, FFAT_Map<double,3>> as produced by FFAT_Map_Serialize::LoadAll."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def LoadAll(cls, dirname):
+        h = C.c_void_p()
+        rc = lib().pbso_ffat_load_dir(dirname.encode(), C.byref(h))
+        self = cls(h)
+        if rc != capi.OK:
+            self.close()
+            check(rc)
+        return self
+
+    @classmethod
+    def Load(cls, filename):
+        h = C.c_void_p()
+        check(lib().pbso_ffat_load_file(filename.encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_dicts(cls, maps):
+        n = len(maps); D = len(maps[0]["psi"])
+        geom = np.empty((n, 32)); igeom = np.empty((n, 18), dtype=np.int32); psi = np.empty((n, D))
+        ids = np.empty(n, dtype=np.int32); comp = np.zeros(n, dtype=np.uint8)
+        for i, m in enumerate(maps):
+            geom[i, 0] = m["cellsize"]; geom[i, 1:19] = np.asarray(m["lowcorners"], dtype=np.float64).reshape(18)
+            geom[i, 19:22] = m["center1"]; geom[i, 22:25] = m["bboxlow"]; geom[i, 25:28] = m["bboxtop"]
+            geom[i, 28:31] = m["center"]; geom[i, 31] = m["k"]
+            igeom[i, :12] = np.asarray(m["n_elements"], dtype=np.int32).reshape(12); igeom[i, 12:] = m["strides"]
+            psi[i] = m["psi"]; ids[i] = m["modeid"]; comp[i] = bool(m.get("is_compressed", False))
+        h = C.c_void_p()
+        check(lib().pbso_ffat_create(n, ip(ids), dp(geom), ip(igeom), dp(psi), D,
+                                     comp.ctypes.data_as(C.POINTER(C.c_ubyte)), C.byref(h)))
+        return cls(h)
+
+    def size(self):
+        n = C.c_int(); check(lib().pbso_ffat_num_maps(self._h, C.byref(n))); return n.value
+
+    def mode_ids(self):
+        ids = np.empty(self.size(), dtype=np.int32)
+        if len(ids):
+            check(lib().pbso_ffat_mode_ids(self._h, ip(ids)))
+        return ids
+
+    def get_map(self, mode_id):
+        geom = np.empty(32); igeom = np.empty(18, dtype=np.int32)
+        n = C.c_int(); cols = C.c_int(); comp = C.c_int()
+        check(lib().pbso_ffat_get_map(self._h, mode_id, dp(geom), ip(igeom), C.byref(n), C.byref(cols), C.byref(comp), None))
+        psi = np.empty((cols.value, n.value))
+        check(lib().pbso_ffat_get_map(self._h, mode_id, None, None, None, None, None, dp(psi)))
+        return dict(cellsize=geom[0], lowcorners=geom[1:19].reshape(6, 3).copy(), center1=geom[19:22].copy(),
+                    bboxlow=geom[22:25].copy(), bboxtop=geom[25:28].copy(), center=geom[28:31].copy(), k=geom[31],
+                    n_elements=igeom[:12].reshape(6, 2).copy(), strides=igeom[12:].copy(),
+                    psi=psi[0].copy(), psi_cols=[c.copy() for c in psi], is_compressed=bool(comp.value), modeid=mode_id)
+
+    def Save(self, mode_id, filename):
+        check(lib().pbso_ffat_save_file(self._h, mode_id, filename.encode()))
+
+    def computeTransfer(self, pos, n_modes=None, use_compressed=False):
+        """modal_solver.h:286-315 for L listeners: returns [L][n_modes]."""
+        pos = f64(pos).reshape(-1, 3); L = len(pos)
+        n = self.size() if n_modes is None else n_modes
+        out = np.empty((L, n))
+        check(lib().pbso_ffat_eval(self._h, n, dp(pos), L, int(use_compressed), dp(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pbso_ffat_destroy(self._h); self._h = None
+
+    __del__ = close
+
+
+class ModeShapes:
+    """ModeData<double>::_modes resident on the device + GetModalForceVertex/Face."""
+
+    def __init__(self, U=None, _handle=None, _shape=None):
+        if _handle is not None:
+            self._h = _handle; self.M, self.K = _shape
+            return
+        U = f64(U); self.M, self.K = U.shape
+        self._h = C.c_void_p()
+        check(lib().pbso_modes_upload(dp(U), self.M, self.K, C.byref(self._h)))
+
+    @classmethod
+    def read(cls, filename):
+        """ModeData::read (ModeData.h:61-83)"""
+        h = C.c_void_p(); M = C.c_int(); K = C.c_int()
+        check(lib().pbso_modes_read_file(filename.encode(), C.byref(h), C.byref(M), C.byref(K)))
+        return cls(_handle=h, _shape=(M.value, K.value))
+
+    def omegaSquared(self):
+        w2 = np.empty(self.M); check(lib().pbso_modes_omega_squared(self._h, dp(w2))); return w2
+
+    def GetModalForceVertex(self, forceDim, vid, vn):
+        vn = f64(vn); out = np.empty(forceDim)
+        check(lib().pbso_modes_project_vertex(self._h, forceDim, int(vid), dp(vn), dp(out)))
+        return out
+
+    def GetModalForceFace(self, forceDim, vids, coords, vn):
+        vids = np.ascontiguousarray(vids, dtype=np.int32); coords = f64(coords); vn = f64(vn)
+        out = np.empty(forceDim)
+        check(lib().pbso_modes_project_face(self._h, forceDim, ip(vids), dp(coords), dp(vn), dp(out)))
+        return out
+
+    def project_vertices(self, forceDim, vids, vn):
+        vids = np.ascontiguousarray(vids, dtype=np.int32); vn = f64(vn).reshape(-1, 3); B = len(vids)
+        out = np.empty((B, forceDim))
+        check(lib().pbso_modes_project_vertices(self._h, forceDim, B, ip(vids), dp(vn), dp(out)))
+        return out
+
+    def project_dense(self, F, forceDim=None):
+        F = f64(F)
+        if F.ndim == 1:
+            F = F.reshape(-1, 1)
+        n = self.M if forceDim is None else forceDim
+        Y = np.empty((n, F.shape[1]))
+        check(lib().pbso_modes_project_dense(self._h, n, dp(F), F.shape[1], dp(Y)))
+        return Y
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pbso_modes_destroy(self._h); self._h = None
+
+    __del__ = close
+
+
+class BatchRenderer:
+    """Many independent ModalSolver step loops rendered offline and mixed."""
+
+    def __init__(self, h, a, b):
+        a = f64(a); b = f64(b)
+        self.n_obj, self.n_modes = a.shape
+        self._h = C.c_void_p()
+        check(lib().pbso_batch_create(self.n_obj, self.n_modes, h, dp(a), dp(b), C.byref(self._h)))
+
+    def set_transfer(self, trans):
+        t = f64(trans); assert t.shape == (self.n_obj, self.n_modes)
+        check(lib().pbso_batch_set_transfer(self._h, dp(t)))
+
+    def set_impulses(self, obj, buf, space):
+        obj = np.ascontiguousarray(obj, dtype=np.int32); buf = np.ascontiguousarray(buf, dtype=np.int32)
+        space = f64(space).reshape(len(obj), self.n_modes)
+        check(lib().pbso_batch_set_impulses(self._h, len(obj), ip(obj), ip(buf), dp(space)))
+
+    def render_mix(self, buf_size, n_buffers, precision=capi.PREC_F32_TILED, n_chunks=0):
+        mix = np.empty(buf_size * n_buffers)
+        check(lib().pbso_batch_render_mix(self._h, buf_size, n_buffers, precision, n_chunks, dp(mix)))
+        return mix
+
+    def render_mix_device(self, buf_size, n_buffers, d_mix_ptr, precision=capi.PREC_F32_TILED, n_chunks=0):
+        check(lib().pbso_batch_render_mix_device(self._h, buf_size, n_buffers, precision, n_chunks, C.c_void_p(d_mix_ptr)))
+
+    def render_stems(self, buf_size, n_buffers, precision=capi.PREC_F32_TILED):
+        st = np.empty((self.n_obj, buf_size * n_buffers), dtype=np.float32)
+        check(lib().pbso_batch_render_stems(self._h, buf_size, n_buffers, precision, st.ctypes.data_as(capi.c_fp)))
+        return st
+
+    def sync(self):
+        check(lib().pbso_batch_sync(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().pbso_batch_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def last_kernel_ms(self):
+        ms = C.c_float(); n = C.c_int()
+        check(lib().pbso_batch_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pbso_batch_destroy(self._h); self._h = None
+
+    __del__ = close

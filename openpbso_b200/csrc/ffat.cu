@@ -1,0 +1,440 @@
+// =============================================================================
+// ffat.cu -- FFAT cube-map set on the device + kernel K3 (transfer evaluation).
+//
+// Restates, per (mode m, listener l):   ModalSolver::computeTransfer   modal_solver.h:286-315
+//   FFAT_Map<T,3>::GetMapVal   ffat_solver.h:1180-1206
+//     -> FFAT_Map<T,1>::Intersect     :676-712   ray from listener toward centre vs bbox slabs
+//     -> FFAT_Map<T,1>::Interpolate   :736-803   texel-centre bilinear indices + weights
+//     -> GetDataQuadStride            :141-144   strides[f] + x*Ny + y
+//     -> FFAT_Solver<T,3>::Reconstruct:899-906   |psi / (k r)|
+// All geometry runs in FP64 and reproduces the reference's IEEE behaviour (explicit ternaries
+// instead of fmin/fmax so NaN/inf propagate the same way).
+//
+// HBM layout.  geom[n][32] / igeom[n][18] records (see pbso_b200.h), Psi column 0 stored twice:
+//   psi_mm [n][D]   mode-major  -- general path, one map per thread block column
+//   psi_tm [D][n]   texel-major -- used when every map shares bit-identical geometry (checked at
+//                    build time like FFAT_Map_Serialize_Double::Check, ffat_map_serialize.h:281-306):
+//                    a listener then hits the SAME four texels in every map, so the gather becomes
+//                    four fully coalesced row reads of n doubles and the geometry is solved once per
+//                    listener instead of once per (listener, mode).
+// =============================================================================
+#include "common.cuh"
+#include "fatcube_codec.h"
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <vector>
+
+using namespace pbso;
+
+namespace {
+struct HostMap {
+    double geom[32];
+    int igeom[18];
+    bool is_compressed = false;
+    std::vector<std::vector<double>> psi;     // columns
+    int modeid = 0;
+};
+}  // namespace
+
+struct pbso_ffat {
+    int device = 0;
+    std::map<int, HostMap> maps;               // keyed by modeId like LoadAll (:267-279)
+    // device mirror of ids [0, n_dense): built lazily by ensure_device()
+    bool dirty = true;
+    int n_dense = 0;                           // largest n such that ids 0..n-1 all exist
+    int D = 0;                                 // psi length when uniform, else 0
+    bool shared_geom = false;
+    double* d_geom = nullptr; int* d_igeom = nullptr;
+    double* d_psi_mm = nullptr; double* d_psi_tm = nullptr;
+    size_t* d_psi_off = nullptr;               // per-map offset into d_psi_mm
+    cudaStream_t stream = nullptr;
+    double* d_pos = nullptr; double* d_out = nullptr; size_t pos_cap = 0, out_cap = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+struct Geo {           // one map's geometry in registers / local
+    double cell, low[6][3], c1[3], blo[3], bhi[3], c3[3], k;
+    int ne[6][2], st[6];
+};
+__device__ __forceinline__ void load_geo(Geo& g, const double* __restrict__ geom, const int* __restrict__ igeom) {
+    g.cell = geom[0];
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g.low[f][d] = geom[1 + f * 3 + d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { g.c1[d] = geom[19 + d]; g.blo[d] = geom[22 + d]; g.bhi[d] = geom[25 + d]; g.c3[d] = geom[28 + d]; }
+    g.k = geom[31];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) { g.ne[f][0] = igeom[2 * f]; g.ne[f][1] = igeom[2 * f + 1]; g.st[f] = igeom[12 + f]; }
+}
+
+// Intersect + Interpolate: returns the four Psi indices, weights and r = |p - centre|.
+__device__ __forceinline__ void ffat_locate(const Geo& g, const double p[3], int idx[4], double w[4], double& r) {
+    double d[3], surf[3], t_en = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        d[i] = g.c1[i] - p[i];                                          // ffat_solver.h:681
+        const double tmin = (g.blo[i] - p[i]) / d[i];                   // :682
+        const double tmax = (g.bhi[i] - p[i]) / d[i];                   // :683
+        const double te = (tmax < tmin) ? tmax : tmin;                  // :684 std::min semantics
+        if (i == 0) t_en = te; else if (te > t_en) t_en = te;           // :685 maxCoeff
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) surf[i] = p[i] + t_en * d[i];           // :686
+    double minDist = 1.7976931348623157e308;                            // :688
+    int face = 0;
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {                                    // :689-698 strict '<', low first
+        const double a = fabs(g.blo[dd] - surf[dd]);
+        if (a < minDist) { minDist = a; face = dd * 2 + 1; }
+        const double b = fabs(g.bhi[dd] - surf[dd]);
+        if (b < minDist) { minDist = b; face = dd * 2; }
+    }
+    const int dk = face >> 1, di = (dk + 1) % 3, dj = (dk + 2) % 3;     // :699-702
+    // (Intersect's own texel index, :706-711, is not used by GetMapVal beyond the face id.)
+    const int Nx = g.ne[face][0], Ny = g.ne[face][1];
+    const double h = g.cell;
+    const double lowi = g.low[face][di], lowj = g.low[face][dj];
+    const double xf = (surf[di] - (lowi + 0.5 * h)) / h;                // :757
+    const double yf = (surf[dj] - (lowj + 0.5 * h)) / h;                // :758
+    int x = (int)floor(xf), y = (int)floor(yf), xp, yp;
+    double tx, ty;
+    if (x < 0) { x = 0; xp = 0; tx = 0; }                               // :763-776
+    else if (x < Nx - 1) { xp = x + 1; tx = xf - (double)x; }
+    else { x = Nx - 1; xp = Nx - 1; tx = 0; }
+    if (y < 0) { y = 0; yp = 0; ty = 0; }                               // :777-790
+    else if (y < Ny - 1) { yp = y + 1; ty = yf - (double)y; }
+    else { y = Ny - 1; yp = Ny - 1; ty = 0; }
+    { double t = (tx < 0.0) ? 0.0 : tx; tx = (1.0 < t) ? 1.0 : t; }     // :791 min(max(tx,0),1)
+    { double t = (ty < 0.0) ? 0.0 : ty; ty = (1.0 < t) ? 1.0 : t; }     // :792
+    const int base = g.st[face];
+    idx[0] = base + x * Ny + y;   idx[1] = base + xp * Ny + y;          // :141-144, :795-798
+    idx[2] = base + x * Ny + yp;  idx[3] = base + xp * Ny + yp;
+    w[0] = (1.0 - tx) * (1.0 - ty); w[1] = tx * (1.0 - ty);             // :799-802
+    w[2] = (1.0 - tx) * ty;         w[3] = tx * ty;
+    const double dx = p[0] - g.c3[0], dy = p[1] - g.c3[1], dz = p[2] - g.c3[2];
+    r = sqrt(dx * dx + dy * dy + dz * dz);                              // :1205 (p-_center).norm()
+}
+
+// General path: one thread per (mode, listener); per-map geometry.
+__global__ void __launch_bounds__(128)
+k_ffat_eval_general(int n_modes, int L, const double* __restrict__ geom, const int* __restrict__ igeom,
+                    const double* __restrict__ psi, const size_t* __restrict__ psi_off,
+                    const double* __restrict__ pos, double* __restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (m >= n_modes) return;
+    Geo g; load_geo(g, geom + (size_t)m * 32, igeom + (size_t)m * 18);
+    const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
+    int idx[4]; double w[4], r;
+    ffat_locate(g, p, idx, w, r);
+    const double* P = psi + psi_off[m];
+    double psi0 = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) psi0 += w[kk] * P[idx[kk]];          // :1198-1204
+    out[(size_t)l * n_modes + m] = fabs(psi0 / (g.k * r));              // :904-905 + :295 std::abs
+}
+
+// Shared-geometry path: geometry solved once per listener (thread 0 of each block -> smem), then a
+// coalesced gather over modes from the texel-major table.  k differs per mode (geom[m][31]).
+__global__ void __launch_bounds__(256)
+k_ffat_eval_shared(int n_modes, int L, const double* __restrict__ geom, const int* __restrict__ igeom,
+                   const double* __restrict__ psi_tm, int n_stride,
+                   const double* __restrict__ pos, double* __restrict__ out) {
+    __shared__ int s_idx[4];
+    __shared__ double s_w[4], s_r;
+    const int l = blockIdx.y;
+    if (threadIdx.x == 0) {
+        Geo g; load_geo(g, geom, igeom);
+        const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
+        int idx[4]; double w[4], r;
+        ffat_locate(g, p, idx, w, r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s_idx[i] = idx[i]; s_w[i] = w[i]; }
+        s_r = r;
+    }
+    __syncthreads();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_modes) return;
+    double psi0 = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) psi0 += s_w[kk] * psi_tm[(size_t)s_idx[kk] * n_stride + m];
+    const double k = geom[(size_t)m * 32 + 31];
+    out[(size_t)l * n_modes + m] = fabs(psi0 / (k * s_r));
+}
+
+// ---------------------------------------------------------------------------------------------
+static int to_host_map(const FatcubeMap& fm, HostMap& hm, std::string& err) {
+    // sizes FFAT_Map_Serialize_Double::Load relies on (ffat_map_serialize.h:181-222, 243)
+    if (fm.center1.size() != 3 || fm.bboxlow.size() != 3 || fm.bboxtop.size() != 3 || fm.center3.size() != 3) {
+        err = "center/bboxlow/bboxtop must have exactly 3 items (ffat_map_serialize.h:22-28)"; return PBSO_ERR_FORMAT; }
+    if (fm.lowcorners.size() != 6 || fm.n_elements.size() != 6 || fm.strides.size() != 6) {
+        err = "a runtime cube map needs 6 lowcorners / n_elements / strides (ffat_solver.h:689-711)"; return PBSO_ERR_FORMAT; }
+    for (auto& v : fm.lowcorners) if (v.size() < 3) { err = "lowcorners row shorter than 3"; return PBSO_ERR_FORMAT; }
+    for (auto& v : fm.n_elements) if (v.size() < 2) { err = "n_elements row shorter than 2"; return PBSO_ERR_FORMAT; }
+    if (fm.psi.empty()) { err = "psi has no column (Load reads psi().item(0), ffat_map_serialize.h:243)"; return PBSO_ERR_FORMAT; }
+    hm.geom[0] = fm.cellsize;
+    for (int f = 0; f < 6; ++f) for (int d = 0; d < 3; ++d) hm.geom[1 + 3 * f + d] = fm.lowcorners[f][d];
+    for (int d = 0; d < 3; ++d) { hm.geom[19 + d] = fm.center1[d]; hm.geom[22 + d] = fm.bboxlow[d]; hm.geom[25 + d] = fm.bboxtop[d]; hm.geom[28 + d] = fm.center3[d]; }
+    hm.geom[31] = fm.k;
+    for (int f = 0; f < 6; ++f) { hm.igeom[2 * f] = fm.n_elements[f][0]; hm.igeom[2 * f + 1] = fm.n_elements[f][1]; hm.igeom[12 + f] = fm.strides[f]; }
+    hm.is_compressed = fm.is_compressed;
+    // DESERIALIZE_EMAT (:44-53): rows = psi().item(0).item_size(); every column must have that many
+    const size_t rows = fm.psi[0].size();
+    for (auto& c : fm.psi) if (c.size() < rows) { err = "psi columns of unequal length"; return PBSO_ERR_FORMAT; }
+    hm.psi = fm.psi;
+    for (auto& c : hm.psi) c.resize(rows);
+    hm.modeid = fm.modeid;
+    // every texel index Interpolate can produce must be inside Psi
+    for (int f = 0; f < 6; ++f) {
+        long long last = (long long)hm.igeom[12 + f] + (long long)hm.igeom[2 * f] * hm.igeom[2 * f + 1];
+        if (hm.igeom[2 * f] <= 0 || hm.igeom[2 * f + 1] <= 0 || hm.igeom[12 + f] < 0 || last > (long long)rows) {
+            err = "strides/n_elements address texels outside psi"; return PBSO_ERR_FORMAT; }
+    }
+    return PBSO_OK;
+}
+
+static void from_host_map(const HostMap& hm, FatcubeMap& fm) {
+    fm.cellsize = hm.geom[0];
+    fm.lowcorners.assign(6, std::vector<double>(3));
+    fm.n_elements.assign(6, std::vector<int>(2));
+    fm.strides.resize(6);
+    for (int f = 0; f < 6; ++f) {
+        for (int d = 0; d < 3; ++d) fm.lowcorners[f][d] = hm.geom[1 + 3 * f + d];
+        fm.n_elements[f][0] = hm.igeom[2 * f]; fm.n_elements[f][1] = hm.igeom[2 * f + 1];
+        fm.strides[f] = hm.igeom[12 + f];
+    }
+    fm.center1.assign(hm.geom + 19, hm.geom + 22);
+    fm.bboxlow.assign(hm.geom + 22, hm.geom + 25);
+    fm.bboxtop.assign(hm.geom + 25, hm.geom + 28);
+    fm.center3.assign(hm.geom + 28, hm.geom + 31);
+    fm.k = hm.geom[31];
+    fm.is_compressed = hm.is_compressed;
+    fm.psi = hm.psi;
+    fm.modeid = hm.modeid;
+}
+
+static int load_one(const char* filename, HostMap& hm) {
+    std::ifstream stream(filename, std::ios::binary);
+    if (!stream) return set_error(PBSO_ERR_IO, "cannot open %s", filename);
+    std::stringstream ss; ss << stream.rdbuf();
+    const std::string buf = ss.str();
+    FatcubeMap fm; std::string err;
+    if (!fatcube_decode((const uint8_t*)buf.data(), buf.size(), fm, err))
+        return set_error(PBSO_ERR_FORMAT, "%s: %s", filename, err.c_str());
+    if (int rc = to_host_map(fm, hm, err)) return set_error(rc, "%s: %s", filename, err.c_str());
+    return PBSO_OK;
+}
+
+static void free_device(pbso_ffat* f) {
+    cudaFree(f->d_geom); cudaFree(f->d_igeom); cudaFree(f->d_psi_mm); cudaFree(f->d_psi_tm); cudaFree(f->d_psi_off);
+    f->d_geom = nullptr; f->d_igeom = nullptr; f->d_psi_mm = nullptr; f->d_psi_tm = nullptr; f->d_psi_off = nullptr;
+}
+
+static int ensure_device(pbso_ffat* f) {
+    if (!f->dirty) return PBSO_OK;
+    if (int rc = check_device()) return rc;
+    free_device(f);
+    if (!f->stream) { PBSO_CUDA(cudaGetDevice(&f->device)); PBSO_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking)); }
+    int n = 0;
+    while (f->maps.count(n)) ++n;               // ids 0..n-1 are what computeTransfer can reach
+    f->n_dense = n;
+    if (n == 0) { f->dirty = false; return PBSO_OK; }
+    std::vector<double> geom((size_t)n * 32); std::vector<int> igeom((size_t)n * 18);
+    std::vector<size_t> off(n);
+    size_t total = 0; bool uniform = true, same_geo = true;
+    const HostMap& first = f->maps.at(0);
+    for (int m = 0; m < n; ++m) {
+        const HostMap& hm = f->maps.at(m);
+        std::memcpy(&geom[(size_t)m * 32], hm.geom, sizeof(hm.geom));
+        std::memcpy(&igeom[(size_t)m * 18], hm.igeom, sizeof(hm.igeom));
+        off[m] = total; total += hm.psi[0].size();
+        if (hm.psi[0].size() != first.psi[0].size()) uniform = false;
+        // bitwise comparison of everything except k (geom[31]) -- cf. Check/MatchBits (:256-306)
+        if (std::memcmp(hm.geom, first.geom, sizeof(double) * 31) != 0 ||
+            std::memcmp(hm.igeom, first.igeom, sizeof(hm.igeom)) != 0) same_geo = false;
+    }
+    f->D = uniform ? (int)first.psi[0].size() : 0;
+    f->shared_geom = uniform && same_geo;
+    std::vector<double> psi(total);
+    for (int m = 0; m < n; ++m) { const auto& c = f->maps.at(m).psi[0]; std::memcpy(&psi[off[m]], c.data(), c.size() * sizeof(double)); }
+    PBSO_CUDA(cudaMalloc(&f->d_geom, geom.size() * sizeof(double)));
+    PBSO_CUDA(cudaMalloc(&f->d_igeom, igeom.size() * sizeof(int)));
+    PBSO_CUDA(cudaMalloc(&f->d_psi_off, off.size() * sizeof(size_t)));
+    PBSO_CUDA(cudaMalloc(&f->d_psi_mm, std::max<size_t>(total, 1) * sizeof(double)));
+    PBSO_CUDA(cudaMemcpy(f->d_geom, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice));
+    PBSO_CUDA(cudaMemcpy(f->d_igeom, igeom.data(), igeom.size() * sizeof(int), cudaMemcpyHostToDevice));
+    PBSO_CUDA(cudaMemcpy(f->d_psi_off, off.data(), off.size() * sizeof(size_t), cudaMemcpyHostToDevice));
+    PBSO_CUDA(cudaMemcpy(f->d_psi_mm, psi.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    if (f->shared_geom) {
+        const int D = f->D;
+        std::vector<double> tm((size_t)D * n);
+        for (int m = 0; m < n; ++m) { const auto& c = f->maps.at(m).psi[0]; for (int t = 0; t < D; ++t) tm[(size_t)t * n + m] = c[t]; }
+        PBSO_CUDA(cudaMalloc(&f->d_psi_tm, tm.size() * sizeof(double)));
+        PBSO_CUDA(cudaMemcpy(f->d_psi_tm, tm.data(), tm.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    f->dirty = false;
+    return PBSO_OK;
+}
+
+static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, double* d_out, cudaStream_t s) {
+    if (f->shared_geom) {
+        dim3 grid(div_up(n_modes, 256), L);
+        k_ffat_eval_shared<<<grid, 256, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_psi_tm, f->n_dense, d_pos, d_out);
+    } else {
+        dim3 grid(div_up(n_modes, 128), L);
+        k_ffat_eval_general<<<grid, 128, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_psi_mm, f->d_psi_off, d_pos, d_out);
+    }
+    PBSO_CUDA(cudaGetLastError());
+    return PBSO_OK;
+}
+
+static int check_eval_args(pbso_ffat* f, int n_modes, int L, int use_compressed) {
+    PBSO_REQUIRE(f && n_modes >= 0 && L >= 0, PBSO_ERR_INVALID, "bad argument");
+    if (int rc = ensure_device(f)) return rc;
+    if (n_modes > f->n_dense)
+        return set_error(PBSO_ERR_RANGE, "mode id %d has no FFAT map (_ffat_maps->at(ii), modal_solver.h:296)", f->n_dense);
+    for (int m = 0; m < n_modes; ++m) {
+        const HostMap& hm = f->maps.at(m);
+        // GetMapVal(pos, getCompressed): asserts _is_compressed when asked for compressed values
+        // (ffat_solver.h:1183-1186); a compressed file leaves _Psi empty (ffat_map_serialize.h:238-252)
+        if ((use_compressed != 0) != hm.is_compressed)
+            return set_error(PBSO_ERR_UNSUPPORTED,
+                             "map %d: is_compressed=%d but use_compressed=%d (the reference reads an empty matrix here)",
+                             m, (int)hm.is_compressed, use_compressed);
+    }
+    return PBSO_OK;
+}
+
+extern "C" {
+
+int pbso_ffat_load_dir(const char* dirname, pbso_ffat** out) {
+    PBSO_REQUIRE(out && dirname, PBSO_ERR_INVALID, "null argument");
+    pbso_ffat* f = new pbso_ffat();
+    *out = f;                                    // like LoadAll: always hands back a (possibly empty) map
+    std::vector<std::string> names;
+    if (!list_dir_files(dirname, names, ".fatcube"))
+        return set_error(PBSO_ERR_IO, "cannot open directory %s", dirname);
+    for (const auto& name : names) {
+        HostMap hm;
+        if (int rc = load_one(name.c_str(), hm)) return rc;
+        f->maps[hm.modeid] = std::move(hm);      // (*map)[map_.modeId] = map_  (:276)
+    }
+    return PBSO_OK;
+}
+
+int pbso_ffat_load_file(const char* filename, pbso_ffat** out) {
+    PBSO_REQUIRE(out && filename, PBSO_ERR_INVALID, "null argument");
+    *out = nullptr;
+    HostMap hm;
+    if (int rc = load_one(filename, hm)) return rc;
+    pbso_ffat* f = new pbso_ffat();
+    f->maps[hm.modeid] = std::move(hm);
+    *out = f;
+    return PBSO_OK;
+}
+
+int pbso_ffat_create(int n_maps, const int* mode_ids, const double* geom, const int* igeom,
+                     const double* psi, int psi_len, const unsigned char* is_compressed, pbso_ffat** out) {
+    PBSO_REQUIRE(out, PBSO_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    PBSO_REQUIRE(n_maps >= 0 && (n_maps == 0 || (geom && igeom && psi && psi_len > 0)), PBSO_ERR_INVALID, "bad argument");
+    pbso_ffat* f = new pbso_ffat();
+    for (int i = 0; i < n_maps; ++i) {
+        HostMap hm;
+        std::memcpy(hm.geom, geom + (size_t)i * 32, sizeof(hm.geom));
+        std::memcpy(hm.igeom, igeom + (size_t)i * 18, sizeof(hm.igeom));
+        hm.psi.assign(1, std::vector<double>(psi + (size_t)i * psi_len, psi + (size_t)(i + 1) * psi_len));
+        hm.is_compressed = is_compressed ? is_compressed[i] != 0 : false;
+        hm.modeid = mode_ids ? mode_ids[i] : i;
+        FatcubeMap fm; from_host_map(hm, fm);
+        HostMap checked; std::string err;
+        if (int rc = to_host_map(fm, checked, err)) { delete f; return set_error(rc, "map %d: %s", i, err.c_str()); }
+        f->maps[hm.modeid] = std::move(hm);
+    }
+    *out = f;
+    return PBSO_OK;
+}
+
+int pbso_ffat_destroy(pbso_ffat* f) {
+    if (!f) return PBSO_OK;
+    if (f->stream) {
+        DeviceGuard g(f->device);
+        cudaStreamSynchronize(f->stream);
+        free_device(f); cudaFree(f->d_pos); cudaFree(f->d_out);
+        cudaStreamDestroy(f->stream);
+    }
+    delete f;
+    return PBSO_OK;
+}
+
+int pbso_ffat_num_maps(const pbso_ffat* f, int* n) {
+    PBSO_REQUIRE(f && n, PBSO_ERR_INVALID, "null argument");
+    *n = (int)f->maps.size();
+    return PBSO_OK;
+}
+
+int pbso_ffat_mode_ids(const pbso_ffat* f, int* ids) {
+    PBSO_REQUIRE(f && ids, PBSO_ERR_INVALID, "null argument");
+    int i = 0;
+    for (auto& kv : f->maps) ids[i++] = kv.first;
+    return PBSO_OK;
+}
+
+int pbso_ffat_get_map(const pbso_ffat* f, int mode_id, double* geom32, int* igeom18, int* psi_len,
+                      int* psi_cols, int* is_compressed, double* psi) {
+    PBSO_REQUIRE(f, PBSO_ERR_INVALID, "null handle");
+    auto it = f->maps.find(mode_id);
+    if (it == f->maps.end()) return set_error(PBSO_ERR_RANGE, "no map with mode id %d", mode_id);
+    const HostMap& hm = it->second;
+    if (geom32) std::memcpy(geom32, hm.geom, sizeof(hm.geom));
+    if (igeom18) std::memcpy(igeom18, hm.igeom, sizeof(hm.igeom));
+    if (psi_len) *psi_len = (int)hm.psi[0].size();
+    if (psi_cols) *psi_cols = (int)hm.psi.size();
+    if (is_compressed) *is_compressed = hm.is_compressed;
+    if (psi) for (size_t c = 0; c < hm.psi.size(); ++c) std::memcpy(psi + c * hm.psi[0].size(), hm.psi[c].data(), hm.psi[0].size() * sizeof(double));
+    return PBSO_OK;
+}
+
+int pbso_ffat_save_file(const pbso_ffat* f, int mode_id, const char* filename) {
+    PBSO_REQUIRE(f && filename, PBSO_ERR_INVALID, "null argument");
+    auto it = f->maps.find(mode_id);
+    if (it == f->maps.end()) return set_error(PBSO_ERR_RANGE, "no map with mode id %d", mode_id);
+    FatcubeMap fm; from_host_map(it->second, fm);
+    std::string bytes; fatcube_encode(fm, bytes);
+    std::ofstream stream(filename, std::ios::binary);
+    if (!stream) return set_error(PBSO_ERR_IO, "cannot open %s for writing", filename);
+    stream.write(bytes.data(), (std::streamsize)bytes.size());
+    return stream.good() ? PBSO_OK : set_error(PBSO_ERR_IO, "short write to %s", filename);
+}
+
+int pbso_ffat_eval(const pbso_ffat* fc, int n_modes, const double* pos, int L, int use_compressed, double* out) {
+    pbso_ffat* f = const_cast<pbso_ffat*>(fc);
+    if (int rc = check_eval_args(f, n_modes, L, use_compressed)) return rc;
+    PBSO_REQUIRE(pos && out, PBSO_ERR_INVALID, "null argument");
+    if (n_modes == 0 || L == 0) return PBSO_OK;
+    DeviceGuard g(f->device);
+    const size_t np = (size_t)3 * L, no = (size_t)L * n_modes;
+    if (np > f->pos_cap) { cudaFree(f->d_pos); PBSO_CUDA(cudaMalloc(&f->d_pos, np * sizeof(double))); f->pos_cap = np; }
+    if (no > f->out_cap) { cudaFree(f->d_out); PBSO_CUDA(cudaMalloc(&f->d_out, no * sizeof(double))); f->out_cap = no; }
+    PBSO_CUDA(cudaMemcpyAsync(f->d_pos, pos, np * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    if (int rc = launch_eval(f, n_modes, f->d_pos, L, f->d_out, f->stream)) return rc;
+    PBSO_CUDA(cudaMemcpyAsync(out, f->d_out, no * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    PBSO_CUDA(cudaStreamSynchronize(f->stream));
+    return PBSO_OK;
+}
+
+int pbso_ffat_eval_device(const pbso_ffat* fc, int n_modes, const double* d_pos, int L, double* d_out, void* cuda_stream) {
+    pbso_ffat* f = const_cast<pbso_ffat*>(fc);
+    if (int rc = check_eval_args(f, n_modes, L, 0)) return rc;
+    PBSO_REQUIRE(d_pos && d_out, PBSO_ERR_INVALID, "null argument");
+    if (n_modes == 0 || L == 0) return PBSO_OK;
+    DeviceGuard g(f->device);
+    return launch_eval(f, n_modes, d_pos, L, d_out, cuda_stream ? (cudaStream_t)cuda_stream : f->stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,326 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200: -m gpu.
+
+Tolerance (BASELINE.json north_star): waveform rel-L2 <= 1e-5 and max-abs <= 1e-6 of full scale.
+FP64 kernels are held to far tighter bounds; they restate the reference's own arithmetic."""
+import os
+import numpy as np
+import pytest
+from openpbso_b200 import synth
+from conftest import assert_waveform_parity, waveform_errors
+
+pytestmark = pytest.mark.gpu
+H = synth.H
+
+
+def test_native_library_is_loaded(pbso):
+    assert pbso.device_count() >= 1
+    info = pbso.device_info()
+    assert info["cc"][0] == 10, info          # Blackwell
+    maps = open("/proc/self/maps").read()
+    assert "libpbso_b200.so" in maps
+
+
+# --------------------------------------------------------------------------- K2 / Step
+@pytest.mark.parametrize("material", ["low_damping", "high_damping"])
+def test_coefficients(pbso, orc, material):
+    mat = synth.MATERIALS[material]
+    f = synth.mode_frequencies(1024, 7)
+    w2 = synth.omega_squared(f, mat["density"])
+    it = pbso.ModalIntegrator.Build(mat["density"], w2, mat["alpha"], mat["beta"], H, 1000)
+    assert it.N == 1000                                    # Build(..., N) culls (modal_integrator.h:53-57)
+    a, b = orc.build_ab(mat["density"], w2, mat["alpha"], mat["beta"], 1000)
+    c1, c2, c3 = orc.coeffs(H, a, b)
+    g1, g2, g3 = it.coeffs()
+    assert np.allclose(g1, c1, rtol=1e-14) and np.allclose(g2, c2, rtol=1e-14) and np.allclose(g3, c3, rtol=1e-12)
+
+
+def test_build_rejects_bad_N(pbso):
+    with pytest.raises(pbso.PbsoError) as e:
+        pbso.ModalIntegrator.Build(1.0, np.ones(4), 1.0, 1e-7, H, 5)
+    assert e.value.code == 1
+
+
+def test_step_sequence(pbso, orc):
+    mat = synth.MATERIALS["low_damping"]
+    f = synth.mode_frequencies(300, 17)
+    a, b = synth.ab_from_material(f, mat)
+    it = pbso.ModalIntegrator(300, H, a, b); ref = orc.Integrator(H, a, b)
+    rng = np.random.default_rng(1)
+    for k in range(200):
+        Q = rng.standard_normal(300) if k % 5 == 0 else None
+        g = it.Step(Q); r = ref.step(Q)
+        assert np.max(np.abs(g - r)) <= 1e-10 * np.max(np.abs(r)), k
+    q1, q2 = it.get_state(); r1, r2 = ref.state()
+    assert np.allclose(q1, r1, rtol=0, atol=1e-10 * np.max(np.abs(r1)))
+    assert np.allclose(q2, r2, rtol=0, atol=1e-10 * np.max(np.abs(r2)))
+    with pytest.raises(pbso.PbsoError):
+        it.Step(np.ones(299))                              # "input force incorrect dimension" (:108)
+
+
+def test_state_roundtrip_continues_render(pbso, orc):
+    """get_state/set_state (checkpoint of the 3-slot ring): a restored handle continues identically."""
+    f = synth.mode_frequencies(70, 3); a, b = synth.ab_from_material(f, synth.MATERIALS["high_damping"])
+    A = pbso.ModalIntegrator(70, H, a, b); B = pbso.ModalIntegrator(70, H, a, b)
+    sp = np.random.default_rng(0).standard_normal(70); tm = np.zeros(256); tm[0] = 1
+    A.render_buffer(sp, tm)
+    B.set_state(*A.get_state())
+    ya, _ = A.render_buffer(np.zeros(70), np.zeros(256)); yb, _ = B.render_buffer(np.zeros(70), np.zeros(256))
+    assert np.array_equal(ya, yb)
+
+
+# --------------------------------------------------------------------------- K1 per buffer
+def test_cfg1_golden_waveform(pbso, golden_dir):
+    """ball.obj vertex 0, 64 modes, FFAT transfer, one PointForce, 173 x 256 samples."""
+    g = np.load(os.path.join(golden_dir, "cfg1_ball.npz"))
+    mat = synth.MATERIALS["low_damping"]
+    freqs = synth.mode_frequencies(64, 1001)
+    it = pbso.ModalIntegrator.Build(mat["density"], synth.omega_squared(freqs, mat["density"]), mat["alpha"], mat["beta"], H)
+    # projection (K4 sparse) and transfer (K3) from the committed inputs
+    K = 3 * int(g["n_vertices"])
+    U = np.zeros((64, K)); U[:, :3] = g["u_vid"]
+    space = pbso.ModeShapes(U).GetModalForceVertex(64, int(g["vid"]), g["vn"])
+    assert np.allclose(space, g["space"], rtol=1e-13)
+    trans = pbso.FFATMaps.from_dicts(synth.ffat_maps(freqs, 2000)).computeTransfer(g["listener"])[0]
+    assert np.allclose(trans, g["trans"], rtol=1e-12)
+    it.set_transfer(trans)
+    ys = []
+    for bi in range(173):
+        tm = np.zeros(256)
+        sp = np.zeros(64)
+        if bi == 0:
+            tm[0] = 1.0; sp = space * g["scale"]
+        y, _ = it.render_buffer(sp, tm)
+        ys.append(y[0])
+    rel, mx = assert_waveform_parity(np.concatenate(ys), g["y"], rel=1e-9, mx=1e-9)
+
+
+def test_force_script_buffers(pbso, orc, golden_dir):
+    """Every buffer the oracle's force state machine produces (point, overlapping gaussian, clear, sustained
+    AR start/update/end, transfer swap, unit transfer) re-rendered by K1 from the same (space, time)."""
+    g = np.load(os.path.join(golden_dir, "script_forces.npz"))
+    a, b, spaces, trans = g["a"], g["b"], g["spaces"], g["trans"]
+    N = len(a)
+    s = orc.Solver(orc.Integrator(H, a, b), 256)
+    it = pbso.ModalIntegrator(N, H, a, b)
+    n_out = 0
+    for kind, arg in zip(g["kinds"], g["args"]):
+        kind = str(kind); arg = int(arg)
+        if kind == "point": s.enqueue_force(spaces[arg], orc.POINT)
+        elif kind == "gauss": s.enqueue_force(spaces[arg], orc.GAUSSIAN, width_us=900.0)
+        elif kind == "clear": s.enqueue_force(spaces[0], orc.POINT, flags=orc.F_CLEAR)
+        elif kind == "ar_start": s.enqueue_force(spaces[arg], orc.AR, flags=orc.F_SUSTAIN_START)
+        elif kind == "ar_data": s.enqueue_force(spaces[arg], orc.AR)
+        elif kind == "ar_end": s.enqueue_force(spaces[arg], orc.AR, flags=orc.F_SUSTAIN_END)
+        elif kind == "arprm": s.enqueue_arprm(0.7, 0.2, 0.002, 0.1)
+        elif kind == "trans": s.enqueue_trans(trans[arg])
+        elif kind == "unit_transfer": s.set_use_transfer(False)
+        elif kind == "use_transfer": s.set_use_transfer(True)
+        r = s.step()
+        if r is None:
+            continue
+        assert np.allclose(r[0], g["y"][n_out], rtol=1e-9, atol=1e-9 * np.max(np.abs(g["y"])))   # golden fixture
+        sp, tm = s.last_force()
+        it.set_transfer(s.latest_transfer())
+        y, qn = it.render_buffer(sp, tm)
+        full = max(np.max(np.abs(r[0])), 1e-300)
+        assert np.max(np.abs(y[0] - r[0])) <= 1e-9 * max(full, np.max(np.abs(g["y"])) * 1e-3), (kind, n_out)
+        assert np.allclose(qn, r[1], rtol=1e-9, atol=1e-9 * np.max(r[1]) + 1e-300)
+        n_out += 1
+    assert n_out == len(g["y"]) == 22
+
+
+@pytest.mark.parametrize("N,T", [(1, 1), (31, 17), (256, 256), (1000, 513), (2048, 256)])
+def test_render_buffer_shapes(pbso, orc, N, T):
+    """Ragged sizes: N not a multiple of the block, T not a multiple of the 32-sample tile (incl. the
+    reference default FRAMES_PER_BUFFER = 513), n_transfer < N (q.head(n).dot, modal_solver.h:268)."""
+    f = synth.mode_frequencies(N, N + T); a, b = synth.ab_from_material(f, synth.MATERIALS["high_damping"])
+    rng = np.random.default_rng(N)
+    it = pbso.ModalIntegrator(N, H, a, b); ref = orc.Integrator(H, a, b)
+    nt = max(1, N - 3)
+    tr = np.abs(rng.standard_normal(nt)) + 0.1
+    it.set_transfer(tr)
+    for rep in range(3):
+        sp = rng.standard_normal(N); tm = rng.standard_normal(T)
+        y, qn = it.render_buffer(sp, tm)
+        q = np.array([ref.step(sp * tm[i]) for i in range(T)])
+        yr = q[:, :nt] @ tr
+        assert np.max(np.abs(y[0] - yr)) <= 1e-9 * np.max(np.abs(yr))
+        assert np.allclose(qn, np.sqrt((q * q).sum(0)), rtol=1e-9)
+
+
+def test_render_buffer_many_listeners(pbso, orc):
+    """cfg4 shape: 64 listeners share one IIR pass: y_l = sum_m T[l][m] q_m."""
+    N, L, T = 1024, 64, 256
+    f = synth.mode_frequencies(N, 1004); a, b = synth.ab_from_material(f, synth.MATERIALS["low_damping"])
+    rng = np.random.default_rng(4)
+    tr = np.abs(rng.standard_normal((L, N))) + 0.1
+    it = pbso.ModalIntegrator(N, H, a, b); ref = orc.Integrator(H, a, b)
+    it.set_transfer(tr, L)
+    for rep in range(2):
+        sp = rng.standard_normal(N); tm = np.zeros(T); tm[0] = 1.0 if rep == 0 else 0.0
+        y, _ = it.render_buffer(sp, tm)
+        q = np.array([ref.step(sp * tm[i]) for i in range(T)])
+        yr = (q @ tr.T).T
+        assert y.shape == (L, T)
+        assert np.max(np.abs(y - yr)) <= 1e-9 * np.max(np.abs(yr))
+
+
+# --------------------------------------------------------------------------- K3 FFAT
+def test_ffat_shared_geometry(pbso, orc):
+    freqs = synth.mode_frequencies(200, 1004)
+    maps = synth.ffat_maps(freqs, 2000)
+    pos = synth.listeners(50, 12)
+    got = pbso.FFATMaps.from_dicts(maps).computeTransfer(pos)
+    ref = orc.ffat_eval(maps, pos)
+    assert got.shape == (50, 200)
+    assert np.allclose(got, ref, rtol=1e-12)
+
+
+def test_ffat_general_geometry_from_files(pbso, orc, golden_dir):
+    from oracle import fatcube
+    d = os.path.join(golden_dir, "fatcube")
+    ref_maps = fatcube.load_all(d)
+    ref_maps[1]["k"] = 0.0                                        # k = 0 on the wire: division by zero -> inf
+    fm = pbso.FFATMaps.LoadAll(d)
+    pos = np.concatenate([synth.listeners(40, 5, 4.0, 9.0), [[5.0, 0.0, 0.0], [0.0, 0.0, -7.0], [3.0, 3.0, 3.0]]])
+    got = fm.computeTransfer(pos)
+    ref = orc.ffat_eval([ref_maps[i] for i in range(3)], pos)
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    fin = np.isfinite(ref)
+    assert np.allclose(got[fin], ref[fin], rtol=1e-12)
+    with pytest.raises(pbso.PbsoError) as e:                      # _ffat_maps->at(3) throws (modal_solver.h:296)
+        fm.computeTransfer(pos, n_modes=4)
+    assert e.value.code == 5
+
+
+def test_ffat_full_size_properties(pbso):
+    """cfg4 size (1024 modes x 64 listeners): 1/r law and texel-centre identity, no oracle needed."""
+    freqs = synth.mode_frequencies(1024, 1004)
+    maps = synth.ffat_maps(freqs, 2000)
+    fm = pbso.FFATMaps.from_dicts(maps)
+    d = synth.unit_vectors(64, 3)
+    t1 = fm.computeTransfer(4.0 * d); t2 = fm.computeTransfer(8.0 * d)
+    assert np.allclose(t1, 2.0 * t2, rtol=1e-12)
+    pts = synth.texel_centres(maps[0])
+    idx = np.random.default_rng(0).integers(0, len(pts), 64)
+    t = fm.computeTransfer(3.0 * pts[idx])
+    psi = np.array([m["psi"][idx] for m in maps]).T
+    k = np.array([m["k"] for m in maps])
+    r = np.linalg.norm(3.0 * pts[idx], axis=1)[:, None]
+    assert np.allclose(t, np.abs(psi / (k * r)), rtol=1e-12)
+
+
+# --------------------------------------------------------------------------- K4 projection
+def test_projection_sparse_and_dense(pbso, orc):
+    M, V = 96, 500
+    U = synth.mode_shapes(M, 3 * V, 1003)
+    md = pbso.ModeShapes(U)
+    rng = np.random.default_rng(2)
+    vn = synth.unit_vectors(1, 8)[0]
+    assert np.allclose(md.GetModalForceVertex(M, 123, vn), orc.project_vertex(U, 123, vn), rtol=1e-13)
+    assert np.allclose(md.GetModalForceVertex(40, 499, vn), orc.project_vertex(U, 499, vn, 40), rtol=1e-13)
+    vids = [3, 77, 499]; bc = np.array([0.5, 0.25, 0.25])
+    assert np.allclose(md.GetModalForceFace(M, vids, bc, vn), orc.project_face(U, vids, bc, vn), rtol=1e-12, atol=1e-14)
+    vs = rng.integers(0, V, 33); vns = synth.unit_vectors(33, 9)
+    got = md.project_vertices(M, vs, vns)
+    ref = np.array([orc.project_vertex(U, v, n) for v, n in zip(vs, vns)])
+    assert np.allclose(got, ref, rtol=1e-13)
+    f = rng.standard_normal(3 * V)
+    assert np.allclose(md.project_dense(f)[:, 0], orc.project_dense(U, f.reshape(-1, 1))[:, 0], rtol=1e-11, atol=1e-11)
+    F = rng.standard_normal((3 * V, 9))
+    Y = md.project_dense(F); Yr = orc.project_dense(U, F)
+    assert np.max(np.linalg.norm(Y - Yr, axis=0) / np.linalg.norm(Yr, axis=0)) < 1e-12
+    for bad in (-1, V):
+        with pytest.raises(pbso.PbsoError) as e:                   # std::vector::at
+            md.GetModalForceVertex(M, bad, vn)
+        assert e.value.code == 5
+    with pytest.raises(pbso.PbsoError):
+        md.GetModalForceVertex(M + 1, 0, vn)
+
+
+def test_modes_file_roundtrip(pbso, orc, tmp_path):
+    U = synth.mode_shapes(9, 21, 5); w2 = np.linspace(1e5, 1e9, 9)
+    p = str(tmp_path / "t.modes"); orc.modes_write(p, w2, U)
+    md = pbso.ModeShapes.read(p)
+    assert (md.M, md.K) == (9, 21) and np.array_equal(md.omegaSquared(), w2)
+    vn = np.array([0.0, 1.0, 0.0])
+    assert np.array_equal(md.GetModalForceVertex(9, 2, vn), U[:, 7])
+    with pytest.raises(pbso.PbsoError) as e:
+        pbso.ModeShapes.read(str(tmp_path / "missing.modes"))
+    assert e.value.code == 3
+
+
+# --------------------------------------------------------------------------- batch renderer
+def _batch_case(n_obj, n_modes, n_buf, seed, material="low_damping", extra_events=0):
+    w = synth.batch_workload(n_obj, n_modes, n_buf, seed, material, first_second_bufs=max(1, n_buf // 2))
+    return w
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32_tiled"])
+@pytest.mark.parametrize("n_obj,n_modes,n_buf,material", [(5, 80, 24, "low_damping"), (3, 300, 12, "high_damping"), (2, 16, 40, "low_damping")])
+def test_batch_mix_vs_oracle(pbso, orc, precision, n_obj, n_modes, n_buf, material):
+    w = _batch_case(n_obj, n_modes, n_buf, 100 + n_modes, material)
+    ref = orc.batch_render(H, w["a"], w["b"], w["space"], w["trans"], w["imp_buf"], 256, n_buf)
+    br = pbso.BatchRenderer(H, w["a"], w["b"])
+    br.set_transfer(w["trans"])
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], w["space"])
+    prec = pbso.PREC_F64 if precision == "f64" else pbso.PREC_F32_TILED
+    mix = br.render_mix(256, n_buf, prec)
+    if precision == "f64":
+        assert_waveform_parity(mix, ref, rel=1e-10, mx=1e-10)
+    else:
+        rel, mx = assert_waveform_parity(mix, ref)
+        print("f32_tiled: rel-L2 %.2e max-abs %.2e" % (rel, mx))
+
+
+def test_batch_multiple_events_and_stems(pbso, orc):
+    """Two impulses on one object in different buffers; stems sum to the mix."""
+    n_obj, n_modes, n_buf = 4, 64, 30
+    w = _batch_case(n_obj, n_modes, n_buf, 9)
+    rng = np.random.default_rng(9)
+    obj = np.array([0, 1, 2, 3, 1, 3]); buf = np.array([2, 0, 5, 7, 9, 8])
+    space = rng.standard_normal((6, n_modes))
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"]); br.set_impulses(obj, buf, space)
+    ref = np.zeros(n_buf * 256)
+    for o in range(n_obj):
+        s = orc.Solver(orc.Integrator(H, w["a"][o], w["b"][o]), 256)
+        s.enqueue_trans(w["trans"][o])
+        for bi in range(n_buf):
+            for e in np.nonzero((obj == o) & (buf == bi))[0]:
+                s.enqueue_force(space[e])
+            ref[bi * 256:(bi + 1) * 256] += s.step()[0]
+    for prec, tol in ((pbso.PREC_F64, 1e-10), (pbso.PREC_F32_TILED, None)):
+        mix = br.render_mix(256, n_buf, prec)
+        if tol: assert_waveform_parity(mix, ref, rel=tol, mx=tol)
+        else: assert_waveform_parity(mix, ref)
+        stems = br.render_stems(256, n_buf, prec)
+        assert_waveform_parity(stems.astype(np.float64).sum(0), ref, rel=1e-5, mx=2e-6)
+    with pytest.raises(pbso.PbsoError):                      # one message per object per buffer (modal_solver.h:184)
+        br.set_impulses([0, 0], [3, 3], space[:2])
+    with pytest.raises(pbso.PbsoError):
+        br.set_impulses([9], [0], space[:1])
+
+
+def test_batch_full_size_slice_f32_vs_f64(pbso):
+    """cfg5 slice at full length (512 modes x 1723 buffers = 10 s): FP32 pole-power tiles against the FP64
+    direct-form kernel, plus linearity and time-shift invariance (size-independent properties)."""
+    n_obj, n_modes, n_buf = 48, 512, 1723
+    w = synth.batch_workload(n_obj, n_modes, n_buf, 1005)
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"])
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], w["space"])
+    y64 = br.render_mix(256, n_buf, pbso.PREC_F64)
+    y32 = br.render_mix(256, n_buf, pbso.PREC_F32_TILED)
+    rel, mx = assert_waveform_parity(y32, y64)
+    print("cfg5 slice: f32_tiled vs f64 rel-L2 %.2e max-abs %.2e" % (rel, mx))
+    # late-time accuracy: error relative to the local envelope in the last second stays small
+    tail = slice(-44100, None)
+    assert np.linalg.norm(y32[tail] - y64[tail]) <= 1e-5 * np.linalg.norm(y64[tail])
+    # linearity
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], 2.0 * w["space"])
+    y2 = br.render_mix(256, n_buf, pbso.PREC_F32_TILED)
+    assert np.max(np.abs(y2 - 2.0 * y32)) <= 2e-6 * np.max(np.abs(y2))
+    # time shift: all impulses 5 buffers later -> same waveform delayed by 5*256 samples
+    br.set_impulses(np.arange(n_obj), w["imp_buf"] + 5, w["space"])
+    ys = br.render_mix(256, n_buf, pbso.PREC_F32_TILED)
+    assert np.max(np.abs(ys[5 * 256:] - y32[:-5 * 256])) <= 2e-6 * np.max(np.abs(y32))
+    assert not ys[:5 * 256 + int(w["imp_buf"].min()) * 256].any()

