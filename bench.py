@@ -319,7 +319,7 @@ def run_ours(args):
     info = pbso.device_info()
     k_ms = kms.item()
     achieved = (float(n_local) * args.modes * n_samples) * FLOP_PER_MODE_SAMPLE / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp32_fma", "kernel": "k_batch_pow<4>" if prec == pbso.PREC_F32_TILED else "k_batch_f64",
+    roofline = {"bound": "fp32_fma", "kernel": "k_batch_pow_g<16,16,2,ffma2>" if prec == pbso.PREC_F32_TILED else "k_batch_f64",
                 "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 "traffic": None, "kernel_ms": k_ms,
                 "peak_source": "FMA micro-benchmark in this run (pbso_measure_fma_peak; MEASURED_PEAKS.json has no FP32 figure)",

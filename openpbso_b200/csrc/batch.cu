@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -266,6 +267,169 @@ k_batch_pow(int n_modes, int slabs, int n_buf,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Generalised pole-power kernel (BUF = 256): WARPS x MB modes per CTA, JJ sample offsets per lane
+// (tile length L = 32 JJ, TT = 256 / L tiles per buffer).  F2 packs sample offsets (j, j+32) into
+// fma.rn.f32x2 (SASS FFMA2) with the tile-start state as the broadcast scalar operand.
+// Shared-memory wavefronts per FMA fall as 1/JJ (each broadcast state word feeds JJ FMAs per lane);
+// table registers grow as 2 JJ MB, which is what bounds JJ.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long p, float v) {
+    unsigned long long vv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(p), "l"(vv));
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+template <int WARPS, int MB, int JJ, bool F2>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_batch_pow_g(int n_modes, int slabs, int n_buf,
+              const double* __restrict__ lneps, const double* __restrict__ theta,
+              const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
+              const int* __restrict__ ev_off, const int* __restrict__ ev_buf, const double* __restrict__ ev_space,
+              double* __restrict__ mix, float* __restrict__ stems) {
+    constexpr int BUF = 256, L = 32 * JJ, TT = BUF / L, SLAB = WARPS * MB, NT = WARPS * 32;
+    static_assert(BUF % L == 0 && (JJ % 2 == 0) && MB <= 32, "bad tile configuration");
+    __shared__ __align__(16) float sV[WARPS][MB][2 * TT];
+    __shared__ __align__(16) float sY[2][WARPS][BUF];
+    const int obj = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m_base = slab * SLAB + warp * MB;
+    const size_t obase = (size_t)obj * n_modes;
+
+    float A[MB][JJ], B[MB][JJ];
+#pragma unroll
+    for (int i = 0; i < MB; ++i) {
+        const int m = m_base + i;
+        if (m < n_modes) {
+            const double le = lneps[obase + m], th = theta[obase + m], T = trans[obase + m];
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                const double j = (double)(lane + 32 * jj);
+                double s, c; sincos(j * th, &s, &c);
+                const double e = T * exp(j * le);
+                A[i][jj] = (float)(e * s); B[i][jj] = (float)(e * c);
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) A[i][jj] = B[i][jj] = 0.f;
+        }
+    }
+    unsigned long long A2[MB][JJ / 2], B2[MB][JJ / 2];
+    if (F2) {
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+            for (int p = 0; p < JJ / 2; ++p) { A2[i][p] = pack2(A[i][2 * p], A[i][2 * p + 1]); B2[i][p] = pack2(B[i][2 * p], B[i][2 * p + 1]); }
+    }
+    const int my_m = m_base + (lane % MB);
+    const bool owner = lane < MB && my_m < n_modes;
+    double vr = 0.0, vi = 0.0, Wr = 0.0, Wi = 0.0, injr = 0.0, inji = 0.0;
+    if (owner) {
+        const double le = lneps[obase + my_m], th = theta[obase + my_m];
+        double s, c; sincos((double)L * th, &s, &c);
+        const double e = exp((double)L * le);
+        Wr = e * c; Wi = e * s;
+        inji = c3a[obase + my_m];
+        injr = inji * cota[obase + my_m];
+    }
+    int ev = ev_off[obj];
+    const int ev_end = ev_off[obj + 1];
+    int next_buf = ev < ev_end ? ev_buf[ev] : INT_MAX;
+
+    for (int bi = 0; bi < n_buf; ++bi) {
+        if (bi == next_buf) {
+            if (owner) {
+                const double sp = ev_space[(size_t)ev * n_modes + my_m];
+                vr = fma(injr, sp, vr); vi = fma(inji, sp, vi);
+            }
+            ++ev; next_buf = ev < ev_end ? ev_buf[ev] : INT_MAX;
+        }
+        if (lane < MB) {
+            float st[2 * TT];
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                st[t] = (float)vr; st[TT + t] = (float)vi;
+                const double nr = vr * Wr - vi * Wi;
+                vi = vr * Wi + vi * Wr; vr = nr;
+            }
+            if (2 * TT == 4) *reinterpret_cast<float4*>(&sV[warp][lane][0]) = make_float4(st[0], st[1], st[2], st[3]);
+            else {
+#pragma unroll
+                for (int k = 0; k < 2 * TT; ++k) sV[warp][lane][k] = st[k];
+            }
+        }
+        __syncwarp();
+        float acc[TT][JJ];
+        unsigned long long acc2[TT][JJ / 2];
+#pragma unroll
+        for (int t = 0; t < TT; ++t) {
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) acc[t][jj] = 0.f;
+#pragma unroll
+            for (int p = 0; p < JJ / 2; ++p) acc2[t][p] = 0ull;
+        }
+#pragma unroll
+        for (int i = 0; i < MB; ++i) {
+            float st[2 * TT];
+            if (2 * TT == 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(&sV[warp][i][0]);
+                st[0] = v4.x; st[1] = v4.y; st[2 % (2 * TT)] = v4.z; st[3 % (2 * TT)] = v4.w;
+            } else if (2 * TT == 8) {
+                const float4 v4 = *reinterpret_cast<const float4*>(&sV[warp][i][0]);
+                const float4 w4 = *reinterpret_cast<const float4*>(&sV[warp][i][4]);
+                st[0] = v4.x; st[1] = v4.y; st[2] = v4.z; st[3] = v4.w;
+                st[4 % (2 * TT)] = w4.x; st[5 % (2 * TT)] = w4.y; st[6 % (2 * TT)] = w4.z; st[7 % (2 * TT)] = w4.w;
+            } else {
+                const float2 v2 = *reinterpret_cast<const float2*>(&sV[warp][i][0]);
+                st[0] = v2.x; st[1 % (2 * TT)] = v2.y;
+            }
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                if (F2) {
+#pragma unroll
+                    for (int p = 0; p < JJ / 2; ++p) { ffma2(acc2[t][p], A2[i][p], st[t]); ffma2(acc2[t][p], B2[i][p], st[TT + t]); }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < JJ; ++jj) {
+                        acc[t][jj] = fmaf(st[t], A[i][jj], acc[t][jj]);
+                        acc[t][jj] = fmaf(st[TT + t], B[i][jj], acc[t][jj]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        float* yb = &sY[bi & 1][warp][0];
+#pragma unroll
+        for (int t = 0; t < TT; ++t) {
+            if (F2) {
+#pragma unroll
+                for (int p = 0; p < JJ / 2; ++p) unpack2(acc2[t][p], acc[t][2 * p], acc[t][2 * p + 1]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) yb[t * L + 32 * jj + lane] = acc[t][jj];
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < BUF; o += NT) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) s += sY[bi & 1][w][o];
+            const size_t i = (size_t)bi * BUF + o;
+            if (mix) atomicAdd(&mix[i], (double)s);
+            if (stems) {
+                if (slabs == 1) stems[(size_t)obj * n_buf * BUF + i] = s;
+                else atomicAdd(&stems[(size_t)obj * n_buf * BUF + i], s);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precision, double* d_mix, float* d_stems) {
     PBSO_REQUIRE(buf_size > 0 && n_buffers > 0, PBSO_ERR_INVALID, "buf_size and n_buffers must be > 0");
@@ -280,7 +444,19 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
 #define PBSO_LAUNCH_POW(TT)                                                                              \
         k_batch_pow<TT><<<grid, FB_WARPS * 32, 0, bt->stream>>>(bt->n_modes, slabs, n_buffers, bt->lneps(), \
             bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, d_mix, d_stems)
-        if (buf_size == 64) PBSO_LAUNCH_POW(1);
+        // default: 16 warps x 16 modes, 64-sample tiles, packed FFMA2 (best of the measured variants, see profiles/)
+        static const int variant = getenv("PBSO_POW_VARIANT") ? atoi(getenv("PBSO_POW_VARIANT")) : 1;
+#define PBSO_LAUNCH_G(W, MB, JJ, F2)                                                                       \
+        do { const int sl = div_up(bt->n_modes, (W) * (MB));                                               \
+             k_batch_pow_g<W, MB, JJ, F2><<<bt->n_obj * sl, (W) * 32, 0, bt->stream>>>(bt->n_modes, sl, n_buffers, \
+                 bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf,  \
+                 bt->d_ev_space, d_mix, d_stems); } while (0)
+        if (buf_size == 256 && variant == 1) PBSO_LAUNCH_G(16, 16, 2, true);
+        else if (buf_size == 256 && variant == 2) PBSO_LAUNCH_G(8, 16, 4, false);
+        else if (buf_size == 256 && variant == 3) PBSO_LAUNCH_G(8, 16, 4, true);
+        else if (buf_size == 256 && variant == 4) PBSO_LAUNCH_G(16, 8, 4, true);
+        else if (buf_size == 256 && variant == 5) PBSO_LAUNCH_G(8, 8, 8, true);
+        else if (buf_size == 64) PBSO_LAUNCH_POW(1);
         else if (buf_size == 128) PBSO_LAUNCH_POW(2);
         else if (buf_size == 256) PBSO_LAUNCH_POW(4);
         else return set_error(PBSO_ERR_UNSUPPORTED, "PBSO_PREC_F32_TILED needs buf_size in {64,128,256}; got %d (use PBSO_PREC_F64)", buf_size);

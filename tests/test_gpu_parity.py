@@ -184,7 +184,7 @@ def test_ffat_general_geometry_from_files(pbso, orc, golden_dir):
     fm = pbso.FFATMaps.LoadAll(d)
     pos = np.concatenate([synth.listeners(40, 5, 4.0, 9.0), [[5.0, 0.0, 0.0], [0.0, 0.0, -7.0], [3.0, 3.0, 3.0]]])
     got = fm.computeTransfer(pos)
-    ref = orc.ffat_eval([ref_maps[i] for i in range(3)], pos)
+    ref = np.concatenate([orc.ffat_eval([ref_maps[i]], pos) for i in range(3)], axis=1)   # maps differ in size
     assert np.array_equal(np.isinf(got), np.isinf(ref))
     fin = np.isfinite(ref)
     assert np.allclose(got[fin], ref[fin], rtol=1e-12)
