@@ -52,10 +52,8 @@ def parse():
 
 
 def shard(n_obj, world, rank):
-    """Contiguous block of objects for `rank`."""
-    per = (n_obj + world - 1) // world
-    lo = min(rank * per, n_obj)
-    return lo, min(lo + per, n_obj)
+    from openpbso_b200.shard import shard_range
+    return shard_range(n_obj, world, rank)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -128,7 +126,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx = gpu_index; self.rows = []; self.p = None
+        self.idx = gpu_index; self.rows = []; self.p = None; self.t_begin = None; self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -141,7 +145,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.p:
@@ -150,7 +154,11 @@ class ClockSampler:
         try: self.p.wait(timeout=2)
         except Exception: self.p.kill()
         sm = []; mx = None; reasons = set(); power = []
-        for r in self.rows:
+        # samples taken inside the timed region; if the region was shorter than the sampling period, the
+        # samples taken under the same load during warm-up are used and the fact is recorded
+        inside = [r for (t, r) in self.rows if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t)]
+        window = "timed region" if inside else "warm-up + timed region (timed region shorter than the sampling period)"
+        for r in (inside or [r for (_, r) in self.rows]):
             try:
                 sm.append(float(r[1])); mx = float(r[2]); power.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -159,7 +167,7 @@ class ClockSampler:
             except (ValueError, IndexError):
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+                "samples": len(sm), "power_w_max": max(power) if power else None, "window": window}
 
 
 def measured_peaks():
@@ -217,6 +225,7 @@ def run_ours(args):
         dist.barrier()
     import openpbso_b200 as pbso
     from openpbso_b200 import synth
+    from openpbso_b200.shard import reduce_mix
     pbso.set_device(local)
     prec = pbso.PREC_F32_TILED if args.precision == "f32_tiled" else pbso.PREC_F64
 
@@ -246,22 +255,23 @@ def run_ours(args):
 
     def step_device():
         br.render_mix_device(BUF, args.buffers, mix.data_ptr(), prec)
-        if world > 1:
-            dist.reduce(mix, dst=0, op=dist.ReduceOp.SUM)
+        reduce_mix(mix, 0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local); sampler.start()          # started early: nvidia-smi needs ~0.2 s to come up
+    pbso.flush_l2(256 << 20)                                # allocates the flush scratch outside the timed region
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
     # ---- timed region: exactly K steps, device-resident inputs -----------------------------
-    sampler = ClockSampler(local); sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     barrier()
+    sampler.mark_begin()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         pbso.flush_l2(256 << 20)                       # evict L2 between timed iterations (default stream)
@@ -272,6 +282,7 @@ def run_ours(args):
         kernel_ms.append(br.last_kernel_ms()[0])       # syncs on the render kernel's own event pair
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    sampler.mark_end()
     clocks = sampler.stop()
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
