@@ -10,9 +10,9 @@
 // Parity status: the reference ships no tests or golden vectors for this path
 // (SURVEY.md section 4).  Rows marked [pinned:_ref] below are additionally
 // cross-checked in tests/test_oracle_vs_ref.py against the reference's OWN
-// headers compiled from /root/reference (oracle/build_ref.sh ->
+// headers compiled from /root/reference (oracle/Makefile target `ref` ->
 // oracle/_ref/libpbso_ref.so; Eigen is absent in the image so those headers
-// are compiled against the minimal Eigen shim of include/openpbso/Eigen).
+// are compiled against the minimal shim include/openpbso/eigen_shim/Eigen/Dense).
 // Rows without that mark are "parity unpinned": they are anchored only on
 // analytic known-answer tests (tests/test_oracle_kat.py).
 //
