@@ -40,6 +40,11 @@ enum {
     PBSO_ERR_UNSUPPORTED = 7
 };
 
+/* arithmetic selectors */
+#define PBSO_PREC_F64 0        /* FP64: the reference's arithmetic */
+#define PBSO_PREC_F32_TILED 1  /* batch renderer: FP32 pole-power tiles evaluated from an FP64 carrier */
+#define PBSO_PREC_TF32X3 2     /* batched projection: tcgen05 tensor cores, 3xTF32 split, FP32 accumulate */
+
 typedef struct pbso_integrator pbso_integrator;  /* ModalIntegrator<double> + per-buffer renderer */
 typedef struct pbso_ffat pbso_ffat;              /* std::map<int, FFAT_Map<double,3>> */
 typedef struct pbso_modes pbso_modes;            /* ModeData<double>::_modes on the device */
@@ -134,10 +139,16 @@ int pbso_modes_project_face(const pbso_modes* md, int force_dim, const int* vids
 /* Batched sparse form: B vertex impulses at once; out is B x force_dim (row per impulse). */
 int pbso_modes_project_vertices(const pbso_modes* md, int force_dim, int B, const int* vids,
                                 const double* vn, double* out);
-/* Dense form Y = U F, U[force_dim][K] and F[K][B] row-major, Y[force_dim][B] (kernel K4 for B == 1:
- * HBM-bound GEMV; K5 for B > 1: tensor-core contraction with 3xTF32 split, FP32 accumulate). */
-int pbso_modes_project_dense(const pbso_modes* md, int force_dim, const double* F, int B,
-                             double* Y);
+/* Dense form for B impulses with dense load vectors: Y[b][m] = sum_k U[m][k] F[b][k]; F is B x K (one load
+ * vector per row), Y is B x force_dim (one ForceMessage::data per row).
+ *   PBSO_PREC_F64     B == 1: HBM-bound FP64 GEMV (kernel K4); B > 1: FP64 tile GEMM -- exact-parity path
+ *   PBSO_PREC_TF32X3  kernel K5: tcgen05 tensor cores, operands split hi+lo into TF32, three MMAs per product,
+ *                     FP32 accumulation in TMEM (column rel-L2 error ~1e-6) */
+int pbso_modes_project_dense(const pbso_modes* md, int force_dim, const double* F, int B, double* Y,
+                             int precision);
+/* CUDA-event time of the kernel(s) of the last pbso_modes_project_dense call (copies excluded). */
+int pbso_modes_last_kernel_ms(const pbso_modes* md, float* ms);
+/* K5 with device-resident FP32 inputs/outputs (d_F[B][K], d_Y[B][force_dim]); enqueue only. */
 int pbso_modes_project_dense_device(const pbso_modes* md, int force_dim, const float* d_F, int B,
                                     float* d_Y, void* cuda_stream);
 
@@ -156,8 +167,6 @@ int pbso_batch_set_transfer(pbso_batch* bt, const double* trans);
  * in the same buffer are rejected with PBSO_ERR_INVALID. */
 int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const int* buf,
                             const double* space);
-#define PBSO_PREC_F64 0        /* FP64 direct form: the reference's arithmetic */
-#define PBSO_PREC_F32_TILED 1  /* FP32 coupled-form tiles re-seeded from an FP64 carrier */
 /* Render n_buffers x buf_size samples of every object from zero state and mix them down:
  * mix[i] = sum_obj y_obj[i]  (double, n_buffers*buf_size).  Runs on n_chunks independent time
  * chunks (0 = choose) whose start states come from closed-form pole powers. */

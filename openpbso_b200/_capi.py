@@ -18,7 +18,7 @@ c_ip = C.POINTER(C.c_int)
 c_vpp = C.POINTER(C.c_void_p)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_FORMAT, ERR_RANGE, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(8)
-PREC_F64, PREC_F32_TILED = 0, 1
+PREC_F64, PREC_F32_TILED, PREC_TF32X3 = 0, 1, 2
 
 
 class PbsoError(RuntimeError):
@@ -79,7 +79,8 @@ def lib():
             "pbso_modes_project_vertex": [vp, C.c_int, C.c_int, c_dp, c_dp],
             "pbso_modes_project_face": [vp, C.c_int, c_ip, c_dp, c_dp, c_dp],
             "pbso_modes_project_vertices": [vp, C.c_int, C.c_int, c_ip, c_dp, c_dp],
-            "pbso_modes_project_dense": [vp, C.c_int, c_dp, C.c_int, c_dp],
+            "pbso_modes_project_dense": [vp, C.c_int, c_dp, C.c_int, c_dp, C.c_int],
+            "pbso_modes_last_kernel_ms": [vp, c_fp],
             "pbso_modes_project_dense_device": [vp, C.c_int, vp, C.c_int, vp, vp],
             "pbso_batch_create": [C.c_int, C.c_int, C.c_double, c_dp, c_dp, c_vpp],
             "pbso_batch_destroy": [vp],

@@ -96,7 +96,11 @@ class ModalIntegrator:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().pbso_integrator_destroy(self._h); self._h = None
+            try:
+                lib().pbso_integrator_destroy(self._h)
+            except Exception:          # interpreter shutdown
+                pass
+            self._h = None
 
     __del__ = close
 
@@ -172,7 +176,11 @@ class FFATMaps:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().pbso_ffat_destroy(self._h); self._h = None
+            try:
+                lib().pbso_ffat_destroy(self._h)
+            except Exception:          # interpreter shutdown
+                pass
+            self._h = None
 
     __del__ = close
 
@@ -215,18 +223,32 @@ class ModeShapes:
         check(lib().pbso_modes_project_vertices(self._h, forceDim, B, ip(vids), dp(vn), dp(out)))
         return out
 
-    def project_dense(self, F, forceDim=None):
+    def project_dense(self, F, forceDim=None, precision=capi.PREC_F64):
+        """F: [B][K] dense load vectors (or one K-vector) -> Y [B][forceDim]."""
         F = f64(F)
         if F.ndim == 1:
-            F = F.reshape(-1, 1)
+            F = F.reshape(1, -1)
+        assert F.shape[1] == self.K
         n = self.M if forceDim is None else forceDim
-        Y = np.empty((n, F.shape[1]))
-        check(lib().pbso_modes_project_dense(self._h, n, dp(F), F.shape[1], dp(Y)))
+        Y = np.empty((F.shape[0], n))
+        check(lib().pbso_modes_project_dense(self._h, n, dp(F), F.shape[0], dp(Y), precision))
         return Y
+
+    def last_kernel_ms(self):
+        ms = C.c_float(); check(lib().pbso_modes_last_kernel_ms(self._h, C.byref(ms))); return ms.value
+
+    def project_dense_device(self, d_F_ptr, B, d_Y_ptr, forceDim=None, stream_ptr=0):
+        n = self.M if forceDim is None else forceDim
+        check(lib().pbso_modes_project_dense_device(self._h, n, C.c_void_p(d_F_ptr), B, C.c_void_p(d_Y_ptr),
+                                                    C.c_void_p(stream_ptr)))
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().pbso_modes_destroy(self._h); self._h = None
+            try:
+                lib().pbso_modes_destroy(self._h)
+            except Exception:          # interpreter shutdown
+                pass
+            self._h = None
 
     __del__ = close
 
@@ -275,6 +297,10 @@ class BatchRenderer:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().pbso_batch_destroy(self._h); self._h = None
+            try:
+                lib().pbso_batch_destroy(self._h)
+            except Exception:          # interpreter shutdown
+                pass
+            self._h = None
 
     __del__ = close

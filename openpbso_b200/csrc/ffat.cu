@@ -52,6 +52,8 @@ struct pbso_ffat {
     size_t* d_psi_off = nullptr;               // per-map offset into d_psi_mm
     cudaStream_t stream = nullptr;
     double* d_pos = nullptr; double* d_out = nullptr; size_t pos_cap = 0, out_cap = 0;
+    void* d_loc = nullptr; size_t loc_cap = 0;          // per-listener stencils (shared-geometry path)
+    int n_uncompressed = 0, n_compressed = 0;           // leading maps with is_compressed == false / true
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -139,32 +141,46 @@ k_ffat_eval_general(int n_modes, int L, const double* __restrict__ geom, const i
     out[(size_t)l * n_modes + m] = fabs(psi0 / (g.k * r));              // :904-905 + :295 std::abs
 }
 
-// Shared-geometry path: geometry solved once per listener (thread 0 of each block -> smem), then a
-// coalesced gather over modes from the texel-major table.  k differs per mode (geom[m][31]).
+// Shared-geometry path, two launches.
+//  k_ffat_locate: one thread per listener solves the ray/box intersection and the bilinear stencil ONCE
+//                 ("interpolates once per buffer per listener") -> loc[l] = {idx[4], w[4], r}
+//  k_ffat_gather: block = 256 modes x FG_LPB listeners; the stencil sits in shared memory, every thread gathers its
+//                 mode's four texels from the texel-major table -- a warp reads 32 consecutive doubles per texel
+//                 row, fully coalesced -- and writes out[l][m] coalesced.  k differs per mode (geom[m][31]).
+struct FfatLoc { int idx[4]; double w[4]; double r; };
+
+__global__ void __launch_bounds__(128)
+k_ffat_locate(int L, const double* __restrict__ geom, const int* __restrict__ igeom,
+              const double* __restrict__ pos, FfatLoc* __restrict__ loc) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    Geo g; load_geo(g, geom, igeom);
+    const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
+    FfatLoc o;
+    ffat_locate(g, p, o.idx, o.w, o.r);
+    loc[l] = o;
+}
+
+constexpr int FG_LPB = 8;
 __global__ void __launch_bounds__(256)
-k_ffat_eval_shared(int n_modes, int L, const double* __restrict__ geom, const int* __restrict__ igeom,
-                   const double* __restrict__ psi_tm, int n_stride,
-                   const double* __restrict__ pos, double* __restrict__ out) {
-    __shared__ int s_idx[4];
-    __shared__ double s_w[4], s_r;
-    const int l = blockIdx.y;
-    if (threadIdx.x == 0) {
-        Geo g; load_geo(g, geom, igeom);
-        const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
-        int idx[4]; double w[4], r;
-        ffat_locate(g, p, idx, w, r);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { s_idx[i] = idx[i]; s_w[i] = w[i]; }
-        s_r = r;
-    }
+k_ffat_gather(int n_modes, int L, const double* __restrict__ geom, const double* __restrict__ psi_tm, int n_stride,
+              const FfatLoc* __restrict__ loc, double* __restrict__ out) {
+    __shared__ FfatLoc s_loc[FG_LPB];
+    const int l0 = blockIdx.y * FG_LPB;
+    if (threadIdx.x < FG_LPB && l0 + threadIdx.x < L) s_loc[threadIdx.x] = loc[l0 + threadIdx.x];
     __syncthreads();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_modes) return;
-    double psi0 = 0.0;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) psi0 += s_w[kk] * psi_tm[(size_t)s_idx[kk] * n_stride + m];
     const double k = geom[(size_t)m * 32 + 31];
-    out[(size_t)l * n_modes + m] = fabs(psi0 / (k * s_r));
+#pragma unroll
+    for (int i = 0; i < FG_LPB; ++i) {
+        if (l0 + i >= L) break;
+        const FfatLoc& q = s_loc[i];
+        double psi0 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * psi_tm[(size_t)q.idx[kk] * n_stride + m];    // ffat_solver.h:1198-1204
+        out[(size_t)(l0 + i) * n_modes + m] = fabs(psi0 / (k * q.r));                                  // :904-905
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -277,14 +293,22 @@ static int ensure_device(pbso_ffat* f) {
         PBSO_CUDA(cudaMalloc(&f->d_psi_tm, tm.size() * sizeof(double)));
         PBSO_CUDA(cudaMemcpy(f->d_psi_tm, tm.data(), tm.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    f->n_uncompressed = 0; while (f->n_uncompressed < n && !f->maps.at(f->n_uncompressed).is_compressed) ++f->n_uncompressed;
+    f->n_compressed = 0; while (f->n_compressed < n && f->maps.at(f->n_compressed).is_compressed) ++f->n_compressed;
     f->dirty = false;
     return PBSO_OK;
 }
 
 static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, double* d_out, cudaStream_t s) {
     if (f->shared_geom) {
-        dim3 grid(div_up(n_modes, 256), L);
-        k_ffat_eval_shared<<<grid, 256, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_psi_tm, f->n_dense, d_pos, d_out);
+        if ((size_t)L > f->loc_cap) {
+            cudaFree(f->d_loc);
+            PBSO_CUDA(cudaMalloc(&f->d_loc, sizeof(FfatLoc) * (size_t)L));
+            f->loc_cap = L;
+        }
+        k_ffat_locate<<<div_up(L, 128), 128, 0, s>>>(L, f->d_geom, f->d_igeom, d_pos, (FfatLoc*)f->d_loc);
+        k_ffat_gather<<<dim3(div_up(n_modes, 256), div_up(L, FG_LPB)), 256, 0, s>>>(n_modes, L, f->d_geom, f->d_psi_tm,
+                                                                                 f->n_dense, (const FfatLoc*)f->d_loc, d_out);
     } else {
         dim3 grid(div_up(n_modes, 128), L);
         k_ffat_eval_general<<<grid, 128, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_psi_mm, f->d_psi_off, d_pos, d_out);
@@ -298,15 +322,13 @@ static int check_eval_args(pbso_ffat* f, int n_modes, int L, int use_compressed)
     if (int rc = ensure_device(f)) return rc;
     if (n_modes > f->n_dense)
         return set_error(PBSO_ERR_RANGE, "mode id %d has no FFAT map (_ffat_maps->at(ii), modal_solver.h:296)", f->n_dense);
-    for (int m = 0; m < n_modes; ++m) {
-        const HostMap& hm = f->maps.at(m);
-        // GetMapVal(pos, getCompressed): asserts _is_compressed when asked for compressed values
-        // (ffat_solver.h:1183-1186); a compressed file leaves _Psi empty (ffat_map_serialize.h:238-252)
-        if ((use_compressed != 0) != hm.is_compressed)
-            return set_error(PBSO_ERR_UNSUPPORTED,
-                             "map %d: is_compressed=%d but use_compressed=%d (the reference reads an empty matrix here)",
-                             m, (int)hm.is_compressed, use_compressed);
-    }
+    // GetMapVal(pos, getCompressed) asserts _is_compressed when asked for compressed values
+    // (ffat_solver.h:1183-1186); a compressed file leaves _Psi empty (ffat_map_serialize.h:238-252)
+    const int ok_upto = use_compressed ? f->n_compressed : f->n_uncompressed;
+    if (n_modes > ok_upto)
+        return set_error(PBSO_ERR_UNSUPPORTED,
+                         "map %d: is_compressed does not match use_compressed=%d (the reference reads an empty matrix here)",
+                         ok_upto, use_compressed);
     return PBSO_OK;
 }
 
@@ -365,7 +387,7 @@ int pbso_ffat_destroy(pbso_ffat* f) {
     if (f->stream) {
         DeviceGuard g(f->device);
         cudaStreamSynchronize(f->stream);
-        free_device(f); cudaFree(f->d_pos); cudaFree(f->d_out);
+        free_device(f); cudaFree(f->d_pos); cudaFree(f->d_out); cudaFree(f->d_loc);
         cudaStreamDestroy(f->stream);
     }
     delete f;

@@ -25,7 +25,20 @@ struct pbso_modes {
     std::vector<double> omega2;       // only when read from a .modes file
     cudaStream_t stream = nullptr;
     void* d_scratch = nullptr; size_t scratch_cap = 0;
+    // tensor-core path (project_tc.cu): TF32 hi/lo planes of U, built on first use
+    float* d_Uhi = nullptr; float* d_Ulo = nullptr;
+    float* d_Fsplit = nullptr; size_t fsplit_cap = 0;      // F_hi | F_lo planes
+    int sm_count = 148;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;                // bracket the last projection kernel(s)
 };
+
+namespace pbso {
+int tc_pitch(int K);
+int tc_split_f64(const double* d_src, int rows, int cols, float* d_hi, float* d_lo, cudaStream_t s);
+int tc_split_f32(const float* d_src, int rows, int cols, float* d_hi, float* d_lo, cudaStream_t s);
+int tc_project(const float* d_Uhi, const float* d_Ulo, int M, const float* d_Fhi, const float* d_Flo, int B, int K,
+               float* d_Y, int sm_count, cudaStream_t s);
+}
 
 // out[b][m] = sum_{j<nv} coords[b][j] * (vn[b] . U_m[3 vid[b][j] .. +2])
 // nv = 1, coords = 1 reproduces GetModalForceVertex (:276-280); nv = 3 GetModalForceFace (:245-251).
@@ -88,11 +101,11 @@ k_gemv_f64(int K, const double* __restrict__ U, const double* __restrict__ f, do
     }
 }
 
-// Y[M][B] = U[M][K] F[K][B], FP64, 64x64 tile per block, 4x4 per thread.
+// Y[B][M] = U[M][K] F[B][K]^T, FP64, 64x64 tile per block, 4x4 per thread.
 __global__ void __launch_bounds__(256)
 k_gemm_f64(int M, int K, int B, const double* __restrict__ U, const double* __restrict__ F, double* __restrict__ Y) {
     __shared__ double As[16][64 + 1];
-    __shared__ double Bs[16][64];
+    __shared__ double Bs[16][64 + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * 64, b0 = blockIdx.x * 64;
     double acc[4][4] = {};
@@ -100,8 +113,7 @@ k_gemm_f64(int M, int K, int B, const double* __restrict__ U, const double* __re
         for (int e = threadIdx.x; e < 64 * 16; e += 256) {
             const int mm = e >> 4, kk = e & 15;                 // U row-contiguous in k
             As[kk][mm] = (m0 + mm < M && k0 + kk < K) ? U[(size_t)(m0 + mm) * K + k0 + kk] : 0.0;
-            const int k2 = e >> 6, bb = e & 63;                 // F row-contiguous in b
-            Bs[k2][bb] = (k0 + k2 < K && b0 + bb < B) ? F[(size_t)(k0 + k2) * B + b0 + bb] : 0.0;
+            Bs[kk][mm] = (b0 + mm < B && k0 + kk < K) ? F[(size_t)(b0 + mm) * K + k0 + kk] : 0.0;   // F row-contiguous in k
         }
         __syncthreads();
 #pragma unroll
@@ -121,7 +133,7 @@ k_gemm_f64(int M, int K, int B, const double* __restrict__ U, const double* __re
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int m = m0 + ty * 4 + i, b = b0 + tx * 4 + j;
-            if (m < M && b < B) Y[(size_t)m * B + b] = acc[i][j];
+            if (m < M && b < B) Y[(size_t)b * M + m] = acc[i][j];
         }
 }
 
@@ -171,7 +183,9 @@ int pbso_modes_upload(const double* U, int M, int K, pbso_modes** out) {
     pbso_modes* md = new pbso_modes();
     md->M = M; md->K = K;
     PBSO_CUDA(cudaGetDevice(&md->device));
+    PBSO_CUDA(cudaDeviceGetAttribute(&md->sm_count, cudaDevAttrMultiProcessorCount, md->device));
     PBSO_CUDA(cudaStreamCreateWithFlags(&md->stream, cudaStreamNonBlocking));
+    PBSO_CUDA(cudaEventCreate(&md->e0)); PBSO_CUDA(cudaEventCreate(&md->e1));
     PBSO_CUDA(cudaMalloc(&md->d_U, sizeof(double) * (size_t)M * K));
     PBSO_CUDA(cudaMemcpy(md->d_U, U, sizeof(double) * (size_t)M * K, cudaMemcpyHostToDevice));
     *out = md;
@@ -209,7 +223,9 @@ int pbso_modes_destroy(pbso_modes* md) {
     if (!md) return PBSO_OK;
     DeviceGuard g(md->device);
     if (md->stream) cudaStreamSynchronize(md->stream);
-    cudaFree(md->d_U); cudaFree(md->d_scratch);
+    cudaFree(md->d_U); cudaFree(md->d_scratch); cudaFree(md->d_Uhi); cudaFree(md->d_Ulo); cudaFree(md->d_Fsplit);
+    if (md->e0) cudaEventDestroy(md->e0);
+    if (md->e1) cudaEventDestroy(md->e1);
     if (md->stream) cudaStreamDestroy(md->stream);
     delete md;
     return PBSO_OK;
@@ -230,7 +246,24 @@ int pbso_modes_project_vertices(const pbso_modes* md, int force_dim, int B, cons
     return project_sparse(const_cast<pbso_modes*>(md), force_dim, B, 1, vids, nullptr, vn, out);
 }
 
-int pbso_modes_project_dense(const pbso_modes* mdc, int force_dim, const double* F, int B, double* Y) {
+static int ensure_u_planes(pbso_modes* md) {
+    if (md->d_Uhi) return PBSO_OK;
+    const size_t n = (size_t)md->M * tc_pitch(md->K);
+    PBSO_CUDA(cudaMalloc(&md->d_Uhi, sizeof(float) * n));
+    PBSO_CUDA(cudaMalloc(&md->d_Ulo, sizeof(float) * n));
+    return tc_split_f64(md->d_U, md->M, md->K, md->d_Uhi, md->d_Ulo, md->stream);
+}
+static int ensure_f_planes(pbso_modes* md, int B) {
+    const size_t n = 2 * (size_t)B * tc_pitch(md->K);
+    if (n > md->fsplit_cap) {
+        cudaFree(md->d_Fsplit);
+        PBSO_CUDA(cudaMalloc(&md->d_Fsplit, sizeof(float) * n));
+        md->fsplit_cap = n;
+    }
+    return PBSO_OK;
+}
+
+int pbso_modes_project_dense(const pbso_modes* mdc, int force_dim, const double* F, int B, double* Y, int precision) {
     pbso_modes* md = const_cast<pbso_modes*>(mdc);
     PBSO_REQUIRE(md && F && Y && B > 0, PBSO_ERR_INVALID, "bad argument");
     PBSO_REQUIRE(force_dim > 0 && force_dim <= md->M, PBSO_ERR_RANGE, "forceDim exceeds number of modes");
@@ -241,20 +274,54 @@ int pbso_modes_project_dense(const pbso_modes* mdc, int force_dim, const double*
     if (int rc = ensure_scratch(md, off_y + nb_y)) return rc;
     char* s = (char*)md->d_scratch;
     PBSO_CUDA(cudaMemcpyAsync(s, F, nb_f, cudaMemcpyHostToDevice, md->stream));
-    if (B == 1 && (K % 2 == 0)) {
-        k_gemv_f64<<<force_dim, 256, 0, md->stream>>>(K, md->d_U, (const double*)s, (double*)(s + off_y));
-    } else {
-        k_gemm_f64<<<dim3(div_up(B, 64), div_up(force_dim, 64)), 256, 0, md->stream>>>(
-            force_dim, K, B, md->d_U, (const double*)s, (double*)(s + off_y));
+    PBSO_CUDA(cudaEventRecord(md->e0, md->stream));
+    if (precision == PBSO_PREC_F64) {
+        if (B == 1 && (K % 2 == 0)) {
+            k_gemv_f64<<<force_dim, 256, 0, md->stream>>>(K, md->d_U, (const double*)s, (double*)(s + off_y));
+        } else {
+            k_gemm_f64<<<dim3(div_up(B, 64), div_up(force_dim, 64)), 256, 0, md->stream>>>(
+                force_dim, K, B, md->d_U, (const double*)s, (double*)(s + off_y));
+        }
+        PBSO_CUDA(cudaGetLastError());
+        PBSO_CUDA(cudaEventRecord(md->e1, md->stream));
+        PBSO_CUDA(cudaMemcpyAsync(Y, s + off_y, nb_y, cudaMemcpyDeviceToHost, md->stream));
+        PBSO_CUDA(cudaStreamSynchronize(md->stream));
+        return PBSO_OK;
     }
-    PBSO_CUDA(cudaGetLastError());
-    PBSO_CUDA(cudaMemcpyAsync(Y, s + off_y, nb_y, cudaMemcpyDeviceToHost, md->stream));
+    PBSO_REQUIRE(precision == PBSO_PREC_TF32X3, PBSO_ERR_INVALID, "precision must be PBSO_PREC_F64 or PBSO_PREC_TF32X3");
+    if (int rc = ensure_u_planes(md)) return rc;
+    if (int rc = ensure_f_planes(md, B)) return rc;
+    const size_t plane = (size_t)B * tc_pitch(K);
+    if (int rc = tc_split_f64((const double*)s, B, K, md->d_Fsplit, md->d_Fsplit + plane, md->stream)) return rc;
+    float* d_Y = (float*)(s + off_y);
+    if (int rc = tc_project(md->d_Uhi, md->d_Ulo, force_dim, md->d_Fsplit, md->d_Fsplit + plane, B, K, d_Y, md->sm_count, md->stream)) return rc;
+    PBSO_CUDA(cudaEventRecord(md->e1, md->stream));
+    std::vector<float> yf((size_t)force_dim * B);
+    PBSO_CUDA(cudaMemcpyAsync(yf.data(), d_Y, sizeof(float) * yf.size(), cudaMemcpyDeviceToHost, md->stream));
     PBSO_CUDA(cudaStreamSynchronize(md->stream));
+    for (size_t i = 0; i < yf.size(); ++i) Y[i] = (double)yf[i];
     return PBSO_OK;
 }
 
-int pbso_modes_project_dense_device(const pbso_modes*, int, const float*, int, float*, void*) {
-    return set_error(PBSO_ERR_UNSUPPORTED, "tensor-core batched projection not built yet");
+int pbso_modes_last_kernel_ms(const pbso_modes* md, float* ms) {
+    PBSO_REQUIRE(md && ms, PBSO_ERR_INVALID, "null argument");
+    DeviceGuard g(md->device);
+    PBSO_CUDA(cudaEventSynchronize(md->e1));
+    PBSO_CUDA(cudaEventElapsedTime(ms, md->e0, md->e1));
+    return PBSO_OK;
+}
+
+int pbso_modes_project_dense_device(const pbso_modes* mdc, int force_dim, const float* d_F, int B, float* d_Y, void* cuda_stream) {
+    pbso_modes* md = const_cast<pbso_modes*>(mdc);
+    PBSO_REQUIRE(md && d_F && d_Y && B > 0, PBSO_ERR_INVALID, "bad argument");
+    PBSO_REQUIRE(force_dim > 0 && force_dim <= md->M, PBSO_ERR_RANGE, "forceDim exceeds number of modes");
+    DeviceGuard g(md->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : md->stream;
+    if (!md->d_Uhi) { if (int rc = ensure_u_planes(md)) return rc; PBSO_CUDA(cudaStreamSynchronize(md->stream)); }
+    if (int rc = ensure_f_planes(md, B)) return rc;
+    const size_t plane = (size_t)B * tc_pitch(md->K);
+    if (int rc = tc_split_f32(d_F, B, md->K, md->d_Fsplit, md->d_Fsplit + plane, st)) return rc;
+    return tc_project(md->d_Uhi, md->d_Ulo, force_dim, md->d_Fsplit, md->d_Fsplit + plane, B, md->K, d_Y, md->sm_count, st);
 }
 
 }  // extern "C"

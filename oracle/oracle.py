@@ -248,9 +248,9 @@ def project_face(U, vids, coords, vn, forceDim=None):
 
 
 def project_dense(U, F):
-    """Y = U F  (U [M][K], F [K][B]) -- dense form of the same projection (cfg3)."""
-    U = _f64(U); F = _f64(F); M, K = U.shape; B = F.shape[1]
-    Y = np.empty((M, B))
+    """Y[b][m] = sum_k U[m][k] F[b][k]  (U [M][K], F [B][K]) -- dense form of the same projection (cfg3)."""
+    U = _f64(U); F = _f64(F); M, K = U.shape; B = F.shape[0]
+    Y = np.empty((B, M))
     lib().orc_project_dense(M, K, B, _dp(U), _dp(F), _dp(Y))
     return Y
 

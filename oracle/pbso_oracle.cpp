@@ -526,17 +526,16 @@ void orc_project_face(int forceDim, const double* U, int nDOF, const int* vids,
                       const double* coords, const double* vn, double* out) {
     project_face(forceDim, U, nDOF, vids, coords, vn, out);
 }
-// Dense restatement used only for the batched-projection parity check: Y[m][b] = sum_d U[m][d] F[d][b]
-// (F is K x B row-major).  Same operation as GetModalForceVertex with a dense load vector.
+// Dense restatement used only for the batched-projection parity check: Y[b][m] = sum_d U[m][d] F[b][d]
+// (F is B x K, one dense load vector per impulse).  Same contraction as GetModalForceVertex with a dense f.
 void orc_project_dense(int M, int K, int B, const double* U, const double* F, double* Y) {
-    for (int m = 0; m < M; ++m) {
-        double* y = Y + (size_t)m * B;
-        std::fill(y, y + B, 0.0);
-        const double* u = U + (size_t)m * K;
-        for (int d = 0; d < K; ++d) {
-            const double ud = u[d];
-            const double* f = F + (size_t)d * B;
-            for (int b = 0; b < B; ++b) y[b] += ud * f[b];
+    for (int b = 0; b < B; ++b) {
+        const double* f = F + (size_t)b * K;
+        for (int m = 0; m < M; ++m) {
+            const double* u = U + (size_t)m * K;
+            double acc = 0.0;
+            for (int d = 0; d < K; ++d) acc += u[d] * f[d];
+            Y[(size_t)b * M + m] = acc;
         }
     }
 }

@@ -1,0 +1,75 @@
+"""GPU-box micro-benchmarks for the non-dominant kernels (run under gpurun): K5 batched projection on tensor
+cores (TFLOP/s, algorithmic 2 M K B), K4 dense GEMV and K3 FFAT evaluation (GB/s of algorithmic bytes vs the
+measured HBM copy bandwidth).  Prints one JSON object."""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import openpbso_b200 as pbso
+from openpbso_b200 import synth
+
+def ev_time(fn, iters=10, warm=3, flush=True):
+    s = torch.cuda.current_stream()
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush: pbso.flush_l2(256 << 20); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(s); fn(); e1.record(s); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+out = {}
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+hbm = peaks["hbm_gbs"]
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+sp = stream.cuda_stream
+
+# ---- K5 / K4: cfg3 sizes -----------------------------------------------------------------
+M, V = 2048, 20000; K = 3 * V
+quick = "--quick" in sys.argv
+if quick: M, K = 1024, 6000
+rng = np.random.default_rng(1003)
+U = rng.standard_normal((M, K))
+md = pbso.ModeShapes(U)
+k5 = []
+for B in ([64, 580] if quick else [8, 64, 580, 4096]):
+    F = torch.randn(B, K, device="cuda", dtype=torch.float32)
+    Y = torch.empty(B, M, device="cuda", dtype=torch.float32)
+    fn = lambda: md.project_dense_device(F.data_ptr(), B, Y.data_ptr(), stream_ptr=sp)
+    med, best = ev_time(fn, iters=8)
+    # parity on a few columns against float64 torch
+    ref = (F[:4].double() @ torch.from_numpy(U).cuda().T)
+    err = ((Y[:4].double() - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    k5.append({"B": B, "ms": med, "ms_best": best, "tflops": 2.0 * M * K * B / (med * 1e-3) / 1e12, "col_rel_l2": err})
+out["K5_project_tc"] = {"M": M, "K": K, "runs": k5, "note": "includes the per-call TF32 hi/lo split of F; algorithmic FLOP = 2 M K B (3 MMAs issued per product)"}
+
+f = rng.standard_normal((1, K))
+kms = []; t0 = time.perf_counter(); n = 20
+for _ in range(n):
+    pbso.flush_l2(256 << 20); torch.cuda.synchronize()
+    md.project_dense(f); kms.append(md.last_kernel_ms())
+dt = (time.perf_counter() - t0) / n
+alg = (M * K * 8 + K * 8 + M * 8)
+out["K4_gemv_f64"] = {"kernel_ms": float(np.median(kms)), "algorithmic_GB": alg / 1e9, "GBps": alg / (np.median(kms) * 1e-3) / 1e9,
+                      "frac_of_hbm": alg / (np.median(kms) * 1e-3) / 1e9 / hbm, "hbm_peak_gbs": hbm,
+                      "host_call_ms_incl_copies_and_flush": dt * 1e3}
+
+# ---- K3: cfg4 (1024 modes x 64 listeners) and the HUD sphere (10242 listeners) ---------------
+Mf = 1024
+freqs = synth.mode_frequencies(Mf, 1004)
+fm = pbso.FFATMaps.from_dicts(synth.ffat_maps(freqs, 2000))
+k3 = []
+for L in ([64] if quick else [1, 64, 10242]):
+    pos = torch.from_numpy(synth.listeners(L, 5)).cuda()
+    o = torch.empty(L, Mf, device="cuda", dtype=torch.float64)
+    import ctypes as C
+    fn = lambda: pbso._capi.check(pbso.lib().pbso_ffat_eval_device(fm._h, Mf, C.c_void_p(pos.data_ptr()), L, C.c_void_p(o.data_ptr()), C.c_void_p(sp)))
+    med, best = ev_time(fn, iters=10)
+    D = 6144
+    bytes_alg = Mf * (min(D, 4 * L) * 8 + L * 8)
+    k3.append({"L": L, "us": med * 1e3, "algorithmic_MB": bytes_alg / 1e6, "GBps": bytes_alg / (med * 1e-3) / 1e9, "frac_of_hbm": bytes_alg / (med * 1e-3) / 1e9 / hbm})
+out["K3_ffat_eval"] = {"modes": Mf, "texels": 6144, "runs": k3}
+print(json.dumps(out))

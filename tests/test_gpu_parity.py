@@ -226,10 +226,10 @@ def test_projection_sparse_and_dense(pbso, orc):
     ref = np.array([orc.project_vertex(U, v, n) for v, n in zip(vs, vns)])
     assert np.allclose(got, ref, rtol=1e-13)
     f = rng.standard_normal(3 * V)
-    assert np.allclose(md.project_dense(f)[:, 0], orc.project_dense(U, f.reshape(-1, 1))[:, 0], rtol=1e-11, atol=1e-11)
-    F = rng.standard_normal((3 * V, 9))
+    assert np.allclose(md.project_dense(f)[0], orc.project_dense(U, f.reshape(1, -1))[0], rtol=1e-11, atol=1e-11)
+    F = rng.standard_normal((9, 3 * V))
     Y = md.project_dense(F); Yr = orc.project_dense(U, F)
-    assert np.max(np.linalg.norm(Y - Yr, axis=0) / np.linalg.norm(Yr, axis=0)) < 1e-12
+    assert np.max(np.linalg.norm(Y - Yr, axis=1) / np.linalg.norm(Yr, axis=1)) < 1e-12
     for bad in (-1, V):
         with pytest.raises(pbso.PbsoError) as e:                   # std::vector::at
             md.GetModalForceVertex(M, bad, vn)
@@ -248,6 +248,22 @@ def test_modes_file_roundtrip(pbso, orc, tmp_path):
     with pytest.raises(pbso.PbsoError) as e:
         pbso.ModeShapes.read(str(tmp_path / "missing.modes"))
     assert e.value.code == 3
+
+
+@pytest.mark.parametrize("M,K,B", [(128, 64, 128), (128, 256, 16), (96, 1500, 9), (300, 4100, 200), (2048, 6000, 580)])
+def test_projection_tensor_core_3xtf32(pbso, M, K, B):
+    """K5: tcgen05 3xTF32 batched projection; column rel-L2 <= 1e-5 against float64 numpy.
+    Ragged M, K (not multiples of the 128 x 32 tiles), B below and above one N tile, split-K."""
+    rng = np.random.default_rng(M + K + B)
+    U = rng.standard_normal((M, K)); F = rng.standard_normal((B, K))
+    md = pbso.ModeShapes(U)
+    Y = md.project_dense(F, precision=pbso.PREC_TF32X3)
+    Yr = F @ U.T
+    err = np.linalg.norm(Y - Yr, axis=1) / np.linalg.norm(Yr, axis=1)
+    print("3xTF32 M=%d K=%d B=%d: max column rel-L2 %.2e" % (M, K, B, err.max()))
+    assert err.max() <= 1e-5
+    Y2 = md.project_dense(F[:, :], forceDim=M - 5, precision=pbso.PREC_TF32X3)      # forceDim < M (culled modes)
+    assert np.allclose(Y2, Y[:, :M - 5], rtol=0, atol=1e-4 * np.abs(Yr).max())
 
 
 # --------------------------------------------------------------------------- batch renderer

@@ -141,8 +141,8 @@ def test_projection(orc):
     vids = [1, 5, 9]; bc = np.array([0.2, 0.3, 0.5])
     ref = sum(bc[j] * (U[:, 3 * v:3 * v + 3] @ vn) for j, v in enumerate(vids))
     assert np.allclose(orc.project_face(U, vids, bc, vn), ref, rtol=1e-13)
-    F = np.random.default_rng(0).standard_normal((30, 3))
-    assert np.allclose(orc.project_dense(U, F), U @ F, rtol=1e-12)
+    F = np.random.default_rng(0).standard_normal((3, 30))
+    assert np.allclose(orc.project_dense(U, F), F @ U.T, rtol=1e-12)
 
 
 def test_solver_quirks(orc):
