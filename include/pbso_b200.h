@@ -168,8 +168,9 @@ int pbso_batch_set_transfer(pbso_batch* bt, const double* trans);
 int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const int* buf,
                             const double* space);
 /* Render n_buffers x buf_size samples of every object from zero state and mix them down:
- * mix[i] = sum_obj y_obj[i]  (double, n_buffers*buf_size).  Runs on n_chunks independent time
- * chunks (0 = choose) whose start states come from closed-form pole powers. */
+ * mix[i] = sum_obj y_obj[i]  (double, n_buffers*buf_size).  With PBSO_PREC_F32_TILED and buf_size 256 the
+ * render is also parallel over n_chunks independent time chunks (0 = choose from the SM count) whose start
+ * states come from closed-form pole powers of the impulses before them; FP64 runs one chunk. */
 int pbso_batch_render_mix(pbso_batch* bt, int buf_size, int n_buffers, int precision,
                           int n_chunks, double* mix);
 /* Device-resident variant: enqueue only; d_mix (double[n_buffers*buf_size]) is zeroed then

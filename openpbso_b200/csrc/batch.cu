@@ -45,6 +45,7 @@ struct pbso_batch {
     double* d_mix = nullptr; size_t mix_cap = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int last_launches = 0;
+    int sm_count = 148;
     size_t npm() const { return (size_t)n_obj * n_modes; }
     double* lneps() const { return d_par; }
     double* theta() const { return d_par + npm(); }
@@ -287,9 +288,9 @@ __device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 
-template <int WARPS, int MB, int JJ, bool F2>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-k_batch_pow_g(int n_modes, int slabs, int n_buf,
+template <int WARPS, int MB, int JJ, bool F2, int MINB = 1>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_batch_pow_g(int n_modes, int slabs, int n_buf, int n_chunks, int bufs_per_chunk,
               const double* __restrict__ lneps, const double* __restrict__ theta,
               const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
               const int* __restrict__ ev_off, const int* __restrict__ ev_buf, const double* __restrict__ ev_space,
@@ -298,7 +299,12 @@ k_batch_pow_g(int n_modes, int slabs, int n_buf,
     static_assert(BUF % L == 0 && (JJ % 2 == 0) && MB <= 32, "bad tile configuration");
     __shared__ __align__(16) float sV[WARPS][MB][2 * TT];
     __shared__ __align__(16) float sY[2][WARPS][BUF];
-    const int obj = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    // blockIdx.x = (object, slab, time chunk): chunks are independent because a chunk's start state follows in
+    // closed form from the impulses before it (v = sum_e inj_e w^(256 (b0 - b_e))), evaluated in FP64 below.
+    const int chunk = blockIdx.x % n_chunks;
+    const int obj = (blockIdx.x / n_chunks) / slabs, slab = (blockIdx.x / n_chunks) % slabs;
+    const int b_begin = chunk * bufs_per_chunk;
+    const int b_end = min(n_buf, b_begin + bufs_per_chunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m_base = slab * SLAB + warp * MB;
     const size_t obase = (size_t)obj * n_modes;
@@ -341,9 +347,23 @@ k_batch_pow_g(int n_modes, int slabs, int n_buf,
     }
     int ev = ev_off[obj];
     const int ev_end = ev_off[obj + 1];
+    // impulses before this chunk: advance each with the exact pole power (FP64 exp / sincos of the total angle)
+    while (ev < ev_end && ev_buf[ev] < b_begin) {
+        if (owner) {
+            const double n = (double)BUF * (double)(b_begin - ev_buf[ev]);
+            const double le = lneps[obase + my_m], th = theta[obase + my_m];
+            double s, c; sincos(n * th, &s, &c);
+            const double e = exp(n * le);
+            const double pr = e * c, pi = e * s;                    // w^n
+            const double sp = ev_space[(size_t)ev * n_modes + my_m];
+            const double ir = injr * sp, ii = inji * sp;
+            vr += ir * pr - ii * pi; vi += ir * pi + ii * pr;
+        }
+        ++ev;
+    }
     int next_buf = ev < ev_end ? ev_buf[ev] : INT_MAX;
 
-    for (int bi = 0; bi < n_buf; ++bi) {
+    for (int bi = b_begin; bi < b_end; ++bi) {
         if (bi == next_buf) {
             if (owner) {
                 const double sp = ev_space[(size_t)ev * n_modes + my_m];
@@ -431,7 +451,7 @@ k_batch_pow_g(int n_modes, int slabs, int n_buf,
 }
 
 // ---------------------------------------------------------------------------------------------
-static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precision, double* d_mix, float* d_stems) {
+static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precision, int n_chunks, double* d_mix, float* d_stems) {
     PBSO_REQUIRE(buf_size > 0 && n_buffers > 0, PBSO_ERR_INVALID, "buf_size and n_buffers must be > 0");
     PBSO_REQUIRE(bt->d_ev_off, PBSO_ERR_INVALID, "no impulse script: call pbso_batch_set_impulses first");
     const size_t ns = (size_t)buf_size * n_buffers;
@@ -446,9 +466,13 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
             bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, d_mix, d_stems)
         // default: 16 warps x 16 modes, 64-sample tiles, packed FFMA2 (best of the measured variants, see profiles/)
         static const int variant = getenv("PBSO_POW_VARIANT") ? atoi(getenv("PBSO_POW_VARIANT")) : 1;
-#define PBSO_LAUNCH_G(W, MB, JJ, F2)                                                                       \
+#define PBSO_LAUNCH_G(W, MB, JJ, ...)                                                                      \
         do { const int sl = div_up(bt->n_modes, (W) * (MB));                                               \
-             k_batch_pow_g<W, MB, JJ, F2><<<bt->n_obj * sl, (W) * 32, 0, bt->stream>>>(bt->n_modes, sl, n_buffers, \
+             /* time chunks: enough CTAs for ~4 waves of SMs when there are few objects; >= 8 buffers each */ \
+             int nc = n_chunks > 0 ? n_chunks : div_up(4 * bt->sm_count, bt->n_obj * sl);                  \
+             nc = std::max(1, std::min(nc, div_up(n_buffers, 8)));                                         \
+             const int bpc = div_up(n_buffers, nc); nc = div_up(n_buffers, bpc);                           \
+             k_batch_pow_g<W, MB, JJ, __VA_ARGS__><<<bt->n_obj * sl * nc, (W) * 32, 0, bt->stream>>>(bt->n_modes, sl, n_buffers, nc, bpc, \
                  bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf,  \
                  bt->d_ev_space, d_mix, d_stems); } while (0)
         if (buf_size == 256 && variant == 1) PBSO_LAUNCH_G(16, 16, 2, true);
@@ -456,6 +480,10 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
         else if (buf_size == 256 && variant == 3) PBSO_LAUNCH_G(8, 16, 4, true);
         else if (buf_size == 256 && variant == 4) PBSO_LAUNCH_G(16, 8, 4, true);
         else if (buf_size == 256 && variant == 5) PBSO_LAUNCH_G(8, 8, 8, true);
+        else if (buf_size == 256 && variant == 6) PBSO_LAUNCH_G(8, 16, 2, true, 2);
+        else if (buf_size == 256 && variant == 7) PBSO_LAUNCH_G(4, 16, 2, true, 4);
+        else if (buf_size == 256 && variant == 8) PBSO_LAUNCH_G(12, 16, 4, true);
+        else if (buf_size == 256 && variant == 9) PBSO_LAUNCH_G(11, 16, 4, true);
         else if (buf_size == 64) PBSO_LAUNCH_POW(1);
         else if (buf_size == 128) PBSO_LAUNCH_POW(2);
         else if (buf_size == 256) PBSO_LAUNCH_POW(4);
@@ -484,6 +512,7 @@ int pbso_batch_create(int n_obj, int n_modes, double h, const double* a, const d
     pbso_batch* bt = new pbso_batch();
     bt->n_obj = n_obj; bt->n_modes = n_modes; bt->h = h;
     PBSO_CUDA(cudaGetDevice(&bt->device));
+    PBSO_CUDA(cudaDeviceGetAttribute(&bt->sm_count, cudaDevAttrMultiProcessorCount, bt->device));
     PBSO_CUDA(cudaStreamCreateWithFlags(&bt->own_stream, cudaStreamNonBlocking));
     bt->stream = bt->own_stream;
     PBSO_CUDA(cudaEventCreate(&bt->e0)); PBSO_CUDA(cudaEventCreate(&bt->e1));
@@ -564,18 +593,16 @@ int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const 
 
 int pbso_batch_render_mix_device(pbso_batch* bt, int buf_size, int n_buffers, int precision, int n_chunks, double* d_mix) {
     PBSO_REQUIRE(bt && d_mix, PBSO_ERR_INVALID, "null argument");
-    (void)n_chunks;
     DeviceGuard g(bt->device);
-    return launch_render(bt, buf_size, n_buffers, precision, d_mix, nullptr);
+    return launch_render(bt, buf_size, n_buffers, precision, n_chunks, d_mix, nullptr);
 }
 
 int pbso_batch_render_mix(pbso_batch* bt, int buf_size, int n_buffers, int precision, int n_chunks, double* mix) {
     PBSO_REQUIRE(bt && mix, PBSO_ERR_INVALID, "null argument");
-    (void)n_chunks;
     DeviceGuard g(bt->device);
     const size_t ns = (size_t)buf_size * n_buffers;
     if (ns > bt->mix_cap) { cudaFree(bt->d_mix); PBSO_CUDA(cudaMalloc(&bt->d_mix, sizeof(double) * ns)); bt->mix_cap = ns; }
-    if (int rc = launch_render(bt, buf_size, n_buffers, precision, bt->d_mix, nullptr)) return rc;
+    if (int rc = launch_render(bt, buf_size, n_buffers, precision, n_chunks, bt->d_mix, nullptr)) return rc;
     PBSO_CUDA(cudaMemcpyAsync(mix, bt->d_mix, sizeof(double) * ns, cudaMemcpyDeviceToHost, bt->stream));
     PBSO_CUDA(cudaStreamSynchronize(bt->stream));
     return PBSO_OK;
@@ -586,7 +613,7 @@ int pbso_batch_render_stems(pbso_batch* bt, int buf_size, int n_buffers, int pre
     DeviceGuard g(bt->device);
     const size_t ns = (size_t)buf_size * n_buffers * bt->n_obj;
     float* d_stems; PBSO_CUDA(cudaMalloc(&d_stems, sizeof(float) * ns));
-    int rc = launch_render(bt, buf_size, n_buffers, precision, nullptr, d_stems);
+    int rc = launch_render(bt, buf_size, n_buffers, precision, 0, nullptr, d_stems);
     if (rc == PBSO_OK) {
         cudaError_t e = cudaMemcpyAsync(stems, d_stems, sizeof(float) * ns, cudaMemcpyDeviceToHost, bt->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(bt->stream);

@@ -20,7 +20,9 @@
 // =============================================================================
 #include "common.cuh"
 #include "fatcube_codec.h"
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -53,7 +55,8 @@ struct pbso_ffat {
     cudaStream_t stream = nullptr;
     double* d_pos = nullptr; double* d_out = nullptr; size_t pos_cap = 0, out_cap = 0;
     void* d_loc = nullptr; size_t loc_cap = 0;          // per-listener stencils (shared-geometry path)
-    int n_uncompressed = 0, n_compressed = 0;           // leading maps with is_compressed == false / true
+    int n_uncompressed = 0, n_compressed = 0;
+    int sm_count = 148;           // leading maps with is_compressed == false / true
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -147,7 +150,7 @@ k_ffat_eval_general(int n_modes, int L, const double* __restrict__ geom, const i
 //  k_ffat_gather: block = 256 modes x FG_LPB listeners; the stencil sits in shared memory, every thread gathers its
 //                 mode's four texels from the texel-major table -- a warp reads 32 consecutive doubles per texel
 //                 row, fully coalesced -- and writes out[l][m] coalesced.  k differs per mode (geom[m][31]).
-struct FfatLoc { int idx[4]; double w[4]; double r; };
+struct __align__(16) FfatLoc { int idx[4]; double w[4]; double r; double pad; };   // 64 B: int4 + 3 x double2 loads
 
 __global__ void __launch_bounds__(128)
 k_ffat_locate(int L, const double* __restrict__ geom, const int* __restrict__ igeom,
@@ -158,6 +161,7 @@ k_ffat_locate(int L, const double* __restrict__ geom, const int* __restrict__ ig
     const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
     FfatLoc o;
     ffat_locate(g, p, o.idx, o.w, o.r);
+    o.pad = 0.0;
     loc[l] = o;
 }
 
@@ -180,6 +184,79 @@ k_ffat_gather(int n_modes, int L, const double* __restrict__ geom, const double*
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * psi_tm[(size_t)q.idx[kk] * n_stride + m];    // ffat_solver.h:1198-1204
         out[(size_t)(l0 + i) * n_modes + m] = fabs(psi0 / (k * q.r));                                  // :904-905
+    }
+}
+
+// Many listeners (the 10 242-direction sphere of tools/real_time_modal_sound.cpp:921-927, or any L >> D/4):
+// every texel of every map is needed, so each CTA stages FS_G whole maps (column 0 of Psi, mode-major, 48 KB each
+// for 6 x 32 x 32 texels) in shared memory with bulk async copies (cp.async.bulk + mbarrier: the TMA engine, SASS
+// UBLKCP) and then streams the listeners' precomputed stencils past them: four shared-memory gathers per
+// (listener, map), one 32-byte store of four adjacent modes per listener.
+constexpr int FS_G = 4;
+constexpr int FS_THREADS = 1024;
+
+__global__ void __launch_bounds__(FS_THREADS, 1)
+k_ffat_staged(int n_modes, int L, int D, int l_split, const double* __restrict__ geom, const double* __restrict__ psi_mm,
+              const FfatLoc* __restrict__ loc, double* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char fs_smem[];
+    double* s_psi = reinterpret_cast<double*>(fs_smem);                    // [FS_G][D]
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int m0 = blockIdx.x * FS_G;
+    const int g_live = min(FS_G, n_modes - m0);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)(D * sizeof(double));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * g_live) : "memory");
+        for (int g = 0; g < g_live; ++g) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_psi + (size_t)g * D);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(psi_mm + (size_t)(m0 + g) * D), "r"(bytes), "r"(bar) : "memory");
+        }
+    }
+    double inv_k[FS_G];
+#pragma unroll
+    for (int g = 0; g < FS_G; ++g) inv_k[g] = g < g_live ? 1.0 / geom[(size_t)(m0 + g) * 32 + 31] : 0.0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+        ::"r"(bar) : "memory");
+    const int per = (L + l_split - 1) / l_split;
+    const int l_begin = blockIdx.y * per, l_end = min(L, l_begin + per);
+    const bool vec4 = (g_live == FS_G) && ((n_modes & 3) == 0);
+    for (int l = l_begin + threadIdx.x; l < l_end; l += FS_THREADS) {
+        FfatLoc q;
+        {
+            const int4* p4 = reinterpret_cast<const int4*>(loc + l);
+            const int4 i4 = p4[0];
+            const double2 w01 = reinterpret_cast<const double2*>(p4)[1], w23 = reinterpret_cast<const double2*>(p4)[2];
+            const double2 rr = reinterpret_cast<const double2*>(p4)[3];
+            q.idx[0] = i4.x; q.idx[1] = i4.y; q.idx[2] = i4.z; q.idx[3] = i4.w;
+            q.w[0] = w01.x; q.w[1] = w01.y; q.w[2] = w23.x; q.w[3] = w23.y; q.r = rr.x;
+        }
+        const double inv_r = 1.0 / q.r;
+        double v[FS_G];
+#pragma unroll
+        for (int g = 0; g < FS_G; ++g) {
+            const double* P = s_psi + (size_t)g * D;
+            double psi0 = 0.0;
+            if (g < g_live) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * P[q.idx[kk]];          // ffat_solver.h:1198-1204
+            }
+            v[g] = fabs(psi0 * inv_k[g] * inv_r);                                        // |psi / (k r)|, :904-905
+        }
+        double* o = out + (size_t)l * n_modes + m0;
+        if (vec4) {
+            *reinterpret_cast<double2*>(o) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(v[2], v[3]);
+        } else {
+            for (int g = 0; g < g_live; ++g) o[g] = v[g];
+        }
     }
 }
 
@@ -255,7 +332,11 @@ static int ensure_device(pbso_ffat* f) {
     if (!f->dirty) return PBSO_OK;
     if (int rc = check_device()) return rc;
     free_device(f);
-    if (!f->stream) { PBSO_CUDA(cudaGetDevice(&f->device)); PBSO_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking)); }
+    if (!f->stream) {
+        PBSO_CUDA(cudaGetDevice(&f->device));
+        PBSO_CUDA(cudaDeviceGetAttribute(&f->sm_count, cudaDevAttrMultiProcessorCount, f->device));
+        PBSO_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    }
     int n = 0;
     while (f->maps.count(n)) ++n;               // ids 0..n-1 are what computeTransfer can reach
     f->n_dense = n;
@@ -307,8 +388,25 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
             f->loc_cap = L;
         }
         k_ffat_locate<<<div_up(L, 128), 128, 0, s>>>(L, f->d_geom, f->d_igeom, d_pos, (FfatLoc*)f->d_loc);
-        k_ffat_gather<<<dim3(div_up(n_modes, 256), div_up(L, FG_LPB)), 256, 0, s>>>(n_modes, L, f->d_geom, f->d_psi_tm,
-                                                                                 f->n_dense, (const FfatLoc*)f->d_loc, d_out);
+        const size_t stage_bytes = (size_t)FS_G * f->D * sizeof(double);
+        // Measured on B200 (profiles/r1_ffat.md): for 1024 maps x 10 242 listeners the staged kernel is bound by LSU
+        // wavefronts (scattered 8-byte shared-memory gathers + 32-byte output segments) at ~100 us, the coalesced
+        // texel-major gather by L2 bandwidth at ~54 us -- so the gather is the default and staging is opt-in.
+        const char* env = getenv("PBSO_FFAT_STAGED");
+        const bool staged = env && env[0] == '1';
+        if (staged && L >= 1024 && (f->D % 2 == 0) && stage_bytes <= 200 * 1024) {
+            // whole maps in shared memory; listeners split so that the grid is ~7 waves of SMs
+            static bool attr_set = false;
+            if (!attr_set) { PBSO_CUDA(cudaFuncSetAttribute(k_ffat_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+            const int groups = div_up(n_modes, FS_G);
+            // one pass over the listeners per staged group unless there are too few groups to occupy the SMs
+            int l_split = std::max(1, std::min(div_up(f->sm_count, groups), div_up(L, FS_THREADS)));
+            k_ffat_staged<<<dim3(groups, l_split), FS_THREADS, stage_bytes, s>>>(n_modes, L, f->D, l_split, f->d_geom, f->d_psi_mm,
+                                                                                 (const FfatLoc*)f->d_loc, d_out);
+        } else {
+            k_ffat_gather<<<dim3(div_up(n_modes, 256), div_up(L, FG_LPB)), 256, 0, s>>>(n_modes, L, f->d_geom, f->d_psi_tm,
+                                                                                     f->n_dense, (const FfatLoc*)f->d_loc, d_out);
+        }
     } else {
         dim3 grid(div_up(n_modes, 128), L);
         k_ffat_eval_general<<<grid, 128, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_psi_mm, f->d_psi_off, d_pos, d_out);

@@ -27,15 +27,17 @@ hbm = peaks["hbm_gbs"]
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 sp = stream.cuda_stream
 
+ffat_only = "--ffat-only" in sys.argv
 # ---- K5 / K4: cfg3 sizes -----------------------------------------------------------------
 M, V = 2048, 20000; K = 3 * V
 quick = "--quick" in sys.argv
 if quick: M, K = 1024, 6000
+if ffat_only: M, K = 128, 64
 rng = np.random.default_rng(1003)
 U = rng.standard_normal((M, K))
 md = pbso.ModeShapes(U)
 k5 = []
-for B in ([64, 580] if quick else [8, 64, 580, 4096]):
+for B in ([] if ffat_only else [64, 580] if quick else [8, 64, 580, 4096]):
     F = torch.randn(B, K, device="cuda", dtype=torch.float32)
     Y = torch.empty(B, M, device="cuda", dtype=torch.float32)
     fn = lambda: md.project_dense_device(F.data_ptr(), B, Y.data_ptr(), stream_ptr=sp)
@@ -62,7 +64,7 @@ Mf = 1024
 freqs = synth.mode_frequencies(Mf, 1004)
 fm = pbso.FFATMaps.from_dicts(synth.ffat_maps(freqs, 2000))
 k3 = []
-for L in ([64] if quick else [1, 64, 10242]):
+for L in ([10242] if ffat_only else [64] if quick else [1, 64, 10242]):
     pos = torch.from_numpy(synth.listeners(L, 5)).cuda()
     o = torch.empty(L, Mf, device="cuda", dtype=torch.float64)
     import ctypes as C

@@ -193,6 +193,24 @@ def test_ffat_general_geometry_from_files(pbso, orc, golden_dir):
     assert e.value.code == 5
 
 
+def test_ffat_many_listeners_staged(pbso, orc):
+    """Many listeners: the default coalesced gather and the opt-in kernel that stages whole maps in shared memory
+    with bulk async copies; modes not a multiple of 4 and a ragged listener count exercise the tails."""
+    freqs = synth.mode_frequencies(37, 77)
+    maps = synth.ffat_maps(freqs, 2000, n=16)
+    pos = synth.listeners(2500, 13)
+    ref = orc.ffat_eval(maps, pos)
+    os.environ["PBSO_FFAT_STAGED"] = "1"                      # opt-in: whole maps staged in shared memory (UBLKCP)
+    try:
+        got = pbso.FFATMaps.from_dicts(maps).computeTransfer(pos)
+    finally:
+        del os.environ["PBSO_FFAT_STAGED"]
+    assert np.allclose(got, ref, rtol=1e-13)
+    assert np.allclose(pbso.FFATMaps.from_dicts(maps).computeTransfer(pos), ref, rtol=1e-13)   # default gather path
+    got1 = pbso.FFATMaps.from_dicts(maps).computeTransfer(pos[:100])            # small-L path, same numbers
+    assert np.allclose(got1, got[:100], rtol=1e-14)
+
+
 def test_ffat_full_size_properties(pbso):
     """cfg4 size (1024 modes x 64 listeners): 1/r law and texel-centre identity, no oracle needed."""
     freqs = synth.mode_frequencies(1024, 1004)
@@ -315,6 +333,41 @@ def test_batch_multiple_events_and_stems(pbso, orc):
         br.set_impulses([0, 0], [3, 3], space[:2])
     with pytest.raises(pbso.PbsoError):
         br.set_impulses([9], [0], space[:1])
+
+
+@pytest.mark.parametrize("n_chunks", [0, 1, 5, 22])
+def test_batch_time_chunks_cfg1_golden(pbso, golden_dir, n_chunks):
+    """One 64-mode object, 173 buffers: too small to fill the GPU by objects, so the render is split into
+    independent time chunks whose start states come from closed-form pole powers (north_star (1)).  Checked
+    against the cfg1 golden waveform for automatic and explicit chunk counts."""
+    g = np.load(os.path.join(golden_dir, "cfg1_ball.npz"))
+    mat = synth.MATERIALS["low_damping"]
+    freqs = synth.mode_frequencies(64, 1001)
+    a, b = synth.ab_from_material(freqs, mat)
+    br = pbso.BatchRenderer(H, a[None, :], b[None, :])
+    br.set_transfer(g["trans"][None, :])
+    br.set_impulses([0], [0], (g["space"] * g["scale"])[None, :])
+    y = br.render_mix(256, 173, pbso.PREC_F32_TILED, n_chunks)
+    rel, mx = assert_waveform_parity(y, g["y"])
+    print("chunks=%d: rel-L2 %.2e max-abs %.2e" % (n_chunks, rel, mx))
+
+
+def test_batch_time_chunks_many_events(pbso):
+    """Impulse stream on few objects (cfg2-like) rendered in chunks: identical to the single-chunk render."""
+    n_obj, n_modes, n_buf = 3, 200, 400
+    w = synth.batch_workload(n_obj, n_modes, n_buf, 21, "high_damping")
+    rng = np.random.default_rng(21)
+    obj = np.repeat(np.arange(n_obj), 40)
+    buf = np.concatenate([rng.choice(n_buf, 40, replace=False) for _ in range(n_obj)])
+    space = rng.standard_normal((len(obj), n_modes))
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"]); br.set_impulses(obj, buf, space)
+    y1 = br.render_mix(256, n_buf, pbso.PREC_F32_TILED, 1)
+    y64 = br.render_mix(256, n_buf, pbso.PREC_F64)
+    assert_waveform_parity(y1, y64)
+    for nc in (0, 7, 50):
+        yc = br.render_mix(256, n_buf, pbso.PREC_F32_TILED, nc)
+        assert_waveform_parity(yc, y64)
+        assert np.max(np.abs(yc - y1)) <= 5e-7 * np.max(np.abs(y64))
 
 
 def test_batch_full_size_slice_f32_vs_f64(pbso):
