@@ -125,6 +125,25 @@ def ref():
         R.ref_material_xi.argtypes = [C.c_double] * 3
         R.ref_material_omega_di.restype = C.c_double
         R.ref_material_omega_di.argtypes = [C.c_double] * 3
+        R.ref_solver_create.restype = C.c_void_p
+        R.ref_solver_create.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        R.ref_solver_destroy.argtypes = [C.c_void_p]
+        R.ref_solver_enqueue_force.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_double, C.c_int]
+        R.ref_solver_enqueue_trans.argtypes = [C.c_void_p, c_dp, C.c_int]
+        R.ref_solver_enqueue_arprm.argtypes = [C.c_void_p] + [C.c_double] * 4
+        R.ref_solver_set_use_transfer.argtypes = [C.c_void_p, C.c_int]
+        R.ref_solver_step.argtypes = [C.c_void_p, c_dp, c_dp]
+        R.ref_solver_latest_transfer.argtypes = [C.c_void_p, c_dp]
+        R.ref_solver_read_ffat_maps.argtypes = [C.c_void_p, C.c_char_p]
+        R.ref_solver_compute_transfer.argtypes = [C.c_void_p, c_dp, c_dp]
+        R.ref_solver_compute_transfer_enqueue.argtypes = [C.c_void_p, c_dp]
+        R.ref_ffat_load_all.restype = C.c_void_p
+        R.ref_ffat_load_all.argtypes = [C.c_char_p, c_ip]
+        R.ref_ffat_free.argtypes = [C.c_void_p]
+        R.ref_ffat_eval.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int, c_dp]
+        R.ref_ffat_load_save.argtypes = [C.c_char_p, C.c_char_p, c_ip, c_dp]
+        R.ref_list_dir_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        R.ref_batch_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp]
         _REF = R
     return _REF
 
@@ -219,6 +238,76 @@ class Solver:
     def __del__(self):
         if getattr(self, "_p", None):
             lib().orc_solver_destroy(self._p); self._p = None
+
+
+class RefSolver:
+    """The REFERENCE's own ModalSolver<double,BUF> + ModalIntegrator<double> (modal_solver.h,
+    modal_integrator.h compiled in place into oracle/_ref), behind the same methods as Solver.
+    BUF must be one of the sizes oracle/ref_bridge.cpp instantiates (64, 256, 513)."""
+
+    def __init__(self, h, a, b, BUF=256):
+        R = ref()
+        assert R is not None, "oracle/_ref not built"
+        a = _f64(a); b = _f64(b)
+        self.N = len(a); self.BUF = BUF
+        self._i = R.ref_integrator_create(self.N, h, _dp(a), _dp(b))
+        self._p = R.ref_solver_create(self.N, BUF, self._i)
+        assert self._p, "BUF=%d not instantiated in ref_bridge.cpp" % BUF
+
+    def enqueue_force(self, data, ftype=POINT, width_us=0.0, flags=0):
+        d = _f64(data); assert len(d) == self.N
+        return bool(ref().ref_solver_enqueue_force(self._p, _dp(d), ftype, width_us, flags))
+
+    def enqueue_trans(self, data):
+        d = _f64(data)
+        return bool(ref().ref_solver_enqueue_trans(self._p, _dp(d), len(d)))
+
+    def enqueue_arprm(self, a0, a1, sigma, mu):
+        return bool(ref().ref_solver_enqueue_arprm(self._p, a0, a1, sigma, mu))
+
+    def set_use_transfer(self, use):
+        ref().ref_solver_set_use_transfer(self._p, int(use))
+
+    def step(self):
+        y = np.empty(self.BUF); qn = np.empty(self.N)
+        if ref().ref_solver_step(self._p, _dp(y), _dp(qn)):
+            return y, qn
+        return None
+
+    def latest_transfer(self):
+        t = np.empty(self.N)
+        ref().ref_solver_latest_transfer(self._p, _dp(t))
+        return t
+
+    def read_ffat_maps(self, dirname):
+        ref().ref_solver_read_ffat_maps(self._p, dirname.encode())
+
+    def compute_transfer(self, pos, n):
+        """computeTransfer(pos, T*) (modal_solver.h:303-315); None when no maps are loaded."""
+        out = np.empty(n); pos = _f64(pos)
+        return out if ref().ref_solver_compute_transfer(self._p, _dp(pos), _dp(out)) else None
+
+    def compute_transfer_enqueue(self, pos):
+        """computeTransfer(pos) (modal_solver.h:286-300): evaluates and enqueues a TransMessage."""
+        pos = _f64(pos)
+        return bool(ref().ref_solver_compute_transfer_enqueue(self._p, _dp(pos)))
+
+    def __del__(self):
+        R = _REF
+        if R is not None and getattr(self, "_p", None):
+            R.ref_solver_destroy(self._p); self._p = None
+            R.ref_integrator_destroy(self._i); self._i = None
+
+
+def ref_ffat_eval(dirname, pos, use_compressed=False):
+    """The reference's LoadAll + |GetMapVal| over a directory of .fatcube files -> [L][N] or None."""
+    R = ref(); n = C.c_int()
+    h = R.ref_ffat_load_all(dirname.encode(), C.byref(n))
+    pos = _f64(pos).reshape(-1, 3); L = len(pos)
+    out = np.empty((L, n.value))
+    ok = R.ref_ffat_eval(h, _dp(pos), L, int(use_compressed), _dp(out))
+    R.ref_ffat_free(h)
+    return out if ok else None
 
 
 def force_profile(ftype, width_us, BUF, n_buf):
@@ -337,6 +426,16 @@ def batch_render(h, a, b, space, trans, imp_buf, BUF, n_buf, mix=None):
         mix = np.zeros(n_buf * BUF)
     lib().orc_batch_render(n_obj, N, BUF, n_buf, h, _dp(a), _dp(b), _dp(space), _dp(trans),
                            _ip(imp), _dp(mix))
+    return mix
+
+
+def ref_batch_render(h, a, b, space, trans, imp_buf, n_buf):
+    """Same job as batch_render (BUF = 256) run by the reference's own ModalSolver / ModalIntegrator."""
+    a = _f64(a); b = _f64(b); space = _f64(space); trans = _f64(trans)
+    n_obj, N = a.shape
+    imp = np.ascontiguousarray(imp_buf, dtype=np.int32)
+    mix = np.zeros(n_buf * 256)
+    ref().ref_batch_render(n_obj, N, n_buf, h, _dp(a), _dp(b), _dp(space), _dp(trans), _ip(imp), _dp(mix))
     return mix
 
 

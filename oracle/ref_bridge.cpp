@@ -2,7 +2,9 @@
 // from /root/reference via -I, never copied) against the Eigen shim and exposes them to ctypes so
 // that tests/test_oracle_vs_ref.py can pin oracle/pbso_oracle.cpp to them.  Built by oracle/Makefile
 // into oracle/_ref/libpbso_ref.so (git-ignored).  The reference's arithmetic statements are its own;
-// only the Eigen container underneath (element-wise loops, a dot product) is the shim's.
+// only the Eigen container underneath (element-wise loops, a dot product) is the shim's, and the
+// protobuf message classes under FFAT_Map_Serialize are oracle/ref_stubs/ffat_map.pb.h.
+// io.cpp (ListDirFiles) is compiled alongside, also in place.
 #include <cassert>
 #include <cmath>
 #include <cstring>
@@ -15,6 +17,9 @@
 #include "forces.h"            // /root/reference/forces.h
 #include "ModeData.h"          // /root/reference/ModeData.h
 #include "ModalMaterial.h"     // /root/reference/ModalMaterial.h
+// modal_solver.h pulls in ffat_solver.h and ffat_map_serialize.h; their absent third-party includes
+// (libigl viewer/serialize, protoc-generated ffat_map.pb.h) are satisfied by oracle/ref_stubs/.
+#include "modal_solver.h"      // /root/reference/modal_solver.h
 
 typedef ModalIntegrator<double> Integ;
 typedef Integ::ModalVec Vec;
@@ -95,5 +100,158 @@ double ref_material_xi(double alpha, double beta, double omega) {
 }
 double ref_material_omega_di(double alpha, double beta, double omega) {
     ModalMaterial<double> m; m.alpha = alpha; m.beta = beta; return m.omega_di(omega);
+}
+}
+
+// ---------------------------------------------------------------------------------------------
+// ModalSolver<double,BUF>::step and its queues (modal_solver.h:100-399), FFAT runtime query
+// (ffat_solver.h:676-803, 1180-1206) and the .fatcube loader (ffat_map_serialize.h:90-279),
+// all the reference's own code.
+namespace {
+struct SolverBase {
+    virtual ~SolverBase() {}
+    virtual int enqueue_force(const double* d, int type, double width_us, int flags) = 0;
+    virtual int enqueue_trans(const double* d, int n) = 0;
+    virtual int enqueue_arprm(double a0, double a1, double sigma, double mu) = 0;
+    virtual void set_use_transfer(int u) = 0;
+    virtual int step(double* y, double* qnorm) = 0;
+    virtual void latest_transfer(double* out) = 0;
+    virtual void read_maps(const char* dir) = 0;
+    virtual int compute_transfer(const double* pos, double* out) = 0;
+    virtual int compute_transfer_enqueue(const double* pos) = 0;
+};
+template <int BUF>
+struct SolverT : SolverBase {
+    int N;
+    ModalSolver<double, BUF> s;
+    SolverT(int N_, std::shared_ptr<Integ> integ) : N(N_), s(N_) { s.setIntegrator(integ); }
+    int enqueue_force(const double* d, int type, double width_us, int flags) override {
+        ForceMessage<double, BUF> m;
+        m.data.resize(N);
+        for (int i = 0; i < N; ++i) m.data(i) = d[i];
+        if (type == 1) { m.forceType = ForceType::GaussianForce; m.force.reset(new GaussianForce<double, BUF>(width_us)); }
+        else if (type == 2) { m.forceType = ForceType::AutoregressiveForce; m.force.reset(new AutoregressiveForce<double, BUF>()); }
+        else { m.forceType = ForceType::PointForce; m.force.reset(new PointForce<double, BUF>()); }
+        m.sustainedForceStart = flags & 1; m.sustainedForceEnd = flags & 2; m.clearAllForces = flags & 4;
+        return s.enqueueForceMessage(m) ? 1 : 0;
+    }
+    int enqueue_trans(const double* d, int n) override {
+        TransMessage<double> t; t.N = n; t.data.resize(n);
+        for (int i = 0; i < n; ++i) t.data(i) = d[i];
+        return s.enqueueTransMessage(t) ? 1 : 0;
+    }
+    int enqueue_arprm(double a0, double a1, double sigma, double mu) override {
+        AutoregressiveForceParam<double> p; p.a[0] = a0; p.a[1] = a1; p.sigma = sigma; p.mu = mu;
+        return s.enqueueArprmMessage(p) ? 1 : 0;
+    }
+    void set_use_transfer(int u) override { s.setUseTransfer(u != 0); }
+    int step(double* y, double* qnorm) override {
+        s.step();
+        SoundMessage<double, BUF> snd;
+        if (!s.dequeueSoundMessage(snd)) return 0;      // clearAllForces returns before rendering
+        std::memcpy(y, snd.data.data(), sizeof(double) * BUF);
+        Eigen::Matrix<double, -1, 1> q = s.getQBufferNorm();
+        if (qnorm) std::memcpy(qnorm, q.data(), sizeof(double) * N);
+        return 1;
+    }
+    void latest_transfer(double* out) override {
+        const TransMessage<double>& t = s.getLatestTransfer();
+        std::memcpy(out, t.data.data(), sizeof(double) * t.data.size());
+    }
+    void read_maps(const char* dir) override { s.readFFATMaps(dir); }
+    int compute_transfer(const double* pos, double* out) override {
+        return s.computeTransfer(Eigen::Matrix<double, 3, 1>(pos[0], pos[1], pos[2]), out) ? 1 : 0;
+    }
+    int compute_transfer_enqueue(const double* pos) override {
+        return s.computeTransfer(Eigen::Matrix<double, 3, 1>(pos[0], pos[1], pos[2])) ? 1 : 0;
+    }
+};
+typedef std::map<int, Gpu_Wavesolver::FFAT_Map<double, 3>> MapSet;
+}  // namespace
+
+extern "C" {
+// The solver shares ownership of the integrator the way tools/real_time_modal_sound.cpp:332-345 does;
+// here the bridge keeps the raw pointer alive (no-op deleter), the caller destroys it separately.
+void* ref_solver_create(int N, int BUF, void* integ) {
+    std::shared_ptr<Integ> sp(static_cast<Integ*>(integ), [](Integ*) {});
+    switch (BUF) {
+        case 64:  return static_cast<SolverBase*>(new SolverT<64>(N, sp));
+        case 256: return static_cast<SolverBase*>(new SolverT<256>(N, sp));
+        case 513: return static_cast<SolverBase*>(new SolverT<513>(N, sp));
+        default: return nullptr;
+    }
+}
+void ref_solver_destroy(void* p) { delete static_cast<SolverBase*>(p); }
+int ref_solver_enqueue_force(void* p, const double* d, int type, double width_us, int flags) { return static_cast<SolverBase*>(p)->enqueue_force(d, type, width_us, flags); }
+int ref_solver_enqueue_trans(void* p, const double* d, int n) { return static_cast<SolverBase*>(p)->enqueue_trans(d, n); }
+int ref_solver_enqueue_arprm(void* p, double a0, double a1, double sigma, double mu) { return static_cast<SolverBase*>(p)->enqueue_arprm(a0, a1, sigma, mu); }
+void ref_solver_set_use_transfer(void* p, int u) { static_cast<SolverBase*>(p)->set_use_transfer(u); }
+int ref_solver_step(void* p, double* y, double* qnorm) { return static_cast<SolverBase*>(p)->step(y, qnorm); }
+void ref_solver_latest_transfer(void* p, double* out) { static_cast<SolverBase*>(p)->latest_transfer(out); }
+void ref_solver_read_ffat_maps(void* p, const char* dir) { static_cast<SolverBase*>(p)->read_maps(dir); }
+int ref_solver_compute_transfer(void* p, const double* pos, double* out) { return static_cast<SolverBase*>(p)->compute_transfer(pos, out); }
+int ref_solver_compute_transfer_enqueue(void* p, const double* pos) { return static_cast<SolverBase*>(p)->compute_transfer_enqueue(pos); }
+
+// FFAT_Map_Serialize::LoadAll (ffat_map_serialize.h:268-279) -> handle; returns the number of maps.
+void* ref_ffat_load_all(const char* dir, int* n_maps) {
+    MapSet* m = Gpu_Wavesolver::FFAT_Map_Serialize::LoadAll(dir);
+    *n_maps = (int)m->size();
+    return m;
+}
+void ref_ffat_free(void* h) { delete static_cast<MapSet*>(h); }
+// out[l*n + i] = |maps.at(i).GetMapVal(pos_l)|  (modal_solver.h:286-315); returns 0 on a missing modeId.
+int ref_ffat_eval(void* h, const double* pos, int L, int use_compressed, double* out) {
+    MapSet& m = *static_cast<MapSet*>(h);
+    const int n = (int)m.size();
+    try {
+        for (int l = 0; l < L; ++l) {
+            Eigen::Matrix<double, 3, 1> p(pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]);
+            for (int i = 0; i < n; ++i) out[(size_t)l * n + i] = std::abs(m.at(i).GetMapVal(p, use_compressed != 0));
+        }
+    } catch (const std::out_of_range&) { return 0; }
+    return 1;
+}
+// Load one file and Save it again with the reference's own code (byte-level round trip of the codec).
+int ref_ffat_load_save(const char* in_file, const char* out_file, int* mode_id, double* k_cell) {
+    Gpu_Wavesolver::FFAT_Map<double, 3> map;
+    Gpu_Wavesolver::FFAT_Map_Serialize::Load(in_file, map);
+    *mode_id = map.modeId;
+    k_cell[0] = map.GetData().size() ? map.GetData()(0, 0) : 0.0;
+    k_cell[1] = (double)map.GetData().rows();
+    k_cell[2] = (double)map.GetData().cols();
+    Gpu_Wavesolver::FFAT_Map_Serialize::Save(out_file, map);
+    return 1;
+}
+// Gpu_Wavesolver::ListDirFiles (io.cpp:18-35): count of entries with the extension (sorted list length).
+int ref_list_dir_files(const char* dir, const char* ext, char* joined, int cap) {
+    std::vector<std::string> names;
+    Gpu_Wavesolver::ListDirFiles(dir, names, ext);
+    std::string j;
+    for (auto& s : names) { j += s; j += '\n'; }
+    if (joined && cap > 0) { std::strncpy(joined, j.c_str(), cap - 1); joined[cap - 1] = 0; }
+    return (int)names.size();
+}
+
+// cfg5-style offline batch with the reference's own classes: one ModalSolver<double,256> +
+// ModalIntegrator per object, a single PointForce at buffer imp_buf[o], sound dequeued after every
+// step and mixed down (the loop tools/real_time_modal_sound.cpp:527-535 runs on its sim thread).
+void ref_batch_render(int n_obj, int N, int n_buf, double h, const double* a, const double* b,
+                      const double* space, const double* trans, const int* imp_buf, double* mix) {
+    const int BUF = 256;
+    for (int o = 0; o < n_obj; ++o) {
+        Vec va, vb; va.resize(N); vb.resize(N);
+        for (int i = 0; i < N; ++i) { va(i) = a[(size_t)o * N + i]; vb(i) = b[(size_t)o * N + i]; }
+        std::shared_ptr<Integ> integ(new Integ(N, h, va, vb));
+        SolverT<BUF> s(N, integ);
+        s.enqueue_trans(trans + (size_t)o * N, N);
+        std::vector<double> y(BUF);
+        for (int bi = 0; bi < n_buf; ++bi) {
+            if (bi == imp_buf[o]) s.enqueue_force(space + (size_t)o * N, 0, 0.0, 0);
+            if (s.step(y.data(), nullptr)) {
+                double* out = mix + (size_t)bi * BUF;
+                for (int i = 0; i < BUF; ++i) out[i] += y[i];
+            }
+        }
+    }
 }
 }

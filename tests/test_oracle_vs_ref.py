@@ -104,3 +104,194 @@ def test_modes_and_material_files_match_reference(orc, ref, tmp_path):
     a, b = orc.build_ab(1.0, np.array([om * om]), 5.0, 3e-8)
     assert a[0] == pytest.approx(2 * xi * om, rel=1e-15)
     assert ref.ref_material_omega_di(5.0, 3e-8, om) == pytest.approx(np.sqrt(b[0] - a[0] ** 2 / 4), rel=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# ModalSolver::step, the FFAT runtime query and the .fatcube loader: the reference's own
+# modal_solver.h / ffat_solver.h / ffat_map_serialize.h / io.cpp compiled in place (third-party
+# includes satisfied by oracle/ref_stubs/).
+def _run_script(s, g, orc):
+    ys, qns, produced = [], [], []
+    for kind, arg in zip(g["kinds"], g["args"]):
+        sp = g["spaces"]
+        if kind == "point": s.enqueue_force(sp[arg], orc.POINT)
+        elif kind == "gauss": s.enqueue_force(sp[arg], orc.GAUSSIAN, width_us=900.0)
+        elif kind == "clear": s.enqueue_force(sp[0], orc.POINT, flags=orc.F_CLEAR)
+        elif kind == "ar_start": s.enqueue_force(sp[arg], orc.AR, flags=orc.F_SUSTAIN_START)
+        elif kind == "ar_data": s.enqueue_force(sp[arg], orc.AR)
+        elif kind == "ar_end": s.enqueue_force(sp[arg], orc.AR, flags=orc.F_SUSTAIN_END)
+        elif kind == "arprm": s.enqueue_arprm(0.7, 0.2, 0.002, 0.1)
+        elif kind == "trans": s.enqueue_trans(g["trans"][arg])
+        elif kind == "unit_transfer": s.set_use_transfer(False)
+        elif kind == "use_transfer": s.set_use_transfer(True)
+        r = s.step()
+        produced.append(r is not None)
+        if r is not None:
+            ys.append(r[0]); qns.append(r[1])
+    return np.array(ys), np.array(qns), produced
+
+
+def test_solver_state_machine_matches_reference(orc, ref, golden_dir):
+    """The force state machine of ModalSolver::step (modal_solver.h:181-276): point / gaussian overlap
+    / clearAllForces / sustained AR start-update-end / transfer swap / unit transfer, buffer by buffer."""
+    import os
+    g = np.load(os.path.join(golden_dir, "script_forces.npz"))
+    y_r, qn_r, prod_r = _run_script(orc.RefSolver(H, g["a"], g["b"], 256), g, orc)
+    y_o, qn_o, prod_o = _run_script(orc.Solver(orc.Integrator(H, g["a"], g["b"]), 256), g, orc)
+    assert prod_r == prod_o == g["produced"].tolist()
+    full = np.max(np.abs(y_r))
+    assert np.max(np.abs(y_o - y_r)) <= 1e-11 * full
+    assert np.max(np.abs(g["y"] - y_r)) <= 1e-11 * full            # the committed golden too
+    assert np.allclose(qn_o, qn_r, rtol=1e-9, atol=1e-11 * np.max(qn_r))
+
+
+@pytest.mark.parametrize("BUF", [64, 513])
+def test_solver_other_buffer_sizes_match_reference(orc, ref, BUF):
+    N = 40
+    mat = synth.MATERIALS["low_damping"]
+    a, b = synth.ab_from_material(synth.mode_frequencies(N, 77), mat)
+    rng = np.random.default_rng(BUF)
+    r = orc.RefSolver(H, a, b, BUF); o = orc.Solver(orc.Integrator(H, a, b), BUF)
+    tr = np.abs(rng.standard_normal(N)) + 0.5
+    for s in (r, o):
+        s.enqueue_trans(tr)
+    for k in range(12):
+        if k in (0, 3, 4):
+            sp = rng.standard_normal(N)
+            for s in (r, o):
+                s.enqueue_force(sp, orc.GAUSSIAN if k == 3 else orc.POINT, width_us=300.0)
+        yr, qr = r.step(); yo, qo = o.step()
+        assert np.max(np.abs(yr - yo)) <= 1e-11 * max(np.max(np.abs(yr)), 1e-300), k
+        assert np.allclose(qr, qo, rtol=1e-9, atol=1e-12 * np.max(qr))
+    assert np.array_equal(r.latest_transfer(), tr) and np.array_equal(o.latest_transfer(), tr)
+
+
+def test_cfg1_golden_waveform_matches_reference(orc, ref, golden_dir):
+    """BASELINE cfg1 (ball.obj, 64 modes, one PointForce, 1 s): the committed golden waveform against
+    the reference's own ModalSolver<double,256>::step."""
+    import os
+    g = np.load(os.path.join(golden_dir, "cfg1_ball.npz"))
+    mat = synth.MATERIALS["low_damping"]
+    w2 = synth.omega_squared(synth.mode_frequencies(64, 1001), mat["density"])
+    a, b = orc.build_ab(mat["density"], w2, mat["alpha"], mat["beta"])
+    s = orc.RefSolver(H, a, b, 256)
+    s.enqueue_trans(g["trans"]); s.enqueue_force(g["space"] * float(g["scale"]))
+    y = np.concatenate([s.step()[0] for _ in range(173)])
+    full = np.max(np.abs(y))
+    assert abs(full / 1e10 - 0.5) < 1e-6
+    assert np.max(np.abs(y - g["y"])) <= 1e-10 * full
+    assert np.linalg.norm(y - g["y"]) <= 1e-10 * np.linalg.norm(y)
+
+
+def _probe_positions(m, seed, n=400):
+    """Listener positions around a map: far field, just outside the box, near edges/corners of the
+    cube, exactly on face axes and on face diagonals (ties in the face selection), and inside."""
+    rng = np.random.default_rng(seed)
+    c = np.asarray(m["center1"]); lo = np.asarray(m["bboxlow"]); hi = np.asarray(m["bboxtop"])
+    R = np.max(hi - lo) / 2
+    d = rng.standard_normal((n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = [c + d * rng.uniform(1.8 * R, 10 * R, (n, 1)), c + d[:50] * 1.74 * R]
+    ax = np.eye(3)
+    for s in (1, -1):
+        for i in range(3):
+            pts.append((c + s * ax[i] * 3 * R)[None])                                  # on a face axis
+            pts.append((c + s * (ax[i] + ax[(i + 1) % 3]) * 3 * R)[None])              # edge tie
+    pts.append((c + np.array([[1, 1, 1], [-1, 1, -1], [1, -1, -1.0]]) * 2.5 * R))        # corner ties
+    pts.append(c + d[:30] * 0.4 * R)                                                     # inside the box
+    return np.concatenate(pts)
+
+
+@pytest.mark.parametrize("sub", ["fatcube", "fatcube_unpacked"])
+def test_ffat_query_matches_reference_on_golden_maps(orc, ref, golden_dir, sub):
+    """LoadAll (ffat_map_serialize.h:268-279) + |GetMapVal| (ffat_solver.h:1180-1206 -> Intersect :676-712,
+    Interpolate :736-803, GetDataQuadStride :141-144, Reconstruct :899-906) on the committed fixtures,
+    packed and unpacked encodings, maps with an off-centre box, k = 0 and modeId = 0."""
+    import os
+    from oracle import fatcube
+    d = os.path.join(golden_dir, sub)
+    maps = [fatcube.load(os.path.join(d, "mode-%d.fatcube" % i)) for i in range(3)]
+    for i, m in enumerate(maps):
+        pos = _probe_positions(m, 900 + i)
+        theirs = orc.ref_ffat_eval(d, pos)
+        assert theirs is not None and theirs.shape == (len(pos), 3)
+        mine = np.stack([orc.ffat_eval([mm], pos)[:, 0] for mm in maps], axis=1)   # maps differ in size
+        fin = np.isfinite(theirs)
+        assert np.array_equal(fin, np.isfinite(mine))                 # k = 0 map: inf / nan in both
+        assert np.array_equal(np.isnan(theirs), np.isnan(mine))
+        assert np.allclose(mine[fin], theirs[fin], rtol=1e-13, atol=0)
+
+
+def test_ffat_query_matches_reference_on_synthetic_maps(orc, ref, tmp_path):
+    """The bench geometry (6 x 32 x 32 texels, half-extent 1.5) written as real .fatcube files."""
+    from oracle import fatcube
+    freqs = synth.mode_frequencies(6, 31)
+    maps = synth.ffat_maps(freqs, 2000)
+    for i, m in enumerate(maps):
+        mm = dict(m); mm["modeid"] = i; mm.setdefault("is_compressed", False)
+        fatcube.save(str(tmp_path / ("m%d.fatcube" % i)), mm)
+    pos = np.concatenate([synth.listeners(500, 5), _probe_positions(maps[0], 6)])
+    theirs = orc.ref_ffat_eval(str(tmp_path), pos)
+    mine = orc.ffat_eval(maps, pos)
+    assert np.allclose(mine, theirs, rtol=1e-13, atol=0)
+    # what differs is FMA contraction (-march=native oracle vs generic _ref): measured 4e-15 worst case
+
+
+def test_ffat_missing_mode_id_is_out_of_range(orc, ref, tmp_path, golden_dir):
+    """computeTransfer indexes maps.at(ii) for ii = 0..N-1 (modal_solver.h:294-297): a gap throws."""
+    import os, shutil
+    for i in (0, 2):
+        shutil.copy(os.path.join(golden_dir, "fatcube", "mode-%d.fatcube" % i), tmp_path)
+    assert orc.ref_ffat_eval(str(tmp_path), np.array([[0.0, 0.0, 5.0]])) is None
+
+
+def test_reference_save_is_canonical_protobuf(orc, ref, golden_dir, tmp_path):
+    """Load then Save with the reference's own serializer reproduces the google.protobuf-encoded file
+    byte for byte (packed fixtures) and canonicalises the unpacked ones to the same bytes."""
+    import os
+    for i in range(3):
+        packed = os.path.join(golden_dir, "fatcube", "mode-%d.fatcube" % i)
+        mid = C.c_int(); info = np.empty(3)
+        for sub in ("fatcube", "fatcube_unpacked"):
+            out = str(tmp_path / ("%s-%d.fatcube" % (sub, i)))
+            ref.ref_ffat_load_save(os.path.join(golden_dir, sub, "mode-%d.fatcube" % i).encode(), out.encode(),
+                                   C.byref(mid), _dp(info))
+            assert mid.value == i and info[2] == 1
+            assert open(out, "rb").read() == open(packed, "rb").read()
+
+
+def test_solver_compute_transfer_matches_reference(orc, ref, golden_dir):
+    """readFFATMaps + computeTransfer(pos, T*) and computeTransfer(pos) -> queue -> next step."""
+    import os
+    from oracle import fatcube
+    d = os.path.join(golden_dir, "fatcube")
+    maps = [fatcube.load(os.path.join(d, "mode-%d.fatcube" % i)) for i in range(3)]
+    a, b = synth.ab_from_material(synth.mode_frequencies(3, 5), synth.MATERIALS["low_damping"])
+    s = orc.RefSolver(H, a, b, 256)
+    pos = np.array([0.3, -4.0, 2.5])
+    assert s.compute_transfer(pos, 3) is None and not s.compute_transfer_enqueue(pos)   # no maps yet
+    s.read_ffat_maps(d)
+    t = s.compute_transfer(pos, 3)
+    mine = np.array([orc.ffat_eval([mm], pos)[0, 0] for mm in maps])
+    fin = np.isfinite(t)
+    assert np.allclose(mine[fin], t[fin], rtol=1e-13, atol=0) and np.array_equal(fin, np.isfinite(mine))
+    assert np.all(s.latest_transfer() == 1e7)                    # TransMessage::setToUnit, modal_solver.h:88-91
+    assert s.compute_transfer_enqueue(pos)
+    assert not s.compute_transfer_enqueue(pos)                   # queue of capacity 1 is full
+    s.step()
+    assert np.array_equal(s.latest_transfer(), t, equal_nan=True)
+
+
+def test_list_dir_files_matches_reference(orc, ref, golden_dir):
+    import os
+    buf = C.create_string_buffer(4096)
+    n = ref.ref_list_dir_files(os.path.join(golden_dir, "fatcube").encode(), b".fatcube", buf, 4096)
+    names = sorted(os.path.basename(x) for x in buf.value.decode().split())
+    assert n == 3 and names == ["mode-0.fatcube", "mode-1.fatcube", "mode-2.fatcube"]   # dot file + .txt skipped
+
+
+def test_offline_batch_matches_reference(orc, ref):
+    """cfg5 in miniature: the oracle's batch loop against one reference ModalSolver per object."""
+    w = synth.batch_workload(5, 96, 24, 5)
+    mine = orc.batch_render(H, w["a"], w["b"], w["space"], w["trans"], w["imp_buf"], 256, 24)
+    theirs = orc.ref_batch_render(H, w["a"], w["b"], w["space"], w["trans"], w["imp_buf"], 24)
+    assert np.max(np.abs(mine - theirs)) <= 1e-11 * np.max(np.abs(theirs))
