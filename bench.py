@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--objects", type=int, default=N_OBJ, help="total objects (default cfg5: 4096)")
     ap.add_argument("--modes", type=int, default=N_MODES)
     ap.add_argument("--buffers", type=int, default=N_BUF)
-    ap.add_argument("--precision", default="f32_tiled", choices=["f32_tiled", "f64"])
+    ap.add_argument("--precision", default="f32_tiled", choices=["f32_tiled", "f64", "tc3x"])
     ap.add_argument("--no-realtime", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -227,7 +227,7 @@ def run_ours(args):
     from openpbso_b200 import synth
     from openpbso_b200.shard import reduce_mix
     pbso.set_device(local)
-    prec = pbso.PREC_F32_TILED if args.precision == "f32_tiled" else pbso.PREC_F64
+    prec = {"f32_tiled": pbso.PREC_F32_TILED, "f64": pbso.PREC_F64, "tc3x": pbso.PREC_TC3X}[args.precision]
 
     lo, hi = shard(args.objects, world, rank)
     n_local = hi - lo

@@ -18,7 +18,7 @@ c_ip = C.POINTER(C.c_int)
 c_vpp = C.POINTER(C.c_void_p)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_FORMAT, ERR_RANGE, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(8)
-PREC_F64, PREC_F32_TILED, PREC_TF32X3 = 0, 1, 2
+PREC_F64, PREC_F32_TILED, PREC_TF32X3, PREC_TC3X = 0, 1, 2, 3
 
 
 class PbsoError(RuntimeError):

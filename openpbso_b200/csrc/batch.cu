@@ -24,6 +24,7 @@
 // Events: CSR by object (ev_off[n_obj+1], ev_buf[], ev_space[n_events][n_modes]).
 // =============================================================================
 #include "common.cuh"
+#include "batch_tc.cuh"
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -41,11 +42,15 @@ struct pbso_batch {
     cudaStream_t own_stream = nullptr;  // the handle's own stream
     double* d_par = nullptr;      // 7 arrays of n_obj*n_modes: lneps, theta, c1, c2, c3, cot, trans
     int* d_ev_off = nullptr; int* d_ev_buf = nullptr; double* d_ev_space = nullptr;
+    int* d_ev_src = nullptr; double* d_ev_stage = nullptr; size_t ev_cap = 0, ev_stage_cap = 0;
     int n_events = 0;
     double* d_mix = nullptr; size_t mix_cap = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int last_launches = 0;
     int sm_count = 148;
+    std::vector<int> h_ev_off, h_ev_buf;      // host copy of the impulse CSR (unit list of the tensor-core path)
+    unsigned trans_ver = 0, ev_ver = 0;
+    TcState* tc = nullptr;
     size_t npm() const { return (size_t)n_obj * n_modes; }
     double* lneps() const { return d_par; }
     double* theta() const { return d_par + npm(); }
@@ -55,6 +60,14 @@ struct pbso_batch {
     double* cot() const { return d_par + 5 * npm(); }
     double* trans() const { return d_par + 6 * npm(); }
 };
+
+// row r of dst = row src[r] of stage (impulse scripts that arrive unsorted)
+__global__ void k_gather_rows(int n_modes, const int* __restrict__ src, const double* __restrict__ stage,
+                              double* __restrict__ dst) {
+    const size_t r = blockIdx.x;
+    const double* in = stage + (size_t)src[r] * n_modes;
+    for (int m = threadIdx.x; m < n_modes; m += blockDim.x) dst[r * n_modes + m] = in[m];
+}
 
 __global__ void k_batch_setup(size_t n, double h, const double* __restrict__ a, const double* __restrict__ b,
                               double* __restrict__ lneps, double* __restrict__ theta, double* __restrict__ c1,
@@ -489,6 +502,16 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
         else if (buf_size == 256) PBSO_LAUNCH_POW(4);
         else return set_error(PBSO_ERR_UNSUPPORTED, "PBSO_PREC_F32_TILED needs buf_size in {64,128,256}; got %d (use PBSO_PREC_F64)", buf_size);
 #undef PBSO_LAUNCH_POW
+    } else if (precision == PBSO_PREC_TC3X) {
+        PBSO_REQUIRE(d_mix && !d_stems, PBSO_ERR_UNSUPPORTED, "PBSO_PREC_TC3X renders the mix only");
+        TcArgs ta{bt->n_obj, bt->n_modes, buf_size, n_buffers, bt->sm_count, bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->trans(),
+                  bt->h_ev_off.data(), bt->h_ev_buf.data(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, bt->n_events,
+                  bt->trans_ver, bt->ev_ver, d_mix, bt->stream};
+        int nl = 0;
+        if (int rc = tc_render(&bt->tc, ta, &nl)) return rc;
+        PBSO_CUDA(cudaEventRecord(bt->e1, bt->stream));
+        bt->last_launches = nl;
+        return PBSO_OK;
     } else if (precision == PBSO_PREC_F64) {
         const int slabs = div_up(bt->n_modes, BF_TPB);
         k_batch_f64<<<bt->n_obj * slabs, BF_TPB, 0, bt->stream>>>(bt->n_modes, slabs, buf_size, n_buffers, bt->c1(),
@@ -537,7 +560,8 @@ int pbso_batch_destroy(pbso_batch* bt) {
     if (!bt) return PBSO_OK;
     DeviceGuard g(bt->device);
     if (bt->stream) cudaStreamSynchronize(bt->stream);
-    cudaFree(bt->d_par); cudaFree(bt->d_ev_off); cudaFree(bt->d_ev_buf); cudaFree(bt->d_ev_space); cudaFree(bt->d_mix);
+    cudaFree(bt->d_par); cudaFree(bt->d_ev_off); cudaFree(bt->d_ev_buf); cudaFree(bt->d_ev_space); cudaFree(bt->d_mix); cudaFree(bt->d_ev_src); cudaFree(bt->d_ev_stage);
+    tc_free(bt->tc);
     if (bt->e0) cudaEventDestroy(bt->e0);
     if (bt->e1) cudaEventDestroy(bt->e1);
     if (bt->own_stream) cudaStreamDestroy(bt->own_stream);
@@ -550,6 +574,7 @@ int pbso_batch_set_transfer(pbso_batch* bt, const double* trans) {
     DeviceGuard g(bt->device);
     PBSO_CUDA(cudaMemcpyAsync(bt->trans(), trans, sizeof(double) * bt->npm(), cudaMemcpyHostToDevice, bt->stream));
     PBSO_CUDA(cudaStreamSynchronize(bt->stream));
+    ++bt->trans_ver;
     return PBSO_OK;
 }
 
@@ -570,23 +595,48 @@ int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const 
         if (obj[order[i]] == obj[order[i - 1]] && buf[order[i]] == buf[order[i - 1]])
             return set_error(PBSO_ERR_INVALID, "object %d has two messages for buffer %d: step() dequeues one per buffer",
                              obj[order[i]], buf[order[i]]);
-    std::vector<int> off(bt->n_obj + 1, 0), sbuf(std::max(n_events, 1));
-    std::vector<double> sspace((size_t)std::max(n_events, 1) * bt->n_modes);
+    std::vector<int> off(bt->n_obj + 1, 0), sbuf(std::max(n_events, 1)), src(std::max(n_events, 1));
+    bool identity = true;
     for (int i = 0; i < n_events; ++i) {
         const int e = order[i];
         off[obj[e] + 1]++;
-        sbuf[i] = buf[e];
-        std::memcpy(&sspace[(size_t)i * bt->n_modes], space + (size_t)e * bt->n_modes, sizeof(double) * bt->n_modes);
+        sbuf[i] = buf[e]; src[i] = e;
+        identity &= (e == i);
     }
     for (int o = 0; o < bt->n_obj; ++o) off[o + 1] += off[o];
+    // device buffers are kept across calls and only grow; the rows of `space` go straight from the
+    // caller's (ideally pinned) memory to the device -- when the events arrive unsorted they are
+    // permuted there, never through a pageable host copy.
+    const size_t rows = (size_t)std::max(n_events, 1);
     PBSO_CUDA(cudaStreamSynchronize(bt->stream));
-    cudaFree(bt->d_ev_off); cudaFree(bt->d_ev_buf); cudaFree(bt->d_ev_space);
-    PBSO_CUDA(cudaMalloc(&bt->d_ev_off, sizeof(int) * off.size()));
-    PBSO_CUDA(cudaMalloc(&bt->d_ev_buf, sizeof(int) * sbuf.size()));
-    PBSO_CUDA(cudaMalloc(&bt->d_ev_space, sizeof(double) * sspace.size()));
-    PBSO_CUDA(cudaMemcpy(bt->d_ev_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
-    PBSO_CUDA(cudaMemcpy(bt->d_ev_buf, sbuf.data(), sizeof(int) * sbuf.size(), cudaMemcpyHostToDevice));
-    PBSO_CUDA(cudaMemcpy(bt->d_ev_space, sspace.data(), sizeof(double) * sspace.size(), cudaMemcpyHostToDevice));
+    if (!bt->d_ev_off) PBSO_CUDA(cudaMalloc(&bt->d_ev_off, sizeof(int) * off.size()));
+    if (rows > bt->ev_cap) {
+        cudaFree(bt->d_ev_buf); cudaFree(bt->d_ev_space); cudaFree(bt->d_ev_src);
+        bt->d_ev_buf = nullptr; bt->d_ev_space = nullptr; bt->d_ev_src = nullptr; bt->ev_cap = 0;
+        PBSO_CUDA(cudaMalloc(&bt->d_ev_buf, sizeof(int) * rows));
+        PBSO_CUDA(cudaMalloc(&bt->d_ev_src, sizeof(int) * rows));
+        PBSO_CUDA(cudaMalloc(&bt->d_ev_space, sizeof(double) * rows * bt->n_modes));
+        bt->ev_cap = rows;
+    }
+    PBSO_CUDA(cudaMemcpyAsync(bt->d_ev_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, bt->stream));
+    PBSO_CUDA(cudaMemcpyAsync(bt->d_ev_buf, sbuf.data(), sizeof(int) * sbuf.size(), cudaMemcpyHostToDevice, bt->stream));
+    if (n_events > 0) {
+        const size_t bytes = sizeof(double) * (size_t)n_events * bt->n_modes;
+        if (identity) {
+            PBSO_CUDA(cudaMemcpyAsync(bt->d_ev_space, space, bytes, cudaMemcpyHostToDevice, bt->stream));
+        } else {
+            if ((size_t)n_events > bt->ev_stage_cap) {
+                cudaFree(bt->d_ev_stage); bt->d_ev_stage = nullptr; bt->ev_stage_cap = 0;
+                PBSO_CUDA(cudaMalloc(&bt->d_ev_stage, bytes)); bt->ev_stage_cap = n_events;
+            }
+            PBSO_CUDA(cudaMemcpyAsync(bt->d_ev_stage, space, bytes, cudaMemcpyHostToDevice, bt->stream));
+            PBSO_CUDA(cudaMemcpyAsync(bt->d_ev_src, src.data(), sizeof(int) * n_events, cudaMemcpyHostToDevice, bt->stream));
+            k_gather_rows<<<n_events, 256, 0, bt->stream>>>(bt->n_modes, bt->d_ev_src, bt->d_ev_stage, bt->d_ev_space);
+            PBSO_CUDA(cudaGetLastError());
+        }
+    }
+    PBSO_CUDA(cudaStreamSynchronize(bt->stream));      // the caller may reuse its buffers on return
+    bt->h_ev_off = off; bt->h_ev_buf.assign(sbuf.begin(), sbuf.begin() + n_events); ++bt->ev_ver;
     bt->n_events = n_events;
     return PBSO_OK;
 }

@@ -1,0 +1,23 @@
+// Interface between batch.cu (handle, impulse script, C ABI) and batch_tc.cu (tensor-core render).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pbso {
+
+struct TcState;      // device tables / unit list cached across renders, owned by a pbso_batch
+
+struct TcArgs {
+    int n_obj, n_modes, buf_size, n_buffers, sm_count;
+    const double *lneps, *theta, *c3, *cot, *trans;            // [n_obj][n_modes], device
+    const int *h_ev_off, *h_ev_buf;                            // impulse CSR, host copy
+    const int *d_ev_off, *d_ev_buf; const double* d_ev_space;  // impulse CSR, device
+    int n_events;
+    unsigned trans_ver, ev_ver;                                // bumped by set_transfer / set_impulses
+    double* d_mix;                                             // zeroed by the caller
+    cudaStream_t stream;
+};
+
+int tc_render(TcState** st, const TcArgs& a, int* launches);
+void tc_free(TcState* st);
+
+}  // namespace pbso

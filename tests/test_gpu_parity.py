@@ -393,3 +393,69 @@ def test_batch_full_size_slice_f32_vs_f64(pbso):
     ys = br.render_mix(256, n_buf, pbso.PREC_F32_TILED)
     assert np.max(np.abs(ys[5 * 256:] - y32[:-5 * 256])) <= 2e-6 * np.max(np.abs(y32))
     assert not ys[:5 * 256 + int(w["imp_buf"].min()) * 256].any()
+
+
+# --------------------------------------------------------------------------- K1 batch on tensor cores (3xTF32)
+@pytest.mark.parametrize("n_obj,n_modes,n_buf,material", [(5, 80, 24, "low_damping"), (3, 300, 12, "high_damping"),
+                                                           (2, 16, 150, "low_damping"), (7, 33, 70, "high_damping")])
+def test_batch_tc3x_vs_oracle(pbso, orc, n_obj, n_modes, n_buf, material):
+    """Pole-power synthesis as one tcgen05 contraction (batch_tc.cu) against the CPU oracle: ragged mode counts
+    (not a multiple of the 16-mode K chunk), renders shorter and longer than one 128-tile M-tile."""
+    w = _batch_case(n_obj, n_modes, n_buf, 11, material)
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"])
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], w["space"])
+    ref = orc.batch_render(H, w["a"], w["b"], w["space"], w["trans"], w["imp_buf"], 256, n_buf)
+    mix = br.render_mix(256, n_buf, pbso.PREC_TC3X)
+    rel, mx = assert_waveform_parity(mix, ref)
+    print("tc3x: rel-L2 %.2e max-abs %.2e" % (rel, mx))
+
+
+def test_batch_tc3x_many_events(pbso):
+    """Impulse streams (several impulses per object, some in the same M-tile, unsorted input) against the FP64
+    direct-form kernel; re-render after changing the script and the transfer (cached tables must follow)."""
+    n_obj, n_modes, n_buf = 3, 200, 400
+    w = synth.batch_workload(n_obj, n_modes, n_buf, 21, "high_damping")
+    rng = np.random.default_rng(21)
+    obj = np.repeat(np.arange(n_obj), 40)
+    buf = np.concatenate([rng.choice(n_buf, 40, replace=False) for _ in range(n_obj)])
+    space = rng.standard_normal((len(obj), n_modes))
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"]); br.set_impulses(obj, buf, space)
+    y64 = br.render_mix(256, n_buf, pbso.PREC_F64)
+    ytc = br.render_mix(256, n_buf, pbso.PREC_TC3X)
+    assert_waveform_parity(ytc, y64)
+    br.set_impulses(obj[::3], buf[::3], space[::3]); br.set_transfer(2.0 * w["trans"])
+    assert_waveform_parity(br.render_mix(256, n_buf, pbso.PREC_TC3X), br.render_mix(256, n_buf, pbso.PREC_F64))
+    assert_waveform_parity(br.render_mix(128, 2 * n_buf - 3, pbso.PREC_TC3X), br.render_mix(128, 2 * n_buf - 3, pbso.PREC_F64))
+    with pytest.raises(pbso.PbsoError):
+        br.render_mix(64, n_buf, pbso.PREC_TC3X)              # buf_size must be a multiple of the 128-sample tile
+
+
+def test_batch_tc3x_cfg1_golden(pbso, golden_dir):
+    g = np.load(os.path.join(golden_dir, "cfg1_ball.npz"))
+    a, b = synth.ab_from_material(synth.mode_frequencies(64, 1001), synth.MATERIALS["low_damping"])
+    br = pbso.BatchRenderer(H, a[None, :], b[None, :])
+    br.set_transfer(g["trans"][None, :])
+    br.set_impulses([0], [0], (g["space"] * g["scale"])[None, :])
+    rel, mx = assert_waveform_parity(br.render_mix(256, 173, pbso.PREC_TC3X), g["y"])
+    print("tc3x cfg1: rel-L2 %.2e max-abs %.2e" % (rel, mx))
+
+
+def test_batch_tc3x_full_size_slice(pbso):
+    """cfg5 slice at full length (512 modes x 10 s) against the FP64 kernel, plus linearity and time shift."""
+    n_obj, n_modes, n_buf = 48, 512, 1723
+    w = synth.batch_workload(n_obj, n_modes, n_buf, 1005)
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"])
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], w["space"])
+    y64 = br.render_mix(256, n_buf, pbso.PREC_F64)
+    ytc = br.render_mix(256, n_buf, pbso.PREC_TC3X)
+    rel, mx = assert_waveform_parity(ytc, y64)
+    print("cfg5 slice: tc3x vs f64 rel-L2 %.2e max-abs %.2e" % (rel, mx))
+    tail = slice(-44100, None)
+    assert np.linalg.norm(ytc[tail] - y64[tail]) <= 1e-5 * np.linalg.norm(y64[tail])
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], 2.0 * w["space"])
+    y2 = br.render_mix(256, n_buf, pbso.PREC_TC3X)
+    assert np.max(np.abs(y2 - 2.0 * ytc)) <= 2e-6 * np.max(np.abs(y2))
+    br.set_impulses(np.arange(n_obj), w["imp_buf"] + 5, w["space"])
+    ys = br.render_mix(256, n_buf, pbso.PREC_TC3X)
+    assert np.max(np.abs(ys[5 * 256:] - ytc[:-5 * 256])) <= 2e-6 * np.max(np.abs(ytc))
+    assert not ys[:5 * 256 + int(w["imp_buf"].min()) * 256].any()
