@@ -53,10 +53,7 @@ namespace {
 constexpr int TCB_L = 128;                 // samples per tile = N of the MMA
 constexpr int TCB_ROWS = 128;              // tiles per M-tile = M of the MMA
 constexpr int TCB_KMODES = 16;             // modes per K chunk (K = 32 fp32 = one 128-byte swizzle row)
-constexpr int TCB_STAGES = 3;
 constexpr int TCB_TILE_BYTES = 128 * 32 * 4;
-constexpr int TCB_STAGE_BYTES = 4 * TCB_TILE_BYTES;
-constexpr int TCB_SMEM_BYTES = TCB_STAGES * TCB_STAGE_BYTES + 1024 + 256;
 constexpr int TCB_THREADS = 512;
 constexpr int TCB_TMEM_COLS = 512;         // main[2] | small[2], 128 columns each
 constexpr int TCB_FLUSH_UNITS = 4;         // units between FP64 flushes of the register accumulators
@@ -79,7 +76,9 @@ __device__ __forceinline__ Cplx cmul(const Cplx a, const Cplx b) {
 
 // ---- static per-(object, mode) tables of pole powers, FP64-computed, rounded once to FP32 --------------------
 // tab[i][0..7] = P^(16 blk) (x T for operand B), [8..10] = P^4, P^8, P^12, [11..13] = P, P^2, P^3 with
-// P = w^L (operand A: tile-to-tile) or w (operand B: sample-to-sample).
+// P = w^L (operand A: tile-to-tile) or w (operand B: sample-to-sample).  Operand B holds (Im, Re) = i conj(z) in
+// its K columns; i conj(z1 z2) = (i conj z1) conj(z2), so tabB stores the block starts swapped and the step
+// powers conjugated and the generator runs the same recurrence for both operands.
 __device__ __forceinline__ float2 pole_pow(double le, double th, double k, double scale) {
     double s, c;
     sincos(k * th, &s, &c);
@@ -95,12 +94,14 @@ __global__ void k_tc_tables(size_t n, const double* __restrict__ lneps, const do
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         ta[a] = pole_pow(le, th, 16.0 * a * TCB_L, 1.0);
-        tb[a] = pole_pow(le, th, 16.0 * a, T);
+        { const float2 z = pole_pow(le, th, 16.0 * a, T); tb[a] = make_float2(z.y, z.x); }
     }
 #pragma unroll
     for (int t = 1; t < 4; ++t) {
-        ta[7 + t] = pole_pow(le, th, 4.0 * t * TCB_L, 1.0);  tb[7 + t] = pole_pow(le, th, 4.0 * t, 1.0);
-        ta[10 + t] = pole_pow(le, th, (double)t * TCB_L, 1.0); tb[10 + t] = pole_pow(le, th, (double)t, 1.0);
+        ta[7 + t] = pole_pow(le, th, 4.0 * t * TCB_L, 1.0);
+        ta[10 + t] = pole_pow(le, th, (double)t * TCB_L, 1.0);
+        { const float2 z = pole_pow(le, th, 4.0 * t, 1.0); tb[7 + t] = make_float2(z.x, -z.y); }
+        { const float2 z = pole_pow(le, th, (double)t, 1.0); tb[10 + t] = make_float2(z.x, -z.y); }
     }
     ta[14] = ta[15] = tb[14] = tb[15] = make_float2(0.f, 0.f);
 }
@@ -149,15 +150,16 @@ typedef unsigned long long c32;                                          // pack
 __device__ __forceinline__ c32 pk(float re, float im) { c32 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(re), "f"(im)); return r; }
 __device__ __forceinline__ void upk(c32 v, float& re, float& im) { asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(v)); }
 __device__ __forceinline__ c32 pk2(float2 v) { return pk(v.x, v.y); }
-// p * q with q given as qa = (qr, qi) and qb = (qi, qr):  (pr qr - pi qi, pr qi + pi qr)
-__device__ __forceinline__ c32 cmulf(c32 p, c32 qa, c32 qb) {
+// p * q = pr (qr, qi) + pi (-qi, qr): q is passed with its rotation qrot = i q = (-qi, qr) so that both packed
+// instructions take p's components as broadcast scalars (no register-pair shuffling in the inner loops).
+__device__ __forceinline__ c32 cmulf(c32 p, c32 q, c32 qrot) {
     float pr, pi; upk(p, pr, pi);
-    const c32 pa = pk(pr, pr), pb = pk(-pi, pi);
+    const c32 pa = pk(pr, pr), pb = pk(pi, pi);
     c32 r;
-    asm("{\n\t.reg .b64 t;\n\tmul.rn.f32x2 t, %1, %2;\n\tfma.rn.f32x2 %0, %3, %4, t;\n\t}" : "=l"(r) : "l"(pa), "l"(qa), "l"(pb), "l"(qb));
+    asm("{\n\t.reg .b64 t;\n\tmul.rn.f32x2 t, %1, %2;\n\tfma.rn.f32x2 %0, %3, %4, t;\n\t}" : "=l"(r) : "l"(pa), "l"(q), "l"(pb), "l"(qrot));
     return r;
 }
-__device__ __forceinline__ c32 swp(c32 v) { float a, b; upk(v, a, b); return pk(b, a); }
+__device__ __forceinline__ c32 rot(c32 v) { float a, b; upk(v, a, b); return pk(-b, a); }
 
 template <int SPLIT>
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi_bits, uint32_t& lo_bits) {
@@ -178,47 +180,67 @@ __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
 }
 // row b of the thread's 16-row block, K columns (2 m_l, 2 m_l + 1):
 // byte offset (r/8)*1024 + (r%8)*128 + (((m_l/2) ^ (r%8)) * 16) + (m_l%2)*8 with r = 16 blk + b
-template <int SPLIT, bool kSwap>
+template <int SPLIT>
 __device__ __forceinline__ void store_row(uint32_t tile_hi, uint32_t tile_lo, uint32_t base, int b, c32 v) {
     float re, im; upk(v, re, im);
     uint32_t h0, l0, h1, l1;
-    split_tf32<SPLIT>(kSwap ? im : re, h0, l0);
-    split_tf32<SPLIT>(kSwap ? re : im, h1, l1);
+    split_tf32<SPLIT>(re, h0, l0);
+    split_tf32<SPLIT>(im, h1, l1);
     const uint32_t off = (base ^ ((uint32_t)(b & 7) * 16u)) + (uint32_t)(b >> 3) * 1024u + (uint32_t)(b & 7) * 128u;
     sts_v2(tile_hi + off, h0, h1);
     sts_v2(tile_lo + off, l0, l1);
 }
 
 // Fast path: rows 4t + c = x * Rt[t] * Rc[c]  (Rt[0] = Rc[0] = 1).  t123 / c123 hold entries 8..13 of the table.
-template <int SPLIT, bool kSwap>
+template <int SPLIT>
 __device__ __forceinline__ void gen_block(uint32_t tile_hi, uint32_t tile_lo, int blk, int m_l, c32 x, const c32 (&rt)[3], const c32 (&rc)[3]) {
     const uint32_t base = (uint32_t)blk * 2048u + (uint32_t)(m_l >> 1) * 16u + (uint32_t)(m_l & 1) * 8u;
-    const c32 rcs[3] = {swp(rc[0]), swp(rc[1]), swp(rc[2])};
+    const c32 rcs[3] = {rot(rc[0]), rot(rc[1]), rot(rc[2])};   // i rc
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        const c32 pt = t == 0 ? x : cmulf(x, rt[t - 1], swp(rt[t - 1]));
-        store_row<SPLIT, kSwap>(tile_hi, tile_lo, base, 4 * t, pt);
+        const c32 pt = t == 0 ? x : cmulf(x, rt[t - 1], rot(rt[t - 1]));
+        store_row<SPLIT>(tile_hi, tile_lo, base, 4 * t, pt);
 #pragma unroll
-        for (int c = 1; c < 4; ++c) store_row<SPLIT, kSwap>(tile_hi, tile_lo, base, 4 * t + c, cmulf(pt, rc[c - 1], rcs[c - 1]));
+        for (int c = 1; c < 4; ++c) store_row<SPLIT>(tile_hi, tile_lo, base, 4 * t + c, cmulf(pt, rc[c - 1], rcs[c - 1]));
     }
 }
 
-// General form (impulse units): row j = x * P^(j - shift) for j >= shift, zero before; x = 0 gives a zero block.
-template <int SPLIT>
-__device__ __forceinline__ void gen_block_from(uint32_t tile_hi, uint32_t tile_lo, int blk, int m_l, c32 x, const float2* __restrict__ tab, int shift) {
-    const uint32_t base = (uint32_t)blk * 2048u + (uint32_t)(m_l >> 1) * 16u + (uint32_t)(m_l & 1) * 8u;
-#pragma unroll 1
-    for (int j = 0; j < 16; ++j) {
-        c32 v = pk(0.f, 0.f);
-        const int e = j - shift;
-        if (e >= 0) {
-            v = x;
-            if (e >> 2) { const c32 q = pk2(__ldg(&tab[7 + (e >> 2)])); v = cmulf(v, q, swp(q)); }
-            if (e & 3) { const c32 q = pk2(__ldg(&tab[10 + (e & 3)])); v = cmulf(v, q, swp(q)); }
-        }
-        store_row<SPLIT, false>(tile_hi, tile_lo, base, j, v);
-    }
+// A operand from TMEM, B from shared memory:  D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// 32 lanes x 32 consecutive TMEM columns <- 32 registers per thread (thread = lane of the warp's quarter)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Shared-memory map of k_batch_tc: B stages (B_hi | B_lo, 16 KB each), seed ring, barriers.
+// TMEM map (512 columns): main[0] 0..127, main[1] 128..255, small 256..383, A stage s at 384 + 64 s (hi 32 | lo 32).
+constexpr int TCB_BSTAGES = 4, TCB_ASTAGES = 2, TCB_SEEDS = 4;
+constexpr int TCB_BSTAGE_BYTES = 2 * TCB_TILE_BYTES;
+constexpr int TCB_RROW = 18 * 8;                                      // R row: 16 powers, a zero entry, pad (16-byte aligned)
+constexpr int TCB_SEED_BYTES = TCB_KMODES * 64 + TCB_KMODES * TCB_RROW;   // X[16 modes][8 blk] then R[16 modes][18], float2
+constexpr int TCB_SMEM_TS = TCB_BSTAGES * TCB_BSTAGE_BYTES + TCB_SEEDS * TCB_SEED_BYTES + 1024 + 512;
+constexpr int TCB_SMALL_CHAIN = 8;                                   // chunks per small-accumulator chain
 
 template <int SPLIT, int CHAIN>
 __global__ void __launch_bounds__(TCB_THREADS, 1)
@@ -226,13 +248,22 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
            const float2* __restrict__ tabA, const float2* __restrict__ tabB, const float2* __restrict__ Vbase,
            const double* __restrict__ c3a, const double* __restrict__ cota, const int* __restrict__ ev_row,
            const double* __restrict__ ev_space, double* __restrict__ mix, int flush_units) {
+    static_assert(TCB_SMALL_CHAIN % CHAIN == 0, "small chains end on main chain ends");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = (uint64_t*)(smem + TCB_STAGES * TCB_STAGE_BYTES);
-    uint64_t* empty = full + TCB_STAGES;
-    uint64_t* acc_full = empty + TCB_STAGES;       // [2]
-    uint64_t* acc_empty = acc_full + 2;            // [2]
-    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    uint8_t* seeds = smem + TCB_BSTAGES * TCB_BSTAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(seeds + TCB_SEEDS * TCB_SEED_BYTES);
+    uint64_t* b_full = bars;                       // [4]  B stage written (4 generator warps)
+    uint64_t* b_empty = b_full + TCB_BSTAGES;      // [4]  MMAs reading it retired
+    uint64_t* a_full = b_empty + TCB_BSTAGES;      // [2]  A stage stored to TMEM (4 generator warps)
+    uint64_t* a_empty = a_full + TCB_ASTAGES;      // [2]
+    uint64_t* seed_full = a_empty + TCB_ASTAGES;   // [4]  seeds of a chunk written (1 seed warp)
+    uint64_t* seed_empty = seed_full + TCB_SEEDS;  // [4]  consumed (4 A-generator warps)
+    uint64_t* acc_full = seed_empty + TCB_SEEDS;   // [2]  main accumulator chain finished
+    uint64_t* acc_empty = acc_full + 2;            // [2]  drained (128 epilogue threads)
+    uint64_t* small_full = acc_empty + 2;          // [1]
+    uint64_t* small_empty = small_full + 1;        // [1]
+    uint32_t* tmem_slot = (uint32_t*)(small_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // this CTA's contiguous range of units (sorted by M-tile; ranges of equal estimated cost, built on the host)
@@ -241,8 +272,11 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
     const size_t npm = (size_t)n_obj * n_modes;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TCB_STAGES; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TCB_BSTAGES; ++s) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < TCB_ASTAGES; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < TCB_SEEDS; ++s) { mbar_init(&seed_full[s], 1); mbar_init(&seed_empty[s], 4); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        mbar_init(small_full, 1); mbar_init(small_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -253,81 +287,173 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t n_chunks_total = (uint32_t)(u1 - u0) * (uint32_t)cpu;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         if (warp == 0) {
             // ---------------- MMA issuer ----------------
             // The whole warp runs the loop so that every operand stays warp-uniform (uniform registers feed
-            // UTCHMMA directly); one elected lane issues.  Descriptors differ only in their 14-bit address field:
-            // stage base + tile offset (16 KB -> +1024) + k step (32 B -> +2).
+            // UTCHMMA directly); one elected lane issues.  B descriptors differ only in their 14-bit address field:
+            // stage base + tile offset (16 KB -> +1024) + k step (32 B -> +2); A is a TMEM column address.
             constexpr uint32_t idesc = umma_idesc_tf32(TCB_ROWS, TCB_L);
             const uint64_t desc0 = umma_desc_k_sw128(smem_u32(smem));
-            uint32_t q = 0, g = 0;                                     // stage counter, chain counter
-            const uint32_t n_chunks_total = (uint32_t)(u1 - u0) * (uint32_t)cpu;
+            uint32_t g = 0, gs = 0;                                    // main / small chain counters
             int ch = 0;
-            for (uint32_t qq = 0; qq < n_chunks_total; ++qq, ++q) {
-                const uint32_t s = q % TCB_STAGES;
-                const uint32_t ph = (q / TCB_STAGES) & 1;
+            for (uint32_t q = 0; q < n_chunks_total; ++q) {
+                const uint32_t sa = q % TCB_ASTAGES, pha = (q / TCB_ASTAGES) & 1;
+                const uint32_t sb = q % TCB_BSTAGES, phb = (q / TCB_BSTAGES) & 1;
                 const uint32_t buf = g & 1;
-                const bool chain_start = (ch % CHAIN) == 0;
-                const bool chain_end = (ch % CHAIN) == CHAIN - 1 || ch == cpu - 1;
+                const bool chain_start = (ch % CHAIN) == 0, chain_end = (ch % CHAIN) == CHAIN - 1 || ch == cpu - 1;
+                const bool small_start = (ch % TCB_SMALL_CHAIN) == 0, small_end = (ch % TCB_SMALL_CHAIN) == TCB_SMALL_CHAIN - 1 || ch == cpu - 1;
                 if (chain_start) mbar_wait(&acc_empty[buf], ((g >> 1) & 1) ^ 1);
-                mbar_wait(&full[s], ph);
+                if (small_start) mbar_wait(small_empty, (gs & 1) ^ 1);
+                mbar_wait(&a_full[sa], pha);
+                mbar_wait(&b_full[sb], phb);
                 tcgen05_fence_after();
                 if (elect_one()) {
-                    const uint32_t acc_main = tmem_base + buf * TCB_L;
-                    const uint32_t acc_small = tmem_base + 256 + buf * TCB_L;
-                    const uint64_t dA = desc0 + (uint64_t)(s * (TCB_STAGE_BYTES >> 4));
+                    const uint32_t acc_main = tmem_base + buf * TCB_L, acc_small = tmem_base + 256;
+                    const uint32_t a_hi = tmem_base + 384 + sa * 64, a_lo = a_hi + 32;
+                    const uint64_t dB = desc0 + (uint64_t)(sb * (TCB_BSTAGE_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t dAh = dA + 2 * k, dAl = dAh + (TCB_TILE_BYTES >> 4);
-                        const uint64_t dBh = dAh + 2 * (TCB_TILE_BYTES >> 4), dBl = dAh + 3 * (TCB_TILE_BYTES >> 4);
-                        const uint32_t accf = (chain_start && k == 0) ? 0u : 1u;
-                        umma_tf32(acc_main, dAh, dBh, idesc, accf);
-                        umma_tf32(acc_small, dAh, dBl, idesc, accf);
-                        umma_tf32(acc_small, dAl, dBh, idesc, 1u);
+                        const uint64_t dBh = dB + 2 * k, dBl = dBh + (TCB_TILE_BYTES >> 4);
+                        umma_tf32_ts(acc_main, a_hi + 8 * k, dBh, idesc, (chain_start && k == 0) ? 0u : 1u);
+                        umma_tf32_ts(acc_small, a_hi + 8 * k, dBl, idesc, (small_start && k == 0) ? 0u : 1u);
+                        umma_tf32_ts(acc_small, a_lo + 8 * k, dBh, idesc, 1u);
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&a_empty[sa]);
+                    umma_commit(&b_empty[sb]);
                     if (chain_end) umma_commit(&acc_full[buf]);
+                    if (small_end) umma_commit(small_full);
                 }
                 __syncwarp();
                 if (chain_end) ++g;
+                if (small_end) ++gs;
                 if (++ch == cpu) ch = 0;
+            }
+        } else if (warp <= 2) {
+            // ---------------- seed warps (chunks alternate between warps 1 and 2) ----------------
+            // lanes 0-15: X[m][blk] = v_base * W^(16 blk), the state at the start of each 16-row block;
+            // lanes 16-31: R[m][j] = W^j = W^(4t) W^c for the 16 rows of a block.
+            const int m_l = lane & 15, half = lane >> 4;
+            for (uint32_t q = warp - 1; q < n_chunks_total; q += 2) {
+                const int u = u0 + (int)(q / cpu), ch = (int)(q % cpu);
+                const Unit un = units[u];
+                const int m = ch * TCB_KMODES + m_l;
+                const bool valid = m < n_modes;
+                const size_t idx = (size_t)un.obj * n_modes + (valid ? m : 0);
+                const float4* t4 = reinterpret_cast<const float4*>(tabA + idx * 16);
+                float2 out[16];
+                if (half == 0) {
+                    const float4 r0 = __ldg(t4), r1 = __ldg(t4 + 1), r2 = __ldg(t4 + 2), r3 = __ldg(t4 + 3);
+                    const c32 ra[8] = {pk(r0.x, r0.y), pk(r0.z, r0.w), pk(r1.x, r1.y), pk(r1.z, r1.w),
+                                       pk(r2.x, r2.y), pk(r2.z, r2.w), pk(r3.x, r3.y), pk(r3.z, r3.w)};
+                    if (un.ev < 0) {
+                        const c32 vb = valid ? pk2(__ldg(&Vbase[(size_t)un.it * npm + idx])) : pk(0.f, 0.f);
+#pragma unroll
+                        for (int blk = 0; blk < 8; ++blk) { float a, b; upk(cmulf(vb, ra[blk], rot(ra[blk])), a, b); out[blk] = make_float2(a, b); }
+                    } else {
+                        // impulse unit: zero before the impulse row `re`; block ae starts AT the impulse (rows are
+                        // shifted by be in the row threads); later blocks start at u W^(16 (blk - ae) - be)
+                        const int re = ev_row[un.ev] - un.it * TCB_ROWS, ae = re >> 4, be = re & 15;
+                        const double inji = c3a[idx], injr = inji * cota[idx];
+                        const double sp = valid ? ev_space[(size_t)un.ev * n_modes + m] : 0.0;
+                        const c32 uimp = pk((float)(sp * injr), (float)(sp * inji));
+                        const float2* tab = tabA + idx * 16;
+#pragma unroll
+                        for (int blk = 0; blk < 8; ++blk) {
+                            c32 x = pk(0.f, 0.f);
+                            if (blk == ae) x = uimp;
+                            else if (blk > ae) {
+                                const int d = 16 * (blk - ae) - be;
+                                x = uimp;
+                                if (d >> 4) { const c32 qq = pk2(__ldg(&tab[d >> 4])); x = cmulf(x, qq, rot(qq)); }
+                                if ((d >> 2) & 3) { const c32 qq = pk2(__ldg(&tab[7 + ((d >> 2) & 3)])); x = cmulf(x, qq, rot(qq)); }
+                                if (d & 3) { const c32 qq = pk2(__ldg(&tab[10 + (d & 3)])); x = cmulf(x, qq, rot(qq)); }
+                            }
+                            float a, b; upk(x, a, b); out[blk] = make_float2(a, b);
+                        }
+                    }
+                } else {
+                    const float4 q0 = __ldg(t4 + 4), q1 = __ldg(t4 + 5), q2 = __ldg(t4 + 6);
+                    const c32 rt[4] = {pk(1.f, 0.f), pk(q0.x, q0.y), pk(q0.z, q0.w), pk(q1.x, q1.y)};
+                    const c32 rc[4] = {pk(1.f, 0.f), pk(q1.z, q1.w), pk(q2.x, q2.y), pk(q2.z, q2.w)};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const c32 v = (t == 0) ? rc[c] : (c == 0 ? rt[t] : cmulf(rt[t], rc[c], rot(rc[c])));
+                            float a, b; upk(v, a, b); out[4 * t + c] = make_float2(a, b);
+                        }
+                }
+                const uint32_t slot = q % TCB_SEEDS;
+                mbar_wait(&seed_empty[slot], ((q / TCB_SEEDS) & 1) ^ 1);
+                const uint32_t sbase = smem_u32(seeds) + slot * TCB_SEED_BYTES;
+                if (half == 0) {
+                    const uint32_t dst = sbase + m_l * 64;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sts_v4(dst + 16 * i, out[2 * i].x, out[2 * i].y, out[2 * i + 1].x, out[2 * i + 1].y);
+                } else {
+                    const uint32_t dst = sbase + TCB_KMODES * 64 + m_l * TCB_RROW;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sts_v4(dst + 16 * i, out[2 * i].x, out[2 * i].y, out[2 * i + 1].x, out[2 * i + 1].y);
+                    sts_v4(dst + 128, 0.f, 0.f, 0.f, 0.f);             // R[m][16] = 0: rows before an impulse
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&seed_full[slot]);
             }
         }
     } else if (warp < 8) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-        // ---------------- epilogue: promote finished chains into registers, flush per M-tile ----------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        // ---------------- epilogue: promote finished chains into registers, flush to the FP64 mix ----------------
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         float acc[TCB_L];
 #pragma unroll
         for (int j = 0; j < TCB_L; ++j) acc[j] = 0.f;
-        uint32_t g = 0;
+        uint32_t g = 0, gs = 0;
         int since_flush = 0;
         // mean of the tensor core's accumulate-with-truncation (2.5e-8 per main MMA of a chain, measured) and, when
         // lo is not re-centred (SPLIT < 2), of the dropped lo*lo term
         const double gain = 1.0 + 1.0e-7 * CHAIN + (SPLIT == 2 ? 0.0 : 0.6e-7);
-        const int chains_per_unit = (cpu + CHAIN - 1) / CHAIN;
         for (int u = u0; u < u1; ++u) {
             const int it = units[u].it;
-            for (int c = 0; c < chains_per_unit; ++c, ++g) {
-                const int buf = g & 1;
-                mbar_wait(&acc_full[buf], (g >> 1) & 1);
-                tcgen05_fence_after();
+            for (int ch = 0; ch < cpu; ++ch) {
+                const bool chain_end = (ch % CHAIN) == CHAIN - 1 || ch == cpu - 1;
+                const bool small_end = (ch % TCB_SMALL_CHAIN) == TCB_SMALL_CHAIN - 1 || ch == cpu - 1;
+                if (chain_end) {
+                    const int buf = g & 1;
+                    mbar_wait(&acc_full[buf], (g >> 1) & 1);
+                    tcgen05_fence_after();
 #pragma unroll
-                for (int qd = 0; qd < TCB_L / 32; ++qd) {
-                    uint32_t vm[32], vs[32];
-                    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-                    tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), vm);
-                    tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(256 + buf * TCB_L + qd * 32), vs);
-                    tmem_ld_wait();
+                    for (int qd = 0; qd < TCB_L / 32; ++qd) {
+                        uint32_t vm[32];
+                        tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), vm);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[qd * 32 + j] += __uint_as_float(vm[j]) + __uint_as_float(vs[j]);
+                        for (int j = 0; j < 32; ++j) acc[qd * 32 + j] += __uint_as_float(vm[j]);
+                    }
+                    tcgen05_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                    ++g;
                 }
-                tcgen05_fence_before();
-                mbar_arrive(&acc_empty[buf]);
+                if (small_end) {
+                    mbar_wait(small_full, gs & 1);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int qd = 0; qd < TCB_L / 32; ++qd) {
+                        uint32_t vs[32];
+                        tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(256 + qd * 32), vs);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[qd * 32 + j] += __uint_as_float(vs[j]);
+                    }
+                    tcgen05_fence_before();
+                    mbar_arrive(small_empty);
+                    ++gs;
+                }
             }
             ++since_flush;
             const bool flush = (u + 1 == u1) || (units[u + 1].it != it) || since_flush >= flush_units;
@@ -343,74 +469,76 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                 for (int j = 0; j < TCB_L; ++j) acc[j] = 0.f;
             }
         }
-    } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
-        // ---------------- generators: warps 8-11 -> A (tile-start states), warps 12-15 -> B (pole powers) -----
-        const bool isB = warp >= 12;
-        const int gw = (warp - 8) & 3;
-        const int m_l = lane & 15, blk = gw * 2 + (lane >> 4);
-        // table entries of one 16-row block of one chunk (loaded one chunk ahead): base power, the 4t / c powers
-        struct Opnd { float2 vb, ra; float4 q0, q1, q2; };
-        auto load_opnd = [&](int u, int ch) -> Opnd {
-            Opnd r{{1.f, 0.f}, {0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-            if (u >= u1) return r;
+    } else if (warp < 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        // ---------------- A generators: thread = row (TMEM lane); A[row][2m..2m+1] = X[m][blk] * R[m][j] -----------
+        const int row = (warp - 8) * 32 + lane, blk = row >> 4, j = row & 15;
+        const uint32_t lane_off = (uint32_t)((warp - 8) * 32) << 16;
+        for (uint32_t q = 0; q < n_chunks_total; ++q) {
+            const int u = u0 + (int)(q / cpu);
             const Unit un = units[u];
-            const int m = ch * TCB_KMODES + m_l;
+            int jj = j;
+            if (un.ev >= 0) {                                         // impulse unit: rows of block ae are shifted by be
+                const int re = ev_row[un.ev] - un.it * TCB_ROWS;
+                if (blk == (re >> 4)) jj = j - (re & 15);
+            }
+            const uint32_t slot = q % TCB_SEEDS, sa = q % TCB_ASTAGES;
+            mbar_wait(&seed_full[slot], (q / TCB_SEEDS) & 1);
+            const uint32_t sX = smem_u32(seeds) + slot * TCB_SEED_BYTES + blk * 8;
+            const uint32_t sR = smem_u32(seeds) + slot * TCB_SEED_BYTES + TCB_KMODES * 64 + (jj < 0 ? 16 : jj) * 8;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int m = 0; m < TCB_KMODES; ++m) {
+                const float2 x = lds_f2(sX + m * 64), r = lds_f2(sR + m * TCB_RROW);
+                float vr, vi; upk(cmulf(pk(x.x, x.y), pk(r.x, r.y), pk(-r.y, r.x)), vr, vi);
+                split_tf32<SPLIT>(vr, hi[2 * m], lo[2 * m]);
+                split_tf32<SPLIT>(vi, hi[2 * m + 1], lo[2 * m + 1]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&seed_empty[slot]);
+            mbar_wait(&a_empty[sa], ((q / TCB_ASTAGES) & 1) ^ 1);
+            tcgen05_fence_after();
+            const uint32_t a_col = tmem_base + lane_off + 384 + sa * 64;
+            tmem_st_32x32(a_col, hi);
+            tmem_st_32x32(a_col + 32, lo);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[sa]);
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+        // ---------------- B generators: thread = (mode of the chunk, 16-row block), pole powers T w^j -----------
+        const int m_l = lane & 15, blk = (warp - 12) * 2 + (lane >> 4);
+        struct Opnd { float2 ra; float4 q0, q1, q2; };
+        auto load_opnd = [&](uint32_t q) -> Opnd {
+            Opnd r{{0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            if (q >= n_chunks_total) return r;
+            const int m = (int)(q % cpu) * TCB_KMODES + m_l;
             if (m >= n_modes) return r;
-            const size_t idx = (size_t)un.obj * n_modes + m;
-            const float2* tab = (isB ? tabB : tabA) + idx * 16;
+            const float2* tab = tabB + ((size_t)units[u0 + (int)(q / cpu)].obj * n_modes + m) * 16;
             r.ra = __ldg(&tab[blk]);
             const float4* t4 = reinterpret_cast<const float4*>(tab + 8);
             r.q0 = __ldg(t4); r.q1 = __ldg(t4 + 1); r.q2 = __ldg(t4 + 2);
-            if (!isB && un.ev < 0) r.vb = __ldg(&Vbase[(size_t)un.it * npm + idx]);
             return r;
         };
-        uint32_t q = 0;
-        Opnd nxt = load_opnd(u0, 0);
-        for (int u = u0; u < u1; ++u) {
-            const Unit un = units[u];
-            const size_t obase = (size_t)un.obj * n_modes;
-            int re = -1;                                              // impulse row inside the M-tile, or -1
-            if (!isB && un.ev >= 0) re = ev_row[un.ev] - un.it * TCB_ROWS;
-            const bool general = re >= 0;                             // warp-uniform (unit property)
-            for (int ch = 0; ch < cpu; ++ch, ++q) {
-                const int s = q % TCB_STAGES;
-                const uint32_t ph = (q / TCB_STAGES) & 1;
-                const Opnd op = nxt;
-                nxt = (ch + 1 < cpu) ? load_opnd(u, ch + 1) : load_opnd(u + 1, 0);
-                const c32 rt[3] = {pk(op.q0.x, op.q0.y), pk(op.q0.z, op.q0.w), pk(op.q1.x, op.q1.y)};
-                const c32 rc[3] = {pk(op.q1.z, op.q1.w), pk(op.q2.x, op.q2.y), pk(op.q2.z, op.q2.w)};
-                const c32 ra = pk2(op.ra);
-                c32 x = isB ? ra : cmulf(pk2(op.vb), ra, swp(ra));
-                int shift = 0;
-                if (general) {
-                    const int m = ch * TCB_KMODES + m_l;
-                    const int ae = re >> 4, be = re & 15;
-                    x = pk(0.f, 0.f);
-                    if (m < n_modes && blk >= ae) {
-                        const size_t idx = obase + m;
-                        const double inji = c3a[idx], injr = inji * cota[idx];
-                        const double sp = ev_space[(size_t)un.ev * n_modes + m];
-                        x = pk((float)(sp * injr), (float)(sp * inji));            // the impulse, lands on row `re`
-                        if (blk == ae) shift = be;
-                        else {                                                    // x * W^(16 (blk - ae) - be)
-                            const int d = 16 * (blk - ae) - be;
-                            const float2* tab = tabA + idx * 16;
-                            if (d >> 4) { const c32 qq = pk2(__ldg(&tab[d >> 4])); x = cmulf(x, qq, swp(qq)); }
-                            if ((d >> 2) & 3) { const c32 qq = pk2(__ldg(&tab[7 + ((d >> 2) & 3)])); x = cmulf(x, qq, swp(qq)); }
-                            if (d & 3) { const c32 qq = pk2(__ldg(&tab[10 + (d & 3)])); x = cmulf(x, qq, swp(qq)); }
-                        }
-                    }
-                }
-                mbar_wait(&empty[s], ph ^ 1);
-                const uint32_t st = smem_u32(smem) + s * TCB_STAGE_BYTES + (isB ? 2 * TCB_TILE_BYTES : 0);
-                if (general && shift > 0) gen_block_from<SPLIT>(st, st + TCB_TILE_BYTES, blk, m_l, x, tabA + (obase + min(ch * TCB_KMODES + m_l, n_modes - 1)) * 16, shift);
-                else if (isB) gen_block<SPLIT, true>(st, st + TCB_TILE_BYTES, blk, m_l, x, rt, rc);
-                else gen_block<SPLIT, false>(st, st + TCB_TILE_BYTES, blk, m_l, x, rt, rc);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+        Opnd nxt = load_opnd(0);
+        for (uint32_t q = 0; q < n_chunks_total; ++q) {
+            const uint32_t sb = q % TCB_BSTAGES;
+            const Opnd op = nxt;
+            nxt = load_opnd(q + 1);
+            if (q + 4 < n_chunks_total && blk == 0) {                  // table rows of chunk q+4 into L2 (one lane per mode)
+                const int m = (int)((q + 4) % cpu) * TCB_KMODES + m_l;
+                if (m < n_modes) asm volatile("prefetch.global.L2 [%0];" ::"l"(tabB + ((size_t)units[u0 + (int)((q + 4) / cpu)].obj * n_modes + m) * 16));
             }
+            const c32 rt[3] = {pk(op.q0.x, op.q0.y), pk(op.q0.z, op.q0.w), pk(op.q1.x, op.q1.y)};
+            const c32 rc[3] = {pk(op.q1.z, op.q1.w), pk(op.q2.x, op.q2.y), pk(op.q2.z, op.q2.w)};
+            mbar_wait(&b_empty[sb], ((q / TCB_BSTAGES) & 1) ^ 1);
+            const uint32_t st = smem_u32(smem) + sb * TCB_BSTAGE_BYTES;
+            gen_block<SPLIT>(st, st + TCB_TILE_BYTES, blk, m_l, pk2(op.ra), rt, rc);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_full[sb]);
         }
     }
     tcgen05_fence_before();
@@ -534,8 +662,8 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
 #define PBSO_TC_LAUNCH(S, C)                                                                                         \
     do {                                                                                                             \
         static bool attr = false;                                                                                    \
-        if (!attr) { PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_BYTES)); attr = true; } \
-        k_batch_tc<S, C><<<grid, TCB_THREADS, TCB_SMEM_BYTES, a.stream>>>(a.n_obj, a.n_modes, n_tiles, st->cta_first, st->units, st->tabA, \
+        if (!attr) { PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_TS)); attr = true; } \
+        k_batch_tc<S, C><<<grid, TCB_THREADS, TCB_SMEM_TS, a.stream>>>(a.n_obj, a.n_modes, n_tiles, st->cta_first, st->units, st->tabA, \
             st->tabB, st->Vbase, a.c3, a.cot, st->ev_row, a.d_ev_space, a.d_mix, flush_units);                     \
     } while (0)
     if (split == 0 && chain == 2) PBSO_TC_LAUNCH(0, 2);
