@@ -85,25 +85,37 @@ __device__ __forceinline__ float2 pole_pow(double le, double th, double k, doubl
     const double e = scale * exp(k * le);
     return make_float2((float)(e * c), (float)(e * s));
 }
-__global__ void k_tc_tables(size_t n, const double* __restrict__ lneps, const double* __restrict__ theta,
+// Layout: [object][K chunk][entry 0..15][mode within the chunk 0..15] float2 -- one 2 KB block per K chunk, which
+// the kernel's loader thread brings into shared memory with a single bulk copy; entry-major so that the 16 lanes
+// of a half-warp (= 16 modes) read 128 consecutive bytes.  Modes past n_modes are zero.
+__global__ void k_tc_tables(int n_obj, int n_modes, int cpu, const double* __restrict__ lneps, const double* __restrict__ theta,
                             const double* __restrict__ trans, float2* __restrict__ tabA, float2* __restrict__ tabB) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;       // (object, padded mode)
+    const size_t n = (size_t)n_obj * cpu * TCB_KMODES;
     if (i >= n) return;
-    const double le = lneps[i], th = theta[i], T = trans[i];
-    float2* ta = tabA + i * 16; float2* tb = tabB + i * 16;
+    const int o = (int)(i / ((size_t)cpu * TCB_KMODES)), mp = (int)(i % ((size_t)cpu * TCB_KMODES));
+    float2* ta = tabA + ((size_t)o * cpu + mp / TCB_KMODES) * 256 + (mp % TCB_KMODES);
+    float2* tb = tabB + ((size_t)o * cpu + mp / TCB_KMODES) * 256 + (mp % TCB_KMODES);
+    if (mp >= n_modes) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ta[e * 16] = tb[e * 16] = make_float2(0.f, 0.f);
+        return;
+    }
+    const size_t src = (size_t)o * n_modes + mp;
+    const double le = lneps[src], th = theta[src], T = trans[src];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-        ta[a] = pole_pow(le, th, 16.0 * a * TCB_L, 1.0);
-        { const float2 z = pole_pow(le, th, 16.0 * a, T); tb[a] = make_float2(z.y, z.x); }
+        ta[a * 16] = pole_pow(le, th, 16.0 * a * TCB_L, 1.0);
+        { const float2 z = pole_pow(le, th, 16.0 * a, T); tb[a * 16] = make_float2(z.y, z.x); }
     }
 #pragma unroll
     for (int t = 1; t < 4; ++t) {
-        ta[7 + t] = pole_pow(le, th, 4.0 * t * TCB_L, 1.0);
-        ta[10 + t] = pole_pow(le, th, (double)t * TCB_L, 1.0);
-        { const float2 z = pole_pow(le, th, 4.0 * t, 1.0); tb[7 + t] = make_float2(z.x, -z.y); }
-        { const float2 z = pole_pow(le, th, (double)t, 1.0); tb[10 + t] = make_float2(z.x, -z.y); }
+        ta[(7 + t) * 16] = pole_pow(le, th, 4.0 * t * TCB_L, 1.0);
+        ta[(10 + t) * 16] = pole_pow(le, th, (double)t * TCB_L, 1.0);
+        { const float2 z = pole_pow(le, th, 4.0 * t, 1.0); tb[(7 + t) * 16] = make_float2(z.x, -z.y); }
+        { const float2 z = pole_pow(le, th, (double)t, 1.0); tb[(10 + t) * 16] = make_float2(z.x, -z.y); }
     }
-    ta[14] = ta[15] = tb[14] = tb[15] = make_float2(0.f, 0.f);
+    ta[14 * 16] = ta[15 * 16] = tb[14 * 16] = tb[15 * 16] = make_float2(0.f, 0.f);
 }
 
 // ---- FP64 carrier: state of every (object, mode) at the start of every M-tile -------------------------------
@@ -226,6 +238,10 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr)); return v;
 }
@@ -239,7 +255,8 @@ constexpr int TCB_BSTAGES = 4, TCB_ASTAGES = 2, TCB_SEEDS = 4;
 constexpr int TCB_BSTAGE_BYTES = 2 * TCB_TILE_BYTES;
 constexpr int TCB_RROW = 18 * 8;                                      // R row: 16 powers, a zero entry, pad (16-byte aligned)
 constexpr int TCB_SEED_BYTES = TCB_KMODES * 64 + TCB_KMODES * TCB_RROW;   // X[16 modes][8 blk] then R[16 modes][18], float2
-constexpr int TCB_SMEM_TS = TCB_BSTAGES * TCB_BSTAGE_BYTES + TCB_SEEDS * TCB_SEED_BYTES + 1024 + 512;
+constexpr int TCB_TABS = 6, TCB_TAB_BYTES = 2 * 2048;                 // table ring: tabA block | tabB block of a chunk
+constexpr int TCB_SMEM_TS = TCB_BSTAGES * TCB_BSTAGE_BYTES + TCB_SEEDS * TCB_SEED_BYTES + TCB_TABS * TCB_TAB_BYTES + 1024 + 512;
 constexpr int TCB_SMALL_CHAIN = 8;                                   // chunks per small-accumulator chain
 
 template <int SPLIT, int CHAIN>
@@ -252,7 +269,8 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* seeds = smem + TCB_BSTAGES * TCB_BSTAGE_BYTES;
-    uint64_t* bars = (uint64_t*)(seeds + TCB_SEEDS * TCB_SEED_BYTES);
+    uint8_t* tabs = seeds + TCB_SEEDS * TCB_SEED_BYTES;
+    uint64_t* bars = (uint64_t*)(tabs + TCB_TABS * TCB_TAB_BYTES);
     uint64_t* b_full = bars;                       // [4]  B stage written (4 generator warps)
     uint64_t* b_empty = b_full + TCB_BSTAGES;      // [4]  MMAs reading it retired
     uint64_t* a_full = b_empty + TCB_BSTAGES;      // [2]  A stage stored to TMEM (4 generator warps)
@@ -263,7 +281,9 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
     uint64_t* acc_empty = acc_full + 2;            // [2]  drained (128 epilogue threads)
     uint64_t* small_full = acc_empty + 2;          // [1]
     uint64_t* small_empty = small_full + 1;        // [1]
-    uint32_t* tmem_slot = (uint32_t*)(small_empty + 1);
+    uint64_t* tab_full = small_empty + 1;          // [6]  bulk copies of a chunk's table blocks landed (tx bytes)
+    uint64_t* tab_empty = tab_full + TCB_TABS;     // [6]  consumed (1 seed warp + 4 B-generator warps)
+    uint32_t* tmem_slot = (uint32_t*)(tab_empty + TCB_TABS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // this CTA's contiguous range of units (sorted by M-tile; ranges of equal estimated cost, built on the host)
@@ -277,6 +297,7 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
         for (int s = 0; s < TCB_SEEDS; ++s) { mbar_init(&seed_full[s], 1); mbar_init(&seed_empty[s], 4); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
         mbar_init(small_full, 1); mbar_init(small_empty, 128);
+        for (int s = 0; s < TCB_TABS; ++s) { mbar_init(&tab_full[s], 1); mbar_init(&tab_empty[s], 5); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -332,6 +353,19 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                 if (small_end) ++gs;
                 if (++ch == cpu) ch = 0;
             }
+        } else if (warp == 3) {
+            // ---------------- loader: one bulk copy per operand per chunk into the table ring ----------------
+            if (lane == 0) {
+                for (uint32_t q = 0; q < n_chunks_total; ++q) {
+                    const uint32_t slot = q % TCB_TABS;
+                    mbar_wait(&tab_empty[slot], ((q / TCB_TABS) & 1) ^ 1);
+                    const size_t blk_idx = ((size_t)units[u0 + (int)(q / cpu)].obj * cpu + (q % cpu)) * 256;
+                    const uint32_t dst = smem_u32(tabs) + slot * TCB_TAB_BYTES;
+                    mbar_expect_tx(&tab_full[slot], TCB_TAB_BYTES);
+                    bulk_g2s(dst, tabA + blk_idx, 2048, &tab_full[slot]);
+                    bulk_g2s(dst + 2048, tabB + blk_idx, 2048, &tab_full[slot]);
+                }
+            }
         } else if (warp <= 2) {
             // ---------------- seed warps (chunks alternate between warps 1 and 2) ----------------
             // lanes 0-15: X[m][blk] = v_base * W^(16 blk), the state at the start of each 16-row block;
@@ -343,12 +377,14 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                 const int m = ch * TCB_KMODES + m_l;
                 const bool valid = m < n_modes;
                 const size_t idx = (size_t)un.obj * n_modes + (valid ? m : 0);
-                const float4* t4 = reinterpret_cast<const float4*>(tabA + idx * 16);
+                const uint32_t tslot = q % TCB_TABS;
+                mbar_wait(&tab_full[tslot], (q / TCB_TABS) & 1);
+                const uint32_t tA = smem_u32(tabs) + tslot * TCB_TAB_BYTES + m_l * 8;     // entry e at tA + 128 e
                 float2 out[16];
                 if (half == 0) {
-                    const float4 r0 = __ldg(t4), r1 = __ldg(t4 + 1), r2 = __ldg(t4 + 2), r3 = __ldg(t4 + 3);
-                    const c32 ra[8] = {pk(r0.x, r0.y), pk(r0.z, r0.w), pk(r1.x, r1.y), pk(r1.z, r1.w),
-                                       pk(r2.x, r2.y), pk(r2.z, r2.w), pk(r3.x, r3.y), pk(r3.z, r3.w)};
+                    c32 ra[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ra[e] = pk2(lds_f2(tA + 128 * e));
                     if (un.ev < 0) {
                         const c32 vb = valid ? pk2(__ldg(&Vbase[(size_t)un.it * npm + idx])) : pk(0.f, 0.f);
 #pragma unroll
@@ -360,7 +396,6 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                         const double inji = c3a[idx], injr = inji * cota[idx];
                         const double sp = valid ? ev_space[(size_t)un.ev * n_modes + m] : 0.0;
                         const c32 uimp = pk((float)(sp * injr), (float)(sp * inji));
-                        const float2* tab = tabA + idx * 16;
 #pragma unroll
                         for (int blk = 0; blk < 8; ++blk) {
                             c32 x = pk(0.f, 0.f);
@@ -368,17 +403,16 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                             else if (blk > ae) {
                                 const int d = 16 * (blk - ae) - be;
                                 x = uimp;
-                                if (d >> 4) { const c32 qq = pk2(__ldg(&tab[d >> 4])); x = cmulf(x, qq, rot(qq)); }
-                                if ((d >> 2) & 3) { const c32 qq = pk2(__ldg(&tab[7 + ((d >> 2) & 3)])); x = cmulf(x, qq, rot(qq)); }
-                                if (d & 3) { const c32 qq = pk2(__ldg(&tab[10 + (d & 3)])); x = cmulf(x, qq, rot(qq)); }
+                                if (d >> 4) { const c32 qq = pk2(lds_f2(tA + 128 * (d >> 4))); x = cmulf(x, qq, rot(qq)); }
+                                if ((d >> 2) & 3) { const c32 qq = pk2(lds_f2(tA + 128 * (7 + ((d >> 2) & 3)))); x = cmulf(x, qq, rot(qq)); }
+                                if (d & 3) { const c32 qq = pk2(lds_f2(tA + 128 * (10 + (d & 3)))); x = cmulf(x, qq, rot(qq)); }
                             }
                             float a, b; upk(x, a, b); out[blk] = make_float2(a, b);
                         }
                     }
                 } else {
-                    const float4 q0 = __ldg(t4 + 4), q1 = __ldg(t4 + 5), q2 = __ldg(t4 + 6);
-                    const c32 rt[4] = {pk(1.f, 0.f), pk(q0.x, q0.y), pk(q0.z, q0.w), pk(q1.x, q1.y)};
-                    const c32 rc[4] = {pk(1.f, 0.f), pk(q1.z, q1.w), pk(q2.x, q2.y), pk(q2.z, q2.w)};
+                    const c32 rt[4] = {pk(1.f, 0.f), pk2(lds_f2(tA + 128 * 8)), pk2(lds_f2(tA + 128 * 9)), pk2(lds_f2(tA + 128 * 10))};
+                    const c32 rc[4] = {pk(1.f, 0.f), pk2(lds_f2(tA + 128 * 11)), pk2(lds_f2(tA + 128 * 12)), pk2(lds_f2(tA + 128 * 13))};
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -387,6 +421,8 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                             float a, b; upk(v, a, b); out[4 * t + c] = make_float2(a, b);
                         }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tab_empty[tslot]);
                 const uint32_t slot = q % TCB_SEEDS;
                 mbar_wait(&seed_empty[slot], ((q / TCB_SEEDS) & 1) ^ 1);
                 const uint32_t sbase = smem_u32(seeds) + slot * TCB_SEED_BYTES;
@@ -510,35 +546,21 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
         asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
         // ---------------- B generators: thread = (mode of the chunk, 16-row block), pole powers T w^j -----------
         const int m_l = lane & 15, blk = (warp - 12) * 2 + (lane >> 4);
-        struct Opnd { float2 ra; float4 q0, q1, q2; };
-        auto load_opnd = [&](uint32_t q) -> Opnd {
-            Opnd r{{0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-            if (q >= n_chunks_total) return r;
-            const int m = (int)(q % cpu) * TCB_KMODES + m_l;
-            if (m >= n_modes) return r;
-            const float2* tab = tabB + ((size_t)units[u0 + (int)(q / cpu)].obj * n_modes + m) * 16;
-            r.ra = __ldg(&tab[blk]);
-            const float4* t4 = reinterpret_cast<const float4*>(tab + 8);
-            r.q0 = __ldg(t4); r.q1 = __ldg(t4 + 1); r.q2 = __ldg(t4 + 2);
-            return r;
-        };
-        Opnd nxt = load_opnd(0);
         for (uint32_t q = 0; q < n_chunks_total; ++q) {
-            const uint32_t sb = q % TCB_BSTAGES;
-            const Opnd op = nxt;
-            nxt = load_opnd(q + 1);
-            if (q + 4 < n_chunks_total && blk == 0) {                  // table rows of chunk q+4 into L2 (one lane per mode)
-                const int m = (int)((q + 4) % cpu) * TCB_KMODES + m_l;
-                if (m < n_modes) asm volatile("prefetch.global.L2 [%0];" ::"l"(tabB + ((size_t)units[u0 + (int)((q + 4) / cpu)].obj * n_modes + m) * 16));
-            }
-            const c32 rt[3] = {pk(op.q0.x, op.q0.y), pk(op.q0.z, op.q0.w), pk(op.q1.x, op.q1.y)};
-            const c32 rc[3] = {pk(op.q1.z, op.q1.w), pk(op.q2.x, op.q2.y), pk(op.q2.z, op.q2.w)};
+            const uint32_t sb = q % TCB_BSTAGES, tslot = q % TCB_TABS;
+            mbar_wait(&tab_full[tslot], (q / TCB_TABS) & 1);
+            const uint32_t tB = smem_u32(tabs) + tslot * TCB_TAB_BYTES + 2048 + m_l * 8;   // entry e at tB + 128 e
+            const c32 ra = pk2(lds_f2(tB + 128 * blk));
+            const c32 rt[3] = {pk2(lds_f2(tB + 128 * 8)), pk2(lds_f2(tB + 128 * 9)), pk2(lds_f2(tB + 128 * 10))};
+            const c32 rc[3] = {pk2(lds_f2(tB + 128 * 11)), pk2(lds_f2(tB + 128 * 12)), pk2(lds_f2(tB + 128 * 13))};
             mbar_wait(&b_empty[sb], ((q / TCB_BSTAGES) & 1) ^ 1);
             const uint32_t st = smem_u32(smem) + sb * TCB_BSTAGE_BYTES;
-            gen_block<SPLIT>(st, st + TCB_TILE_BYTES, blk, m_l, pk2(op.ra), rt, rc);
+            gen_block<SPLIT>(st, st + TCB_TILE_BYTES, blk, m_l, ra, rt, rc);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&b_full[sb]);
+            // the table slot is released only here: the loads above are certainly complete once their values have
+            // been used (an arrive issued right after the LDS can overtake them in the MIO queue)
+            if (lane == 0) { mbar_arrive(&tab_empty[tslot]); mbar_arrive(&b_full[sb]); }
         }
     }
     tcgen05_fence_before();
@@ -577,6 +599,8 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     if (!*pst) *pst = new TcState();
     TcState* st = *pst;
     const size_t npm = (size_t)a.n_obj * a.n_modes;
+    const int cpu = div_up(a.n_modes, TCB_KMODES);
+    const size_t ntab = (size_t)a.n_obj * cpu * 256;                  // float2 entries per operand table
     const long long n_samples = (long long)a.buf_size * a.n_buffers;
     const int n_tiles = (int)(n_samples / TCB_L);
     const int n_it = div_up(n_tiles, TCB_ROWS);
@@ -586,12 +610,12 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     if (st->npm != npm) {
         cudaFree(st->tabA); cudaFree(st->tabB);
         st->tabA = st->tabB = nullptr; st->npm = 0;
-        PBSO_CUDA(cudaMalloc(&st->tabA, sizeof(float2) * npm * 16));
-        PBSO_CUDA(cudaMalloc(&st->tabB, sizeof(float2) * npm * 16));
+        PBSO_CUDA(cudaMalloc(&st->tabA, sizeof(float2) * ntab));
+        PBSO_CUDA(cudaMalloc(&st->tabB, sizeof(float2) * ntab));
         st->npm = npm; st->tables_ver = ~0u;
     }
     if (st->tables_ver != a.trans_ver) {
-        k_tc_tables<<<(unsigned)((npm + 255) / 256), 256, 0, a.stream>>>(npm, a.lneps, a.theta, a.trans, st->tabA, st->tabB);
+        k_tc_tables<<<(unsigned)(((size_t)a.n_obj * cpu * TCB_KMODES + 255) / 256), 256, 0, a.stream>>>(a.n_obj, a.n_modes, cpu, a.lneps, a.theta, a.trans, st->tabA, st->tabB);
         PBSO_CUDA(cudaGetLastError());
         st->tables_ver = a.trans_ver; ++*launches;
     }
