@@ -10,8 +10,12 @@ object (FFAT transfer vector resident), mixed down to one track.  Objects are bl
 the N ranks (strong scaling, total work fixed); the only exchange is one NCCL reduce (sum) of the
 441 088-sample FP64 mix.  One "step" = one full render of that job.
 
-The JSON line also carries: the FP32-FMA roofline of the synthesis kernel (peak measured in the same
-run with an FMA micro-benchmark), the CPU oracle timed on this box's host cores on a bounded sample
+The default path (--precision tc3x) is the tensor-core formulation of the synthesis (batch_tc.cu: pole-power
+contraction, tcgen05 3xTF32); --precision f32_tiled selects the FP32-FMA pole-power kernel, f64 the reference
+arithmetic.  The JSON line also carries: the roofline of the synthesis kernel (tensor pipe for tc3x, against
+half the measured bf16 rate; FP32-FMA for f32_tiled, peak measured in the same run with an FMA
+micro-benchmark; both report the algorithmic 8 FLOP per mode-sample figure against the FP32-FMA peak as the
+north star asks), the CPU oracle timed on this box's host cores on a bounded sample
 (`cpu_baseline`), the end-to-end number through the host-pointer C ABI (`e2e`), and the real-time
 per-buffer latency of the second half of the metric (cfg2: 1024 modes, 256-sample buffers) under
 `realtime`.
@@ -33,19 +37,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_OBJ, N_MODES, BUF, N_BUF = 4096, 512, 256, 1723      # cfg5: 441 088 samples = 10.0 s
+TC3X_DRAM_BYTES_PER_MODE_SAMPLE = 14.688e9 / 9.2504e11   # ncu --set full, cfg5 launch: 14.30 GB read + 0.38 GB written (profiles/r1_k_batch_tc.md)
 FLOP_PER_MODE_SAMPLE = 8.0                              # 4 FMA: 3 in Step (modal_integrator.h:109-110) + 1 in the dot (modal_solver.h:267-269)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--objects", type=int, default=N_OBJ, help="total objects (default cfg5: 4096)")
     ap.add_argument("--modes", type=int, default=N_MODES)
     ap.add_argument("--buffers", type=int, default=N_BUF)
-    ap.add_argument("--precision", default="f32_tiled", choices=["f32_tiled", "f64", "tc3x"])
+    ap.add_argument("--precision", default="tc3x", choices=["tc3x", "f32_tiled", "f64"])
     ap.add_argument("--no-realtime", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -329,20 +334,40 @@ def run_ours(args):
     fp32_peak = max(fma["ffma_uniform"], fma["ffma2_uniform"], fma["ffma_3reg"], fma["ffma2_3reg"])
     info = pbso.device_info()
     k_ms = kms.item()
-    achieved = (float(n_local) * args.modes * n_samples) * FLOP_PER_MODE_SAMPLE / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp32_fma", "kernel": "k_batch_pow_g<16,16,2,ffma2>" if prec == pbso.PREC_F32_TILED else "k_batch_f64",
-                "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": None, "kernel_ms": k_ms,
-                "peak_source": "FMA micro-benchmark in this run (pbso_measure_fma_peak; MEASURED_PEAKS.json has no FP32 figure)",
-                "peak_nominal": info["sm_count"] * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12,
-                "fma_microbench_tflops": fma,
-                "algorithmic": "8 FLOP per mode-sample (reference recurrence); the kernel evaluates each sample from "
-                               "precomputed pole powers with 2 FMA, so frac can exceed the FMA-pipe utilisation"}
+    ms_local = float(n_local) * args.modes * n_samples
+    achieved = ms_local * FLOP_PER_MODE_SAMPLE / (k_ms * 1e-3) / 1e12          # algorithmic: 8 FLOP per mode-sample
+    nominal_fp32 = info["sm_count"] * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+    if prec == pbso.PREC_TC3X:
+        # tensor-pipe roofline: the kernel issues 3 TF32 MMAs (hi*hi, hi*lo, lo*hi) per product and 2 K columns per
+        # mode (Re, Im of the tile-start state), i.e. 12 tensor FLOP per mode-sample.  No TF32 figure exists in
+        # MEASURED_PEAKS.json: kind::tf32 runs at half the kind::f16 rate, so the denominator is half the measured
+        # cuBLAS bf16 burst rate.
+        issued = ms_local * 12.0 / (k_ms * 1e-3) / 1e12
+        tf32_peak = 0.5 * float(peaks.get("bf16_tflops", 1590.0))
+        roofline = {"bound": "tensor", "kernel": "k_batch_tc<split=1,chain=2> (tcgen05 kind::tf32, 3xTF32)", "achieved": issued,
+                    "peak": tf32_peak, "unit": "TFLOP/s", "frac": issued / tf32_peak,
+                    "traffic": TC3X_DRAM_BYTES_PER_MODE_SAMPLE * ms_local if (TC3X_DRAM_BYTES_PER_MODE_SAMPLE and args.modes == N_MODES and args.buffers == N_BUF) else None,
+                    "kernel_ms": k_ms,
+                    "peak_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (%s, burst): kind::tf32 issues at half the bf16 rate" % peaks_kind,
+                    "achieved_counts": "issued tensor FLOP: 3 MMAs x 2 K-columns x 2 FLOP = 12 per mode-sample",
+                    "traffic_source": "dram__bytes_read+write of one ncu --set full capture of this kernel, scaled per mode-sample (profiles/r1_k_batch_tc.md)",
+                    "algorithmic_tflops": achieved, "algorithmic": "8 FLOP per mode-sample (reference recurrence + dot, SURVEY 8d)",
+                    "fp32_fma_peak": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak, "peak_nominal_fp32": nominal_fp32,
+                    "fma_microbench_tflops": fma}
+    else:
+        roofline = {"bound": "fp32_fma", "kernel": "k_batch_pow_g<16,16,2,ffma2>" if prec == pbso.PREC_F32_TILED else "k_batch_f64",
+                    "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                    "traffic": None, "kernel_ms": k_ms,
+                    "peak_source": "FMA micro-benchmark in this run (pbso_measure_fma_peak; MEASURED_PEAKS.json has no FP32 figure)",
+                    "peak_nominal": nominal_fp32,
+                    "fma_microbench_tflops": fma,
+                    "algorithmic": "8 FLOP per mode-sample (reference recurrence); the kernel evaluates each sample from "
+                                   "precomputed pole powers with 2 FMA, so frac can exceed the FMA-pipe utilisation"}
     line = {
         "metric": "mode-samples/s (IIR+FFAT)", "value": value, "unit": "mode-samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 tiles + f64 carrier" if prec == pbso.PREC_F32_TILED else "f64",
+        "dtype": {pbso.PREC_TC3X: "tf32x3 (tensor cores, fp32 accumulate) + f64 carrier", pbso.PREC_F32_TILED: "f32 tiles + f64 carrier"}.get(prec, "f64"),
         "data": "synthetic",
         "config": {"workload": "cfg5 offline batch: %d objects x %d modes x %d samples (%d buffers of %d), one PointForce "
                                "per object, static listeners, mixed down" % (args.objects, args.modes, n_samples, args.buffers, BUF),
@@ -350,7 +375,7 @@ def run_ours(args):
                    "l2": "flushed with a 256 MiB write between timed steps; per-step inputs %.0f MB" % (
                        (7 * a.size * 8 + space_h.nbytes) / 1e6),
                    "mix_abs_sum": checksum},
-        "roofline": roofline, "clocks": clocks, "gpu_launches": args.steps * world,
+        "roofline": roofline, "clocks": clocks, "gpu_launches": args.steps * world * (2 if prec == pbso.PREC_TC3X else 1),
         "e2e": {"value": e2e_value, "unit": "mode-samples/s", "h2d_bytes_per_step": int(h2d_t.item()),
                 "d2h_bytes_per_step": int(mix_host.numel() * 8), "ms_per_step": 1e3 * e2e_t.item() / args.steps},
         "wall_ms_per_step": 1e3 * t_wall / args.steps, "peaks": {"source": peaks_kind, "hbm_gbs": peaks.get("hbm_gbs")},
