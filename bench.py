@@ -126,12 +126,14 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / power / throttle reasons sampled DURING the timed region: NVML in a thread every 10 ms (the
+    timed region of a multi-GPU run is only tens of milliseconds), `nvidia-smi -lms 100` if NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index; self.rows = []; self.p = None; self.t_begin = None; self.t_end = None
+        self.nvml = None; self.stop_flag = False; self.source = None
 
     def mark_begin(self):
         self.t_begin = time.time()
@@ -139,25 +141,65 @@ class ClockSampler:
     def mark_end(self):
         self.t_end = time.time()
 
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
+
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml = pynvml; self.source = "nvml, 10 ms period"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True); self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 100"
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except OSError:
             self.p = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        R = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+             ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                flags = ["Active" if mask & bit else "Not Active" for _, bit in R]
+                self.rows.append((time.time(), [str(self.idx), sm, mx, pw, hex(mask)] + flags))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def _read(self):
         for line in self.p.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try: self.p.wait(timeout=2)
-        except Exception: self.p.kill()
+        if self.nvml is not None:
+            self.stop_flag = True; self.t.join(timeout=1)
+        elif self.p:
+            self.p.terminate()
+            try: self.p.wait(timeout=2)
+            except Exception: self.p.kill()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"]}
         sm = []; mx = None; reasons = set(); power = []
         # samples taken inside the timed region; if the region was shorter than the sampling period, the
         # samples taken under the same load during warm-up are used and the fact is recorded
@@ -165,14 +207,14 @@ class ClockSampler:
         window = "timed region" if inside else "warm-up + timed region (timed region shorter than the sampling period)"
         for r in (inside or [r for (_, r) in self.rows]):
             try:
-                sm.append(float(r[1])); mx = float(r[2]); power.append(float(r[3]))
+                sm.append(float(r[1])); mx = float(r[2]) if r[2] is not None else mx; power.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-            except (ValueError, IndexError):
+            except (ValueError, IndexError, TypeError):
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None, "window": window}
+                "samples": len(sm), "power_w_max": max(power) if power else None, "window": window, "source": self.source}
 
 
 def measured_peaks():
