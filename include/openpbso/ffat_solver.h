@@ -1,13 +1,19 @@
-// openpbso drop-in: run-time subset of ffat_solver.h -- the far-field acoustic transfer (FFAT) cube map that
-// ModalSolver::computeTransfer evaluates (reference ffat_solver.h:235-295, 1180-1206).  Map construction /
-// fitting / visualisation (the other ~1000 lines of the reference header) is offline preprocessing and is not
-// part of this path.  A map's data lives on the host (for GetData / Check) and in a device set (pbso_ffat)
-// that kernel K3 reads; GetMapVal evaluates on the B200.
+// openpbso drop-in: ffat_solver.h -- the far-field acoustic transfer (FFAT) cube map that
+// ModalSolver::computeTransfer evaluates (reference ffat_solver.h:235-295, 1180-1206) and its construction from
+// shell pressure samples (constructor :944-989, Solve :1007-1069, ReadNElementsFile :1100-1118).  Visualisation,
+// resampling and JPEG compression (the rest of the reference header) are not part of this path.  A map's data
+// lives on the host (for GetData / Check) and in a device set (pbso_ffat) that kernel K3 reads; GetMapVal
+// evaluates and Solve fits on the B200 (kernels K3 / K6).
 #ifndef FFAT_SOLVER_H
 #define FFAT_SOLVER_H
 #include <cassert>
+#include <complex>
+#include <fstream>
 #include <map>
 #include <memory>
+#include <sstream>
+#include <string>
+#include <utility>
 #include <vector>
 #include "Eigen/Dense"
 #include "io.h"
@@ -23,8 +29,66 @@ class FFAT_Map<T, 3> {
 public:
     typedef Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic> FFAT_MatrixXd;
     typedef Eigen::Matrix<T, 3, 1> FFAT_Vector3d;
+    typedef Eigen::Matrix<std::complex<T>, Eigen::Dynamic, 1> FFAT_VectorXcd;
 
     FFAT_Map() = default;
+    // Shell geometry from the cube-map mesh (reference :944-989): V holds 4 vertices per quad, shells back to back;
+    // N_elements[shell][face] = quads along the two in-face axes.  Shell 2 is the one the run-time map keeps.
+    FFAT_Map(const int& modeId_, const T cellSize, const Eigen::Matrix<T, Eigen::Dynamic, 3>& V,
+             const std::vector<std::vector<std::pair<int, int>>>& N_elements)
+        : modeId(modeId_), _cellSize(cellSize) {
+        const int N_shells = (int)N_elements.size();
+        assert(N_shells > 1 && "need more than 1 shell");
+        std::vector<int> ne; std::vector<double> v((size_t)V.rows() * 3);
+        for (const auto& shell : N_elements) {
+            assert(shell.size() == 6 && "N_elements wrong size");
+            for (const auto& p : shell) { ne.push_back(p.first); ne.push_back(p.second); }
+        }
+        for (int i = 0; i < (int)V.rows(); ++i) for (int j = 0; j < 3; ++j) v[(size_t)i * 3 + j] = (double)V(i, j);
+        pbso_ffat_fitter* h = nullptr;
+        pbso_mirror::check(pbso_ffat_fitter_create((double)cellSize, v.data(), (int)V.rows(), ne.data(), N_shells, &h), "FFAT_Map::FFAT_Map");
+        _fitter = std::shared_ptr<pbso_ffat_fitter>(h, [](pbso_ffat_fitter* p) { pbso_ffat_fitter_destroy(p); });
+        double geom[32];
+        pbso_mirror::check(pbso_ffat_fitter_shell(h, 2, geom, nullptr), "FFAT_Map::FFAT_Map");
+        _center << (T)geom[28], (T)geom[29], (T)geom[30];
+    }
+    // Least-squares fit of Psi from the shells' Dirichlet pressure (reference :1007-1069); a repeated k returns at once.
+    void Solve(const T& k, const FFAT_VectorXcd& dirichletPressure, const bool& powerScaling = false) {
+        if (_k == k) return;
+        assert(_fitter && "Solve started before proper initialization");
+        int n_total = 0, n_dir = 0;
+        pbso_mirror::check(pbso_ffat_fitter_info(_fitter.get(), nullptr, &n_total, &n_dir, nullptr), "FFAT_Map::Solve");
+        assert(dirichletPressure.size() == 2 * n_total && "Dirichlet pressure wrong size.");
+        std::vector<double> p((size_t)4 * n_total);
+        for (int i = 0; i < 2 * n_total; ++i) { p[2 * (size_t)i] = (double)dirichletPressure(i).real(); p[2 * (size_t)i + 1] = (double)dirichletPressure(i).imag(); }
+        const double kd = (double)k;
+        std::vector<double> psi((size_t)n_dir);
+        pbso_mirror::check(pbso_ffat_fitter_solve(_fitter.get(), 1, &kd, p.data(), powerScaling ? 1 : 0, psi.data(), nullptr), "FFAT_Map::Solve");
+        _Psi.resize(n_dir, 1);
+        for (int i = 0; i < n_dir; ++i) _Psi(i, 0) = (T)psi[(size_t)i];
+        _k = k;
+        // the run-time map (what FFAT_Map_Serialize::Save keeps): shell 2 + Psi + k
+        double geom[32]; int igeom[18];
+        pbso_mirror::check(pbso_ffat_fitter_shell(_fitter.get(), 2, geom, igeom), "FFAT_Map::Solve");
+        geom[31] = kd;
+        pbso_ffat* h = nullptr;
+        pbso_mirror::check(pbso_ffat_create(1, &modeId, geom, igeom, psi.data(), n_dir, nullptr, &h), "FFAT_Map::Solve");
+        _set = std::shared_ptr<pbso_ffat>(h, [](pbso_ffat* q) { pbso_ffat_destroy(q); });
+        _single.reset();
+    }
+    // One line per shell: "Nx Ny" for the six faces (reference :1100-1118).
+    static void ReadNElementsFile(const char* filename, std::vector<std::vector<std::pair<int, int>>>& N_elements) {
+        std::ifstream stream(filename);
+        assert(stream && "File not exist");
+        std::string line;
+        N_elements.clear();
+        while (std::getline(stream, line)) {
+            std::istringstream iss(line);
+            std::vector<std::pair<int, int>> v(6);
+            for (int ii = 0; ii < 6; ++ii) { std::pair<int, int> p; iss >> p.first >> p.second; v[ii] = p; }
+            N_elements.push_back(v);
+        }
+    }
     inline FFAT_Vector3d GetCenter() const { return _center; }
     inline T GetCellSize() const { return _cellSize; }
     inline const FFAT_MatrixXd& GetData() const { return _Psi; }
@@ -47,6 +111,7 @@ private:
     FFAT_MatrixXd _Psi;               // column 0 is what GetMapVal reads (reference :1203)
     bool _is_compressed = false;
     std::shared_ptr<pbso_ffat> _set;  // set this map was loaded into (keyed by modeId)
+    std::shared_ptr<pbso_ffat_fitter> _fitter;    // shell geometry, when built from a mesh
     mutable std::shared_ptr<pbso_ffat> _single;   // this map alone, re-keyed to id 0, built on first GetMapVal
 
     pbso_ffat* single() const {

@@ -124,6 +124,40 @@ int pbso_ffat_eval(const pbso_ffat* f, int n_modes, const double* pos, int L, in
 int pbso_ffat_eval_device(const pbso_ffat* f, int n_modes, const double* d_pos, int L,
                           double* d_out, void* cuda_stream);
 
+/* ---- FFAT map construction: ffat_solver.h:944-1069 ------------------
+ * The step before the synthesis path: fit the run-time map Psi from the Dirichlet pressure an acoustic solver
+ * sampled on nested cube shells.  A fitter holds what FFAT_Map<T,3>(modeId, cellSize, V, N_elements)
+ * (ffat_solver.h:944-989; shells :399-428) derives from the mesh -- it is shared by every mode of an object.
+ *   V          n_rows x 3 row-major quad vertices, 4 per quad, shells back to back (CubemapMesh order, :334-397);
+ *              only each face's first vertex (its low corner) is read, as in the reference
+ *   n_elements [n_shells][6][2] quads per face (+x,-x,+y,-y,+z,-z);  n_shells in [3,8]: shell 2 is the one the
+ *              run-time map keeps (_shells.at(2), :982, :1189)
+ * The reference takes the shell bounding box as min/max against uninitialised members (:423-428, undefined
+ * behaviour); here the bounds start from the first low corner, which equals a zero-filled start whenever the box
+ * straddles the origin. */
+typedef struct pbso_ffat_fitter pbso_ffat_fitter;
+int pbso_ffat_fitter_create(double cell_size, const double* V, int n_rows, const int* n_elements,
+                            int n_shells, pbso_ffat_fitter** out);
+int pbso_ffat_fitter_destroy(pbso_ffat_fitter* f);
+/* _N_elements_total, _N_directions, FFAT_Map<T,3>::_strides (:956-965, :983-986); any pointer may be NULL. */
+int pbso_ffat_fitter_info(const pbso_ffat_fitter* f, int* n_shells, int* n_elements_total,
+                          int* n_directions, int* shell_strides);
+/* One shell as the geom[32]/igeom[18] record pbso_ffat_create takes (k = -1 until solved; map centre = shell
+ * 2's centre): shell 2's record plus a solved Psi and its k is a complete run-time map. */
+int pbso_ffat_fitter_shell(const pbso_ffat_fitter* f, int shell, double* geom32, int* igeom18);
+/* FFAT_Map<T,3>::Solve(k, dirichletPressure, powerScaling) (:1007-1069 -> FFAT_Solver<T,3>::Solve :872-897,
+ * Scaling :909-929) for n_maps modes at once (kernel K6):  k[n_maps];  pressure = n_maps vectors of
+ * 2*n_elements_total complex doubles (re,im interleaved; two entries per quad, the even one is read, :1054);
+ * psi[n_maps][n_directions];  scale[n_maps] or NULL receives Scaling's return value (1 without power scaling). */
+int pbso_ffat_fitter_solve(pbso_ffat_fitter* f, int n_maps, const double* k, const double* pressure,
+                           int power_scaling, double* psi, double* scale);
+/* Device-resident variant, enqueue only (cuda_stream NULL = the fitter's own stream); d_scale may be NULL. */
+int pbso_ffat_fitter_solve_device(pbso_ffat_fitter* f, int n_maps, const double* d_k,
+                                  const double* d_pressure, int power_scaling, double* d_psi,
+                                  double* d_scale, void* cuda_stream);
+/* CUDA-event time of the kernels of the last pbso_ffat_fitter_solve call (copies excluded). */
+int pbso_ffat_fitter_last_kernel_ms(const pbso_ffat_fitter* f, float* ms);
+
 /* ---- mode shapes and impulse projection U^T f ---------------------------------------- */
 /* ModeData<REAL>::_modes (ModeData.h:23-24), mode-major U[M][K]. */
 int pbso_modes_upload(const double* U, int M, int K, pbso_modes** out);

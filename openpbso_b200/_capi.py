@@ -72,6 +72,13 @@ def lib():
             "pbso_ffat_save_file": [vp, C.c_int, C.c_char_p],
             "pbso_ffat_eval": [vp, C.c_int, c_dp, C.c_int, C.c_int, c_dp],
             "pbso_ffat_eval_device": [vp, C.c_int, vp, C.c_int, vp, vp],
+            "pbso_ffat_fitter_create": [C.c_double, c_dp, C.c_int, c_ip, C.c_int, c_vpp],
+            "pbso_ffat_fitter_destroy": [vp],
+            "pbso_ffat_fitter_info": [vp, c_ip, c_ip, c_ip, c_ip],
+            "pbso_ffat_fitter_shell": [vp, C.c_int, c_dp, c_ip],
+            "pbso_ffat_fitter_solve": [vp, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp],
+            "pbso_ffat_fitter_solve_device": [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp],
+            "pbso_ffat_fitter_last_kernel_ms": [vp, c_fp],
             "pbso_modes_upload": [c_dp, C.c_int, C.c_int, c_vpp],
             "pbso_modes_read_file": [C.c_char_p, c_vpp, c_ip, c_ip],
             "pbso_modes_omega_squared": [vp, c_dp],

@@ -185,6 +185,67 @@ class FFATMaps:
     __del__ = close
 
 
+class FFATFitter:
+    """FFAT_Map<double,3>(modeId, cellSize, V, N_elements) + Solve(k, dirichletPressure, powerScaling)
+    (reference ffat_solver.h:944-1069) for all modes of an object at once (kernel K6)."""
+
+    def __init__(self, cell_size, V, n_elements):
+        V = f64(V).reshape(-1, 3)
+        ne = np.ascontiguousarray(n_elements, dtype=np.int32).reshape(-1, 12)
+        h = C.c_void_p()
+        check(lib().pbso_ffat_fitter_create(float(cell_size), dp(V), V.shape[0], ip(ne), len(ne), C.byref(h)))
+        self._h = h
+        S = C.c_int(); nt = C.c_int(); nd = C.c_int()
+        check(lib().pbso_ffat_fitter_info(self._h, C.byref(S), C.byref(nt), C.byref(nd), None))
+        self.n_shells, self.n_elements_total, self.n_directions = S.value, nt.value, nd.value
+        self.strides = np.empty(self.n_shells, dtype=np.int32)
+        check(lib().pbso_ffat_fitter_info(self._h, None, None, None, ip(self.strides)))
+
+    def shell(self, s):
+        geom = np.empty(32); igeom = np.empty(18, dtype=np.int32)
+        check(lib().pbso_ffat_fitter_shell(self._h, int(s), dp(geom), ip(igeom)))
+        return geom, igeom
+
+    def Solve(self, k, pressure, powerScaling=False):
+        """k [n_maps]; pressure complex [n_maps][2*N_elements_total].  Returns (Psi [n_maps][N_directions], scale [n_maps])."""
+        k = f64(np.atleast_1d(k)); n = len(k)
+        P = np.ascontiguousarray(pressure, dtype=np.complex128).reshape(n, 2 * self.n_elements_total)
+        psi = np.empty((n, self.n_directions)); scale = np.empty(n)
+        check(lib().pbso_ffat_fitter_solve(self._h, n, dp(k), P.view(np.float64).ctypes.data_as(capi.c_dp),
+                                           int(bool(powerScaling)), dp(psi), dp(scale)))
+        return psi, scale
+
+    def solve_device(self, n_maps, d_k_ptr, d_pressure_ptr, d_psi_ptr, powerScaling=False, d_scale_ptr=0, stream_ptr=0):
+        check(lib().pbso_ffat_fitter_solve_device(self._h, int(n_maps), C.c_void_p(d_k_ptr), C.c_void_p(d_pressure_ptr),
+                                                  int(bool(powerScaling)), C.c_void_p(d_psi_ptr),
+                                                  C.c_void_p(d_scale_ptr) if d_scale_ptr else None,
+                                                  C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def last_kernel_ms(self):
+        ms = C.c_float(); check(lib().pbso_ffat_fitter_last_kernel_ms(self._h, C.byref(ms))); return ms.value
+
+    def to_maps(self, k, psi, mode_ids=None):
+        """The run-time map set (what FFAT_Map_Serialize::Save keeps: shell 2 + Psi + k) of solved modes."""
+        k = f64(np.atleast_1d(k)); psi = f64(psi).reshape(len(k), self.n_directions)
+        g2, ig2 = self.shell(2)
+        geom = np.tile(g2, (len(k), 1)); geom[:, 31] = k
+        igeom = np.tile(ig2, (len(k), 1)).astype(np.int32)
+        ids = np.arange(len(k), dtype=np.int32) if mode_ids is None else np.ascontiguousarray(mode_ids, dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().pbso_ffat_create(len(k), ip(ids), dp(geom), ip(igeom), dp(psi), self.n_directions, None, C.byref(h)))
+        return FFATMaps(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().pbso_ffat_fitter_destroy(self._h)
+            except Exception:          # interpreter shutdown
+                pass
+            self._h = None
+
+    __del__ = close
+
+
 class ModeShapes:
     """ModeData<double>::_modes resident on the device + GetModalForceVertex/Face."""
 

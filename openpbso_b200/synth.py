@@ -85,6 +85,64 @@ def ffat_maps(freqs, seed0=2000, R=1.5, n=32, geom=None):
     return maps
 
 
+def cubemap_vertices(center, half_cells, cell_size):
+    """Quad vertices of one cube-map shell in the order FFAT_Map<T,1>::CubemapMesh emits them (reference
+    ffat_solver.h:334-397): faces +x,-x,+y,-y,+z,-z; per face ii over axis di=(dk+1)%3, jj over dj=(dk+2)%3;
+    four vertices per quad, offsets (-,-),(+,-),(+,+),(-,+) * cell/2 about the cell centre.  The box is
+    2*half_cells[axis] cells wide (half_cells: int or per-axis triple) and centred on `center`.
+    Returns (V [4*n_quads][3], n_elements [6][2])."""
+    center = np.asarray(center, dtype=np.float64); h = float(cell_size)
+    hc = np.broadcast_to(np.asarray(half_cells, dtype=np.int64), (3,))
+    n = 2 * hc
+    low = center - hc * h
+    off = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], dtype=np.float64) * h / 2.0
+    V = []; ne = []
+    for face in range(6):
+        dk = face // 2; di = (dk + 1) % 3; dj = (dk + 2) % 3
+        plane = low[dk] + (n[dk] * h if face % 2 == 0 else 0.0)
+        ii, jj = np.meshgrid(np.arange(n[di]), np.arange(n[dj]), indexing="ij")
+        cc = np.empty((n[di], n[dj], 4, 3))
+        cc[..., dk] = plane
+        cc[..., di] = (low[di] + (0.5 + ii) * h)[..., None] + off[:, 0]
+        cc[..., dj] = (low[dj] + (0.5 + jj) * h)[..., None] + off[:, 1]
+        V.append(cc.reshape(-1, 3)); ne.append([n[di], n[dj]])
+    return np.concatenate(V), np.asarray(ne, dtype=np.int32)
+
+
+def ffat_fit_workload(n_maps, seed, half_cells=(8, 12, 16), cell_size=0.09375, center=(0.0, 0.0, 0.0), noise=0.0):
+    """Synthetic input of FFAT_Map<T,3>::Solve: three nested cube shells (shell 2 outermost, the one the
+    run-time map keeps), one wavenumber per mode and the Dirichlet pressure of a far-field radiator
+    p(x) = Psi(dir) e^{-ikr} / (k r) sampled at the quad centres (two entries per quad like the reference's
+    triangle-mesh ordering; the odd ones hold a different value on purpose: Solve must skip them).
+    Returns dict(V, n_elements [S][6][2], cell_size, k [n_maps], pressure complex [n_maps][2*n_total], psi_true)."""
+    rng = np.random.default_rng(seed)
+    Vs, nes, cents = [], [], []
+    for hc in half_cells:
+        V, ne = cubemap_vertices(center, hc, cell_size)
+        Vs.append(V); nes.append(ne)
+        cents.append(V.reshape(-1, 4, 3).mean(axis=1))
+    X = np.concatenate(cents) - np.asarray(center)
+    r = np.linalg.norm(X, axis=1); u = X / r[:, None]
+    x, y, z = u[:, 0], u[:, 1], u[:, 2]
+    basis = np.stack([np.ones_like(x), x, y, z, x * y, y * z, z * x, x * x - y * y, 3 * z * z - 1])
+    freqs = mode_frequencies(n_maps, seed)
+    k = 2.0 * np.pi * freqs / SPEED_OF_SOUND
+    n_total = len(r)
+    P = np.empty((n_maps, 2 * n_total), dtype=np.complex128)
+    psi_true = np.empty((n_maps, n_total))
+    for m in range(n_maps):
+        c = rng.standard_normal(basis.shape[0])
+        psi = np.abs(c @ basis) + 0.1
+        p = psi * np.exp(-1j * k[m] * r) / (k[m] * r)
+        if noise:
+            p = p * (1.0 + noise * rng.standard_normal(n_total))
+        P[m, 0::2] = p
+        P[m, 1::2] = -3.0 * p + 1.0
+        psi_true[m] = psi
+    return dict(V=np.concatenate(Vs), n_elements=np.stack(nes), cell_size=float(cell_size), k=k, pressure=P,
+                psi_true=psi_true, n_total=n_total)
+
+
 def listeners(L, seed, rmin=3.0, rmax=10.0):
     """Listener positions outside the bbox, directions uniform on S^2 (never axis-aligned)."""
     rng = np.random.default_rng(seed)

@@ -91,6 +91,8 @@ def lib():
         L.orc_ffat_intersect.argtypes = [c_dp, c_ip, c_dp, c_dp, c_ip]
         L.orc_ffat_interpolate.argtypes = [c_dp, c_ip, c_dp, c_ip, c_ip, c_dp]
         L.orc_num_modes_audible.argtypes = [c_dp, C.c_int, C.c_double, C.c_double, c_dp]
+        L.orc_ffat_fit_geometry.argtypes = [C.c_double, c_dp, c_ip, C.c_int, C.c_double, c_dp, c_ip, c_ip, c_ip]
+        L.orc_ffat_fit_solve.argtypes = [C.c_int, c_dp, c_ip, c_ip, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, c_dp, c_dp]
         L.orc_material_read.argtypes = [C.c_char_p, c_dp]
         L.orc_modes_read_header.argtypes = [C.c_char_p, c_ip, c_ip]
         L.orc_modes_read.argtypes = [C.c_char_p, c_dp, c_dp]
@@ -144,6 +146,8 @@ def ref():
         R.ref_ffat_load_save.argtypes = [C.c_char_p, C.c_char_p, c_ip, c_dp]
         R.ref_list_dir_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         R.ref_batch_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp]
+        R.ref_ffat_fit.argtypes = [C.c_int, C.c_double, c_dp, C.c_int, c_ip, C.c_int, C.c_double, c_dp, C.c_int,
+                                   c_dp, c_dp, C.c_char_p]
         _REF = R
     return _REF
 
@@ -384,6 +388,44 @@ def ffat_interpolate(m, surf, nn):
     idx = np.empty((4, 3), dtype=np.int32); co = np.empty(4)
     lib().orc_ffat_interpolate(_dp(geom), _ip(igeom), _dp(surf), _ip(nn), _ip(idx), _dp(co))
     return idx, co
+
+
+def ffat_fit_geometry(cell_size, V, n_elements, bbox_init=0.0):
+    """FFAT_Map<T,3>::FFAT_Map(modeId, cellSize, V, N_elements) (ffat_solver.h:944-989, shells :399-428).
+    V [rows][3]; n_elements [S][6][2].  Returns dict(geom [S][32], igeom [S][18], strides [S], n_total, n_dir)."""
+    V = _f64(V).reshape(-1, 3); ne = np.ascontiguousarray(n_elements, dtype=np.int32).reshape(-1, 12); S = len(ne)
+    geom = np.empty((S, 32)); igeom = np.empty((S, 18), dtype=np.int32); st = np.empty(S, dtype=np.int32)
+    cnt = np.empty(2, dtype=np.int32)
+    assert V.shape[0] >= 4 * int(sum(int(r[2 * f]) * int(r[2 * f + 1]) for r in ne for f in range(6)))
+    lib().orc_ffat_fit_geometry(float(cell_size), _dp(V), _ip(ne), S, float(bbox_init), _dp(geom), _ip(igeom), _ip(st), _ip(cnt))
+    return dict(geom=geom, igeom=igeom, strides=st, n_total=int(cnt[0]), n_dir=int(cnt[1]), cell_size=float(cell_size))
+
+
+def ffat_fit_solve(fit, k, pressure, power_scaling=False, want_R=False):
+    """FFAT_Map<T,3>::Solve (ffat_solver.h:1007-1069) for a batch of modes sharing `fit`:
+    k [n_maps]; pressure complex [n_maps][2*n_total].  Returns (psi [n_maps][n_dir], scale [n_maps]) (+ R, |P|)."""
+    k = _f64(np.atleast_1d(k)); n_maps = len(k)
+    P = np.ascontiguousarray(pressure, dtype=np.complex128).reshape(n_maps, 2 * fit["n_total"])
+    S = len(fit["strides"])
+    psi = np.empty((n_maps, fit["n_dir"])); scale = np.empty(n_maps)
+    R = np.empty((fit["n_dir"], S)); Pabs = np.empty((n_maps, fit["n_dir"], S))
+    lib().orc_ffat_fit_solve(S, _dp(fit["geom"]), _ip(fit["igeom"]), _ip(fit["strides"]), n_maps, _dp(k),
+                             P.view(np.float64).ctypes.data_as(c_dp), int(bool(power_scaling)), _dp(psi), _dp(scale),
+                             _dp(R), _dp(Pabs))
+    return (psi, scale, R, Pabs) if want_R else (psi, scale)
+
+
+def ref_ffat_fit(mode_id, cell_size, V, n_elements, k, pressure, power_scaling=False, save_to=None):
+    """The reference's own FFAT_Map<double,3> ctor + Solve (+ FFAT_Map_Serialize::Save when save_to is given),
+    compiled in place.  Returns (psi [n_dir], centre[3])."""
+    V = _f64(V).reshape(-1, 3); ne = np.ascontiguousarray(n_elements, dtype=np.int32).reshape(-1, 12); S = len(ne)
+    P = np.ascontiguousarray(pressure, dtype=np.complex128).ravel()
+    n_dir = int(sum(int(ne[2][2 * f]) * int(ne[2][2 * f + 1]) for f in range(6)))
+    psi = np.empty(n_dir); centre = np.empty(3)
+    ref().ref_ffat_fit(int(mode_id), float(cell_size), _dp(V), V.shape[0], _ip(ne), S, float(k),
+                       P.view(np.float64).ctypes.data_as(c_dp), int(bool(power_scaling)), _dp(psi), _dp(centre),
+                       None if save_to is None else os.fsencode(save_to))
+    return psi, centre
 
 
 def num_modes_audible(omega2, density, freq, cache=None):

@@ -405,6 +405,134 @@ static double ffat_getmapval(const FFATMap& M, const double p[3]) {
 }
 
 // -----------------------------------------------------------------------------
+// FFAT map CONSTRUCTION   [pinned:_ref, with the shim's JacobiSVD -- see
+// tests/test_oracle_vs_ref.py::test_ffat_fit_*]
+// -----------------------------------------------------------------------------
+// ffat_solver.h:399-428  FFAT_Map<T,1>::FFAT_Map(modeId, cellSize, V, N_elements): V holds 4 vertices per
+// quad (CubemapMesh, :334-397); only the first vertex of each face's first quad is read (the low corner).
+// _bboxLow/_bboxTop are never initialised by the reference (:420-427 min/max against whatever the members
+// hold: undefined behaviour).  `bbox_init` is that starting value: 0 is what a zero-filled frame -- and the
+// Eigen shim's value-initialised Matrix -- gives; it yields the true bounding box whenever the box straddles
+// the origin, which is the only case the reference can be said to define.
+static void ffat_shell_from_vertices(double cellSize, const double* V /*[rows][3]*/, const int nElem[6][2],
+                                     double bbox_init, FFATMap& M, int& n_total) {
+    M.cellSize = cellSize;
+    int sum = 0;
+    for (int f = 0; f < 6; ++f) {
+        const int N = nElem[f][0] * nElem[f][1];                     // :408
+        for (int d = 0; d < 3; ++d) M.lowCorners[f][d] = V[(size_t)(sum * 4) * 3 + d];   // :412-413
+        M.nElem[f][0] = nElem[f][0]; M.nElem[f][1] = nElem[f][1];
+        M.strides[f] = sum;                                          // :414
+        sum += N;                                                    // :415
+    }
+    n_total = sum;                                                   // :418
+    M.center1[0] = (M.lowCorners[0][0] + M.lowCorners[1][0]) / 2.0;  // :419-422
+    M.center1[1] = (M.lowCorners[2][1] + M.lowCorners[3][1]) / 2.0;
+    M.center1[2] = (M.lowCorners[4][2] + M.lowCorners[5][2]) / 2.0;
+    for (int j = 0; j < 3; ++j) { M.bboxLow[j] = bbox_init; M.bboxTop[j] = bbox_init; }
+    for (int f = 0; f < 6; ++f)                                      // :423-428
+        for (int j = 0; j < 3; ++j) {
+            M.bboxLow[j] = std::min(M.bboxLow[j], M.lowCorners[f][j]);
+            M.bboxTop[j] = std::max(M.bboxTop[j], M.lowCorners[f][j]);
+        }
+}
+
+struct FFATFit {                 // FFAT_Map<T,3> before Solve (ffat_solver.h:944-989)
+    std::vector<FFATMap> shells;
+    std::vector<int> strides;    // FFAT_Map<T,3>::_strides: quads before shell s
+    int n_total = 0, n_dir = 0;
+    double center3[3];
+};
+static void ffat_fit_geometry(double cellSize, const double* V, const int* nElem /*[S][6][2]*/, int S,
+                              double bbox_init, FFATFit& F) {
+    F.shells.resize(S); F.strides.resize(S);
+    int offset = 0;                                                  // rows of V consumed (:969-977)
+    F.n_total = 0;
+    for (int s = 0; s < S; ++s) {
+        int ne[6][2]; std::memcpy(ne, nElem + (size_t)s * 12, sizeof(ne));
+        int sum = 0;
+        ffat_shell_from_vertices(cellSize, V + (size_t)offset * 3, ne, bbox_init, F.shells[s], sum);
+        F.strides[s] = F.n_total;                                    // :963
+        F.n_total += sum;                                            // :964
+        offset += sum * 4;                                           // :976
+    }
+    std::memcpy(F.center3, F.shells[2].center1, sizeof(F.center3));  // :982
+    F.n_dir = 0;                                                     // :983-986
+    for (int f = 0; f < 6; ++f) F.n_dir += F.shells[2].nElem[f][0] * F.shells[2].nElem[f][1];
+}
+
+// ffat_solver.h:1007-1069 FFAT_Map<T,3>::Solve -> :872-897 FFAT_Solver<T,3>::Solve -> :909-929 Scaling.
+// pressure: complex interleaved (re, im), 2 * n_total entries (two triangles per quad; the even one is read).
+// R_out / Pabs_out (optional): n_dir x S row-major, the radii and |interpolated pressure| per shell.
+static double ffat_fit_solve(const FFATFit& F, double k, const double* pressure, bool powerScaling,
+                             double* Psi, double* R_out, double* Pabs_out) {
+    const int S = (int)F.shells.size();
+    const FFATMap& outer = F.shells[2];
+    std::vector<double> R((size_t)F.n_dir * S), Pre((size_t)F.n_dir * S), Pim((size_t)F.n_dir * S);
+    int offset = 0;
+    for (int dd = 0; dd < 6; ++dd) {                                 // :1021-1063
+        const int dk = dd / 2, di = (dk + 1) % 3, dj = (dk + 2) % 3;
+        const int dim1 = outer.nElem[dd][0], dim2 = outer.nElem[dd][1];
+        double ijk[3]; ijk[dk] = 0;
+        for (int ii = 0; ii < dim1; ++ii) {
+            ijk[di] = 0.5 + ii;
+            for (int jj = 0; jj < dim2; ++jj) {
+                ijk[dj] = 0.5 + jj;
+                double pos0[3];
+                for (int d = 0; d < 3; ++d) pos0[d] = outer.lowCorners[dd][d] + ijk[d] * outer.cellSize;   // :1035-1036
+                for (int ss = 0; ss < S; ++ss) {
+                    const FFATMap& sh = F.shells[ss];
+                    double pos[3]; int posind[3];
+                    ffat_intersect(sh, pos0, pos, posind);           // :1043
+                    const double dx = pos[0] - F.center3[0], dy = pos[1] - F.center3[1], dz = pos[2] - F.center3[2];
+                    const size_t row = (size_t)(offset + ii * dim2 + jj) * S + ss;
+                    R[row] = std::sqrt(dx * dx + dy * dy + dz * dz); // :1046
+                    int idx[4][3]; double co[4];
+                    ffat_interpolate(sh, pos, posind, idx, co);      // :1051
+                    double pre = 0, pim = 0;
+                    for (int kk = 0; kk < 4; ++kk) {                 // :1052-1057
+                        const int q = sh.strides[idx[kk][0]] + idx[kk][1] * sh.nElem[idx[kk][0]][1] + idx[kk][2];
+                        const size_t e = (size_t)2 * F.strides[ss] + (size_t)2 * q;
+                        pre += co[kk] * pressure[2 * e]; pim += co[kk] * pressure[2 * e + 1];
+                    }
+                    Pre[row] = pre; Pim[row] = pim;
+                }
+            }
+        }
+        offset += dim1 * dim2;
+    }
+    // FFAT_Solver<T,3>::Solve: per direction, least squares of basis * psi = |p| with basis_s = 1/(k r_s)
+    // (:881-895).  Eigen's JacobiSVD of an S x 1 matrix: sigma = |basis|, u = basis/sigma, v = 1, so
+    // solve(b) = (u . b) / sigma.
+    for (int ii = 0; ii < F.n_dir; ++ii) {
+        double ss2 = 0, ub = 0;
+        for (int s = 0; s < S; ++s) {
+            const double kr = R[(size_t)ii * S + s] * k;             // :882
+            const double basis = 1.0 / kr;                           // :883 (pow(kr,1) == kr)
+            const double p2 = std::hypot(Pre[(size_t)ii * S + s], Pim[(size_t)ii * S + s]);   // :885 std::abs(complex)
+            ss2 += basis * basis; ub += basis * p2;
+            if (Pabs_out) Pabs_out[(size_t)ii * S + s] = p2;
+        }
+        const double sigma = std::sqrt(ss2);
+        Psi[ii] = (ub / sigma) / sigma;
+    }
+    if (R_out) std::memcpy(R_out, R.data(), sizeof(double) * R.size());
+    double scale = 1.0;
+    if (powerScaling) {                                              // :909-929 (shell 0 only)
+        double numer = 0, denom = 0;
+        for (int ii = 0; ii < F.n_dir; ++ii) {
+            const double kr = k * R[(size_t)ii * S];
+            const double pa = std::hypot(Pre[(size_t)ii * S], Pim[(size_t)ii * S]);
+            numer += std::pow(pa, 2);
+            denom += std::pow(Psi[ii] / kr, 2);
+        }
+        scale = std::sqrt(numer / denom);
+        for (int ii = 0; ii < F.n_dir; ++ii) Psi[ii] *= scale;
+    }
+    return scale;
+}
+
+// -----------------------------------------------------------------------------
 // ModeData / ModalMaterial helpers   [pinned:_ref]
 // -----------------------------------------------------------------------------
 // ModeData.h:120-148 numModesAudible incl. its cache quirk (the cache is only
@@ -576,6 +704,41 @@ void orc_ffat_interpolate(const double* geom, const int* igeom, const double* su
     int idx[4][3];
     ffat_interpolate(M, surf, nn, idx, co4);
     std::memcpy(idx12, idx, sizeof(idx));
+}
+
+// FFAT map construction.  geom_out [S][32] / igeom_out [S][18] use the record layout of fill_map (k = -1,
+// centre3 = shell 2's centre); shell_strides [S]; counts[2] = {N_elements_total, N_directions}.
+void orc_ffat_fit_geometry(double cellSize, const double* V, const int* nElem, int S, double bbox_init,
+                           double* geom_out, int* igeom_out, int* shell_strides, int* counts) {
+    FFATFit F; ffat_fit_geometry(cellSize, V, nElem, S, bbox_init, F);
+    for (int s = 0; s < S; ++s) {
+        const FFATMap& M = F.shells[s];
+        double* g = geom_out + (size_t)s * 32; int* ig = igeom_out + (size_t)s * 18;
+        g[0] = M.cellSize; std::memcpy(g + 1, M.lowCorners, sizeof(double) * 18);
+        std::memcpy(g + 19, M.center1, 24); std::memcpy(g + 22, M.bboxLow, 24); std::memcpy(g + 25, M.bboxTop, 24);
+        std::memcpy(g + 28, F.center3, 24); g[31] = -1.0;
+        std::memcpy(ig, M.nElem, sizeof(int) * 12); std::memcpy(ig + 12, M.strides, sizeof(int) * 6);
+        shell_strides[s] = F.strides[s];
+    }
+    counts[0] = F.n_total; counts[1] = F.n_dir;
+}
+// Solve for n_maps modes sharing the geometry: k[n_maps], pressure [n_maps][2*n_total] complex interleaved,
+// psi_out [n_maps][n_dir], scale_out [n_maps] or NULL, R_out [n_dir][S] or NULL (same for every map).
+void orc_ffat_fit_solve(int S, const double* geom, const int* igeom, const int* shell_strides, int n_maps,
+                        const double* k, const double* pressure, int power_scaling, double* psi_out,
+                        double* scale_out, double* R_out, double* Pabs_out) {
+    FFATFit F; F.shells.resize(S); F.strides.assign(shell_strides, shell_strides + S);
+    for (int s = 0; s < S; ++s) fill_map(F.shells[s], geom + (size_t)s * 32, igeom + (size_t)s * 18, nullptr, 0);
+    std::memcpy(F.center3, geom + 2 * 32 + 28, 24);
+    F.n_dir = 0; F.n_total = 0;
+    for (int f = 0; f < 6; ++f) F.n_dir += F.shells[2].nElem[f][0] * F.shells[2].nElem[f][1];
+    for (int s = 0; s < S; ++s) for (int f = 0; f < 6; ++f) F.n_total += F.shells[s].nElem[f][0] * F.shells[s].nElem[f][1];
+    for (int m = 0; m < n_maps; ++m) {
+        const double sc = ffat_fit_solve(F, k[m], pressure + (size_t)m * 4 * F.n_total, power_scaling != 0,
+                                         psi_out + (size_t)m * F.n_dir, m == 0 ? R_out : nullptr,
+                                         Pabs_out ? Pabs_out + (size_t)m * F.n_dir * S : nullptr);
+        if (scale_out) scale_out[m] = sc;
+    }
 }
 
 int orc_num_modes_audible(const double* omega2, int n, double density, double freq, double* cache3) {

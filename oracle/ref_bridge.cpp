@@ -254,4 +254,32 @@ void ref_batch_render(int n_obj, int N, int n_buf, double h, const double* a, co
         }
     }
 }
+
+// FFAT map construction: the reference's own FFAT_Map<double,3>(modeId, cellSize, V, N_elements) constructor
+// (ffat_solver.h:944-989 -> shells :399-428), Solve (:1007-1069 -> FFAT_Solver<T,3>::Solve :872-897,
+// Scaling :909-929) and, optionally, FFAT_Map_Serialize::Save of the result.  V arrives row-major [rows][3].
+// The JacobiSVD underneath is the shim's (closed form for a one-column matrix).
+int ref_ffat_fit(int mode_id, double cell_size, const double* V, int n_rows, const int* n_elements, int n_shells,
+                 double k, const double* pressure, int power_scaling, double* psi_out, double* centre_out,
+                 const char* save_to) {
+    typedef Gpu_Wavesolver::FFAT_Map<double, 3> Map3;
+    Eigen::Matrix<double, Eigen::Dynamic, 3> Vm; Vm.resize(n_rows, 3);
+    for (int i = 0; i < n_rows; ++i) for (int j = 0; j < 3; ++j) Vm(i, j) = V[(size_t)i * 3 + j];
+    std::vector<std::vector<std::pair<int, int>>> ne(n_shells, std::vector<std::pair<int, int>>(6));
+    int n_total = 0;
+    for (int s = 0; s < n_shells; ++s) for (int f = 0; f < 6; ++f) {
+        ne[s][f] = std::make_pair(n_elements[(s * 6 + f) * 2], n_elements[(s * 6 + f) * 2 + 1]);
+        n_total += ne[s][f].first * ne[s][f].second;
+    }
+    Map3 map(mode_id, cell_size, Vm, ne);
+    Map3::FFAT_VectorXcd P; P.resize(2 * n_total);
+    for (int i = 0; i < 2 * n_total; ++i) P(i) = std::complex<double>(pressure[2 * i], pressure[2 * i + 1]);
+    map.Solve(k, P, power_scaling != 0);
+    const auto& Psi = map.GetData();
+    for (int i = 0; i < (int)Psi.rows(); ++i) psi_out[i] = Psi(i, 0);
+    const auto c = map.GetCenter();
+    for (int j = 0; j < 3; ++j) centre_out[j] = c(j);
+    if (save_to) Gpu_Wavesolver::FFAT_Map_Serialize::Save(save_to, map);
+    return (int)Psi.rows();
+}
 }

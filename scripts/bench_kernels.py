@@ -27,7 +27,8 @@ hbm = peaks["hbm_gbs"]
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 sp = stream.cuda_stream
 
-ffat_only = "--ffat-only" in sys.argv
+fit_only = "--fit-only" in sys.argv
+ffat_only = "--ffat-only" in sys.argv or fit_only
 # ---- K5 / K4: cfg3 sizes -----------------------------------------------------------------
 M, V = 2048, 20000; K = 3 * V
 quick = "--quick" in sys.argv
@@ -64,7 +65,7 @@ Mf = 1024
 freqs = synth.mode_frequencies(Mf, 1004)
 fm = pbso.FFATMaps.from_dicts(synth.ffat_maps(freqs, 2000))
 k3 = []
-for L in ([10242] if ffat_only else [64] if quick else [1, 64, 10242]):
+for L in ([] if fit_only else [10242] if ffat_only else [64] if quick else [1, 64, 10242]):
     pos = torch.from_numpy(synth.listeners(L, 5)).cuda()
     o = torch.empty(L, Mf, device="cuda", dtype=torch.float64)
     import ctypes as C
@@ -74,4 +75,27 @@ for L in ([10242] if ffat_only else [64] if quick else [1, 64, 10242]):
     bytes_alg = Mf * (min(D, 4 * L) * 8 + L * 8)
     k3.append({"L": L, "us": med * 1e3, "algorithmic_MB": bytes_alg / 1e6, "GBps": bytes_alg / (med * 1e-3) / 1e9, "frac_of_hbm": bytes_alg / (med * 1e-3) / 1e9 / hbm})
 out["K3_ffat_eval"] = {"modes": Mf, "texels": 6144, "runs": k3}
+
+# ---- K6: FFAT map construction (FFAT_Map<T,3>::Solve for all modes of an object at once) -------------
+# shells of 16/24/32 cells per edge (shell 2 = the 6 x 32 x 32 run-time map of the other configs), 1024 modes
+nm = 64 if quick else 1024
+w = synth.ffat_fit_workload(nm, 1006)
+ft = pbso.FFATFitter(w["cell_size"], w["V"], w["n_elements"])
+dk = torch.from_numpy(w["k"]).cuda()
+dp = torch.from_numpy(np.ascontiguousarray(w["pressure"]).view(np.float64)).cuda()
+dpsi = torch.empty(nm, ft.n_directions, dtype=torch.float64, device="cuda")
+dsc = torch.empty(nm, dtype=torch.float64, device="cuda")
+k6 = []
+for scaling in (False, True):
+    fn = lambda: ft.solve_device(nm, dk.data_ptr(), dp.data_ptr(), dpsi.data_ptr(), scaling, dsc.data_ptr(), sp)
+    med, best = ev_time(fn, iters=10)
+    alg = nm * (16 * ft.n_elements_total + 8 * ft.n_directions)          # complex samples read + Psi written
+    touched = nm * (32 * ft.n_elements_total + 8 * ft.n_directions)      # the reference layout interleaves unused entries
+    k6.append({"power_scaling": scaling, "us": med * 1e3, "algorithmic_MB": alg / 1e6, "GBps": alg / (med * 1e-3) / 1e9,
+               "frac_of_hbm": alg / (med * 1e-3) / 1e9 / hbm, "sector_MB": touched / 1e6,
+               "sector_GBps": touched / (med * 1e-3) / 1e9, "sector_frac_of_hbm": touched / (med * 1e-3) / 1e9 / hbm})
+t0 = time.perf_counter(); psi_h, _ = ft.Solve(w["k"], w["pressure"], True); host_ms = (time.perf_counter() - t0) * 1e3
+out["K6_ffat_fit"] = {"modes": nm, "shells": ft.n_shells, "n_elements_total": ft.n_elements_total, "n_directions": ft.n_directions,
+                      "runs": k6, "host_call_ms_incl_copies": host_ms, "host_call_kernel_ms": ft.last_kernel_ms(),
+                      "note": "algorithmic bytes = 16 B per shell sample + 8 B per Psi value; sector bytes count the unused odd entries of the reference's vector layout that share a 32 B sector with each sample"}
 print(json.dumps(out))

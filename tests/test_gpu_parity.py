@@ -459,3 +459,132 @@ def test_batch_tc3x_full_size_slice(pbso):
     ys = br.render_mix(256, n_buf, pbso.PREC_TC3X)
     assert np.max(np.abs(ys[5 * 256:] - ytc[:-5 * 256])) <= 2e-6 * np.max(np.abs(ytc))
     assert not ys[:5 * 256 + int(w["imp_buf"].min()) * 256].any()
+
+
+# --------------------------------------------------------------------------- K6: FFAT map construction
+def _fit_case(orc, n_maps, seed, **kw):
+    w = synth.ffat_fit_workload(n_maps, seed, **kw)
+    fit = orc.ffat_fit_geometry(w["cell_size"], w["V"], w["n_elements"])
+    return w, fit
+
+
+@pytest.mark.parametrize("half_cells,cell,centre", [
+    ((3, 5, 6), 0.25, (0.0, 0.0, 0.0)),
+    ((8, 12, 16), 0.09375, (0.0, 0.0, 0.0)),
+    (((2, 3, 4), (3, 5, 6), (5, 6, 8)), 0.2, (0.1, -0.05, 0.2)),            # ragged: 472 directions, non-cubic faces
+    (((2, 3, 4), (3, 5, 6), (5, 6, 8), (7, 8, 9)), 0.2, (0.0, 0.0, 0.0)),   # four shells: generic kernel
+    ((6, 5, 3), 0.25, (0.0, 0.0, 0.0)),                                     # shell 2 innermost
+])
+@pytest.mark.parametrize("scaling", [False, True])
+def test_ffat_fit_vs_oracle(pbso, orc, half_cells, cell, centre, scaling):
+    """FFAT_Map<T,3> constructor + Solve (+ Scaling) on the device against the restatement (itself pinned to the
+    reference's own Solve in tests/test_oracle_vs_ref.py).  FP64 throughout; what differs is the order of three-
+    and four-term sums and, with scaling, of the two reductions over directions."""
+    w, fit = _fit_case(orc, 7, 41, half_cells=half_cells, cell_size=cell, center=centre, noise=0.05)
+    ft = pbso.FFATFitter(w["cell_size"], w["V"], w["n_elements"])
+    assert (ft.n_shells, ft.n_elements_total, ft.n_directions) == (len(fit["strides"]), fit["n_total"], fit["n_dir"])
+    assert np.array_equal(ft.strides, fit["strides"])
+    for s in range(ft.n_shells):
+        g, ig = ft.shell(s)
+        assert np.array_equal(g, fit["geom"][s]) and np.array_equal(ig, fit["igeom"][s])      # constructor: bit-exact
+    psi, scale = ft.Solve(w["k"], w["pressure"], scaling)
+    want, wscale = orc.ffat_fit_solve(fit, w["k"], w["pressure"], scaling)
+    assert np.allclose(psi, want, rtol=1e-12, atol=0)
+    assert np.allclose(scale, wscale, rtol=1e-12, atol=0)
+
+
+def test_ffat_fit_many_modes_and_device_entry(pbso, orc):
+    """Enough modes that blocks fold several modes (stencil reuse) and the host entry chunks its staging; the
+    device-resident entry must give the same bits as the host entry."""
+    import torch
+    w, fit = _fit_case(orc, 300, 43, half_cells=(4, 6, 8), cell_size=0.1875)
+    ft = pbso.FFATFitter(w["cell_size"], w["V"], w["n_elements"])
+    psi, scale = ft.Solve(w["k"], w["pressure"], True)
+    want, wscale = orc.ffat_fit_solve(fit, w["k"], w["pressure"], True)
+    assert np.allclose(psi, want, rtol=1e-12, atol=0) and np.allclose(scale, wscale, rtol=1e-12, atol=0)
+    assert ft.last_kernel_ms() > 0
+    dk = torch.from_numpy(w["k"]).cuda()
+    dp = torch.from_numpy(np.ascontiguousarray(w["pressure"]).view(np.float64)).cuda()
+    dpsi = torch.empty(300, ft.n_directions, dtype=torch.float64, device="cuda")
+    dscale = torch.empty(300, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream()
+    ft.solve_device(300, dk.data_ptr(), dp.data_ptr(), dpsi.data_ptr(), True, dscale.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(dpsi.cpu().numpy(), psi) and np.array_equal(dscale.cpu().numpy(), scale)
+
+
+def test_ffat_fit_feeds_runtime_map(pbso, orc):
+    """Solve -> run-time map set -> computeTransfer: the whole chain against the oracle's chain, and the property the
+    fit exists for: on shell 2 itself |GetMapVal| reproduces a pure 1/(kr) field sampled on that shell."""
+    w, fit = _fit_case(orc, 5, 47, half_cells=(4, 6, 8), cell_size=0.1875)
+    ft = pbso.FFATFitter(w["cell_size"], w["V"], w["n_elements"])
+    psi, _ = ft.Solve(w["k"], w["pressure"], False)
+    maps = ft.to_maps(w["k"], psi)
+    pos = synth.listeners(64, 3)
+    got = maps.computeTransfer(pos)
+    opsi, _ = orc.ffat_fit_solve(fit, w["k"], w["pressure"], False)
+    g, ig = fit["geom"][2], fit["igeom"][2]
+    omaps = [dict(cellsize=g[0], lowcorners=g[1:19].reshape(6, 3), center1=g[19:22], bboxlow=g[22:25], bboxtop=g[25:28],
+                  center=g[28:31], k=w["k"][m], n_elements=ig[:12].reshape(6, 2), strides=ig[12:], psi=opsi[m], modeid=m) for m in range(5)]
+    assert np.allclose(got, orc.ffat_eval(omaps, pos), rtol=1e-11, atol=0)
+    # uniform-magnitude field: closed form of tests/test_oracle_kat.py::test_ffat_fit_uniform_field_closed_form
+    A, k = 2.0, 5.0
+    P = np.full((1, 2 * ft.n_elements_total), A * np.exp(0.7j))
+    psi1, _ = ft.Solve([k], P, False)
+    centres = w["V"][4 * fit["strides"][2]:].reshape(-1, 4, 3).mean(axis=1)
+    rho = np.array([4, 6, 8]) / 8.0
+    assert np.allclose(psi1[0], A * k * np.linalg.norm(centres, axis=1) * np.sum(1 / rho) / np.sum(1 / rho ** 2), rtol=1e-12)
+
+
+def test_ffat_fit_rejects_bad_arguments(pbso):
+    V, ne = synth.cubemap_vertices((0, 0, 0), 2, 0.5)
+    with pytest.raises(pbso.PbsoError) as e:                 # N_shells must reach _shells.at(2) (ffat_solver.h:982)
+        pbso.FFATFitter(0.5, np.concatenate([V, V]), np.stack([ne, ne]))
+    assert e.value.code == 1
+    with pytest.raises(pbso.PbsoError) as e:                 # V.block would run past the vertex list (:971)
+        pbso.FFATFitter(0.5, np.concatenate([V, V]), np.stack([ne, ne, ne]))
+    assert e.value.code == 1
+
+
+def test_ffat_fit_header_mirror_caller(pbso, orc, tmp_path):
+    """tests/cpp/ffat_fit_main.cpp: ReadNElementsFile + ReadComplexVector (text and binary) + FFAT_Map<double,3> ctor +
+    Solve + FFAT_Map_Serialize::Save/Load/Check + GetMapVal through the header mirror."""
+    import subprocess
+    from oracle import fatcube
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include", "openpbso"); libdir = os.path.join(root, "openpbso_b200")
+    exe = str(tmp_path / "ffat_fit_main")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I" + os.path.join(inc, "eigen_shim"), "-I" + inc,
+                        os.path.join(root, "tests", "cpp", "ffat_fit_main.cpp"), "-L" + libdir, "-lpbso_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    w, fit = _fit_case(orc, 1, 53, half_cells=((2, 3, 4), (3, 5, 6), (5, 6, 8)), cell_size=0.2)
+    nfile = str(tmp_path / "n_elements.txt")
+    with open(nfile, "w") as f:
+        for shell in w["n_elements"]:
+            f.write(" ".join("%d %d" % (a, b) for a, b in shell) + "\n")
+    vfile = str(tmp_path / "V.f64"); np.ascontiguousarray(w["V"]).tofile(vfile)
+    P = w["pressure"][0]
+    pbin = str(tmp_path / "p.bin")
+    with open(pbin, "wb") as f:
+        f.write(np.int32(2 * len(P)).tobytes()); f.write(np.ascontiguousarray(P).view(np.float64).tobytes())
+    ptxt = str(tmp_path / "p.txt")
+    with open(ptxt, "w") as f:
+        for z in P:
+            f.write("%.17g %.17g\n" % (z.real, z.imag))
+    probe = (2.0, -1.0, 3.5)
+    for scaling in (0, 1):
+        want, _ = orc.ffat_fit_solve(fit, w["k"], w["pressure"], bool(scaling))
+        for pfile, binary in ((pbin, 1), (ptxt, 0)):
+            out = str(tmp_path / ("m%d%d.fatcube" % (scaling, binary)))
+            r = subprocess.run([exe, nfile, vfile, repr(w["cell_size"]), "6", repr(float(w["k"][0])), pfile, str(binary), str(scaling),
+                                out] + [repr(x) for x in probe], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            rows, cols, v1, v2 = r.stdout.split()
+            assert (int(rows), int(cols)) == (fit["n_dir"], 1) and v1 == v2
+            d = fatcube.load(out)
+            assert d["modeid"] == 6 and np.allclose(d["psi"], want[0], rtol=1e-12, atol=0)
+            g, ig = fit["geom"][2], fit["igeom"][2]
+            m = dict(cellsize=g[0], lowcorners=g[1:19].reshape(6, 3), center1=g[19:22], bboxlow=g[22:25], bboxtop=g[25:28],
+                     center=g[28:31], k=w["k"][0], n_elements=ig[:12].reshape(6, 2), strides=ig[12:], psi=want[0], modeid=0)
+            assert np.isclose(float(v1), orc.ffat_eval([m], [probe])[0, 0], rtol=1e-11)

@@ -33,6 +33,10 @@ def test_compute_fails_loudly_without_device(pbso):
         pbso.ModeShapes(np.ones((2, 6)))
     with pytest.raises(pbso.PbsoError):
         pbso.measure_fma_peak(0)
+    V, ne = synth.cubemap_vertices((0, 0, 0), 2, 0.5)
+    with pytest.raises(pbso.PbsoError) as e:
+        pbso.FFATFitter(0.5, np.concatenate([V] * 3), np.stack([ne] * 3))
+    assert e.value.code == 6
 
 
 def _check_bits(m1, m2):
@@ -113,3 +117,10 @@ def test_argument_validation_without_device(pbso):
     assert L.pbso_integrator_destroy(None) == 0
     assert L.pbso_ffat_destroy(None) == 0 and L.pbso_modes_destroy(None) == 0 and L.pbso_batch_destroy(None) == 0
     assert b"N must be" in L.pbso_last_error() or True
+    # FFAT fitter: shell count and vertex-count checks come before any CUDA call
+    V, ne = synth.cubemap_vertices((0, 0, 0), 2, 0.5)
+    for shells, rows in ((2, 3), (3, 2)):
+        with pytest.raises(pbso.PbsoError) as e:
+            pbso.FFATFitter(0.5, np.concatenate([V] * rows), np.stack([ne] * shells))
+        assert e.value.code == 1
+    assert L.pbso_ffat_fitter_destroy(None) == 0

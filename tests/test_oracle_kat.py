@@ -177,3 +177,46 @@ def test_golden_cfg1_reproducible(orc, golden_dir):
     y = np.concatenate([s.step()[0] for _ in range(173)])
     assert np.max(np.abs(y - g["y"])) / np.max(np.abs(g["y"])) < 1e-11
     assert np.max(np.abs(g["y"])) / 1e10 == pytest.approx(0.5, rel=1e-6)
+
+
+# --------------------------------------------------------------------------- FFAT map construction
+def test_ffat_fit_uniform_field_closed_form(orc):
+    """Pressure of constant magnitude A and phase on concentric cube shells of half-widths a_s: every shell sees
+    |p_s| = A at radius r_s = r_2 a_s/a_2, so the one-column least squares (ffat_solver.h:881-895) gives
+    psi = A k r_2 (sum_s 1/rho_s) / (sum_s 1/rho_s^2), rho_s = a_s/a_2; and power scaling (:909-929) rescales so
+    that sum |p_0|^2 = sum (psi/(k r_0))^2."""
+    half = (4, 6, 8); cell = 0.125; A = 3.5; k = 7.25
+    Vs, nes = zip(*[synth.cubemap_vertices((0, 0, 0), h, cell) for h in half])
+    V = np.concatenate(Vs); ne = np.stack(nes)
+    fit = orc.ffat_fit_geometry(cell, V, ne)
+    assert fit["n_total"] == 6 * 4 * (16 + 36 + 64) and fit["n_dir"] == 6 * 256
+    assert list(fit["strides"]) == [0, 6 * 64, 6 * 64 + 6 * 144]
+    P = np.full((1, 2 * fit["n_total"]), A * np.exp(0.3j))
+    P[0, 1::2] = 99.0                                  # the odd (second-triangle) entries must never be read (:1054)
+    psi, scale, R, Pabs = orc.ffat_fit_solve(fit, [k], P, False, want_R=True)
+    assert np.allclose(Pabs, A, rtol=1e-14)
+    rho = np.array(half) / half[2]
+    assert np.allclose(R, R[:, 2:3] * rho, rtol=1e-14)
+    centres = V[4 * fit["strides"][2]:].reshape(-1, 4, 3).mean(axis=1)
+    assert np.allclose(R[:, 2], np.linalg.norm(centres, axis=1), rtol=1e-14)
+    want = A * k * R[:, 2] * np.sum(1 / rho) / np.sum(1 / rho ** 2)
+    assert np.allclose(psi[0], want, rtol=1e-13)
+    psi_s, scale_s = orc.ffat_fit_solve(fit, [k], P, True)
+    s = np.sqrt(fit["n_dir"] * A * A / np.sum((psi[0] / (k * R[:, 0])) ** 2))
+    assert np.isclose(scale_s[0], s, rtol=1e-13) and np.allclose(psi_s[0], psi[0] * s, rtol=1e-13)
+
+
+def test_ffat_fit_single_shell_weighting(orc):
+    """With the pressure zero on shells 0 and 1, only shell 2 contributes to u.b: psi = (|p_2|/(k r_2)) / sum_s 1/(k r_s)^2;
+    at shell 2 the stencil sits on texel centres, so |p_2| is the sample itself."""
+    half = (3, 4, 5); cell = 0.2; k = 2.0
+    Vs, nes = zip(*[synth.cubemap_vertices((0, 0, 0), h, cell) for h in half])
+    fit = orc.ffat_fit_geometry(cell, np.concatenate(Vs), np.stack(nes))
+    rng = np.random.default_rng(4)
+    P = np.zeros((1, 2 * fit["n_total"]), dtype=complex)
+    vals = rng.standard_normal(fit["n_dir"]) + 1j * rng.standard_normal(fit["n_dir"])
+    P[0, 2 * fit["strides"][2]::2] = vals
+    psi, _, R, Pabs = orc.ffat_fit_solve(fit, [k], P, False, want_R=True)
+    assert np.allclose(Pabs[0, :, 2], np.abs(vals), rtol=1e-14) and np.all(Pabs[0, :, :2] == 0)
+    want = (np.abs(vals) / (k * R[:, 2])) / np.sum(1 / (k * R) ** 2, axis=1)
+    assert np.allclose(psi[0], want, rtol=1e-13)

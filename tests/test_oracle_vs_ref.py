@@ -295,3 +295,59 @@ def test_offline_batch_matches_reference(orc, ref):
     mine = orc.batch_render(H, w["a"], w["b"], w["space"], w["trans"], w["imp_buf"], 256, 24)
     theirs = orc.ref_batch_render(H, w["a"], w["b"], w["space"], w["trans"], w["imp_buf"], 24)
     assert np.max(np.abs(mine - theirs)) <= 1e-11 * np.max(np.abs(theirs))
+
+
+# --------------------------------------------------------------------------- FFAT map construction
+FIT_CASES = [
+    # half cells per shell (int = cube, triple = per axis), cell size, centre
+    ((3, 5, 6), 0.25, (0.0, 0.0, 0.0)),
+    ((8, 12, 16), 0.09375, (0.0, 0.0, 0.0)),
+    (((2, 3, 4), (3, 5, 6), (5, 6, 8)), 0.2, (0.1, -0.05, 0.2)),                 # non-cubic, off-centre (box straddles 0)
+    (((2, 3, 4), (3, 5, 6), (5, 6, 8), (7, 8, 9)), 0.2, (0.0, 0.0, 0.0)),        # a fourth shell takes part in the fit
+    ((6, 5, 3), 0.25, (0.0, 0.0, 0.0)),                                          # shell 2 innermost: rays leave the box
+]
+
+
+@pytest.mark.parametrize("half_cells,cell,centre", FIT_CASES)
+@pytest.mark.parametrize("scaling", [False, True])
+def test_ffat_fit_matches_reference_solve(orc, ref, tmp_path, half_cells, cell, centre, scaling):
+    """FFAT_Map<double,3>(modeId, cellSize, V, N_elements) + Solve(k, p, powerScaling), the reference's own code
+    (ffat_solver.h:944-1069, :872-929), against the restatement; the shim supplies the one-column JacobiSVD."""
+    from oracle import fatcube
+    w = synth.ffat_fit_workload(3, 31, half_cells=half_cells, cell_size=cell, center=centre, noise=0.05)
+    fit = orc.ffat_fit_geometry(w["cell_size"], w["V"], w["n_elements"])
+    psi, scale = orc.ffat_fit_solve(fit, w["k"], w["pressure"], scaling)
+    assert psi.shape == (3, fit["n_dir"]) and np.all(np.isfinite(psi)) and np.all(psi > 0)
+    for m in range(3):
+        out = str(tmp_path / ("fit-%d.fatcube" % m))
+        rpsi, rcentre = orc.ref_ffat_fit(m, w["cell_size"], w["V"], w["n_elements"], w["k"][m], w["pressure"][m], scaling, save_to=out)
+        # the two differ by the summation order of three-term dot products only
+        assert np.allclose(rpsi, psi[m], rtol=1e-13, atol=0)
+        assert np.array_equal(rcentre, fit["geom"][2][28:31])
+        # geometry the reference's Save writes for shell 2 == the restated constructor's, bit for bit
+        d = fatcube.load(out)
+        g, ig = fit["geom"][2], fit["igeom"][2]
+        assert d["modeid"] == m and d["k"] == w["k"][m] and d["cellsize"] == g[0]
+        assert np.array_equal(np.asarray(d["lowcorners"]).ravel(), g[1:19])
+        assert np.array_equal(d["center1"], g[19:22]) and np.array_equal(d["bboxlow"], g[22:25]) and np.array_equal(d["bboxtop"], g[25:28])
+        assert np.array_equal(np.asarray(d["n_elements"]).ravel(), ig[:12]) and np.array_equal(d["strides"], ig[12:])
+        assert np.array_equal(d["psi"], rpsi)
+    if not scaling:
+        assert np.all(scale == 1.0)
+
+
+def test_ffat_fit_then_getmapval_matches_reference(orc, ref, tmp_path):
+    """Fit with the reference, save, LoadAll, |GetMapVal| -- against the oracle's fit fed to the oracle's evaluator."""
+    w = synth.ffat_fit_workload(4, 5, half_cells=(4, 6, 8), cell_size=0.1875)
+    fit = orc.ffat_fit_geometry(w["cell_size"], w["V"], w["n_elements"])
+    psi, _ = orc.ffat_fit_solve(fit, w["k"], w["pressure"], True)
+    d = tmp_path / "maps"; d.mkdir()
+    for m in range(4):
+        orc.ref_ffat_fit(m, w["cell_size"], w["V"], w["n_elements"], w["k"][m], w["pressure"][m], True, save_to=str(d / ("%d.fatcube" % m)))
+    pos = synth.listeners(40, 9)
+    got = orc.ref_ffat_eval(str(d), pos)
+    g, ig = fit["geom"][2], fit["igeom"][2]
+    maps = [dict(cellsize=g[0], lowcorners=g[1:19].reshape(6, 3), center1=g[19:22], bboxlow=g[22:25], bboxtop=g[25:28],
+                 center=g[28:31], k=w["k"][m], n_elements=ig[:12].reshape(6, 2), strides=ig[12:], psi=psi[m], modeid=m) for m in range(4)]
+    want = orc.ffat_eval(maps, pos)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
