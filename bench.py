@@ -224,16 +224,19 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def realtime_latency(pbso, synth, n_buffers=4000):
+def realtime_latency(pbso, synth, n_buffers=10000):
     """cfg2: one 1024-mode object, 256-sample buffers, Bernoulli(0.12) impulse stream, host pointers in
-    and out through pbso_render_buffer (H2D + kernel + D2H + sync per buffer)."""
+    and out through pbso_render_buffer (H2D + kernel + D2H + sync per buffer); the listener jumps every 50
+    buffers (computeTransfer on the device, K3 -> resident transfer table).  The jump is inside the timed call."""
     N = 1024
     mat = synth.MATERIALS["low_damping"]
     f = synth.mode_frequencies(N, 1002)
     a, b = synth.ab_from_material(f, mat)
     it = pbso.ModalIntegrator(N, synth.H, a, b)
+    fm = pbso.FFATMaps.from_dicts(synth.ffat_maps(f, 2000))
     rng = np.random.default_rng(1002)
-    it.set_transfer(np.abs(rng.standard_normal(N)) + 0.1)
+    listeners = synth.listeners(n_buffers // 50 + 1, 1002)
+    it.set_transfer_ffat(fm, listeners[:1])
     spaces = rng.standard_normal((64, N)); zero = np.zeros(N)
     tm_imp = np.zeros(BUF); tm_imp[0] = 1.0; tm_zero = np.zeros(BUF)
     hits = rng.random(n_buffers) < 0.12
@@ -243,14 +246,51 @@ def realtime_latency(pbso, synth, n_buffers=4000):
     for i in range(n_buffers):
         sp, tm = (spaces[i & 63], tm_imp) if hits[i] else (zero, tm_zero)
         t0 = time.perf_counter()
+        if i % 50 == 0:
+            it.set_transfer_ffat(fm, listeners[i // 50:i // 50 + 1])
         it.render_buffer(sp, tm)
         lat[i] = time.perf_counter() - t0
     it.close()
     us = lat * 1e6
-    return {"workload": "cfg2: 1024 modes, 1 listener, 256-sample buffers, Bernoulli(0.12) PointForce stream, host in/out",
+    return {"workload": "cfg2: 1024 modes, 1 listener (jumps every 50 buffers, FFAT re-evaluated on the device), 256-sample buffers, Bernoulli(0.12) PointForce stream, host in/out",
             "buffers": n_buffers, "p50_us": float(np.percentile(us, 50)), "p99_us": float(np.percentile(us, 99)),
             "p999_us": float(np.percentile(us, 99.9)), "max_us": float(us.max()),
             "mode_samples_per_s": float(N * BUF / np.mean(lat)), "dtype": "f64",
+            "budget_us": 1e6 * BUF / synth.SAMPLE_RATE}
+
+
+def moving_listeners_latency(pbso, synth, n_buffers=2000):
+    """cfg4: 1024 modes, 64 listeners random-walking on the r = 5 sphere; every buffer: 64 positions H2D, K3 into the
+    resident transfer table, one IIR pass rendering 64 outputs, 64 x 256 doubles D2H."""
+    N, L = 1024, 64
+    mat = synth.MATERIALS["low_damping"]
+    f = synth.mode_frequencies(N, 1004)
+    a, b = synth.ab_from_material(f, mat)
+    it = pbso.ModalIntegrator(N, synth.H, a, b)
+    fm = pbso.FFATMaps.from_dicts(synth.ffat_maps(f, 2000))
+    rng = np.random.default_rng(1004)
+    pos = synth.listeners(L, 1004); pos *= 5.0 / np.linalg.norm(pos, axis=1, keepdims=True)
+    spaces = rng.standard_normal((64, N)); zero = np.zeros(N)
+    tm_imp = np.zeros(BUF); tm_imp[0] = 1.0; tm_zero = np.zeros(BUF)
+    hits = rng.random(n_buffers) < 0.12
+    steps = 0.02 * rng.standard_normal((64, L, 3))
+    it.set_transfer_ffat(fm, pos)
+    for _ in range(100):
+        it.render_buffer(zero, tm_zero, want_qnorm=False)
+    lat = np.empty(n_buffers)
+    for i in range(n_buffers):
+        pos = pos + steps[i & 63]; pos *= 5.0 / np.linalg.norm(pos, axis=1, keepdims=True)
+        sp, tm = (spaces[i & 63], tm_imp) if hits[i] else (zero, tm_zero)
+        t0 = time.perf_counter()
+        it.set_transfer_ffat(fm, pos)
+        it.render_buffer(sp, tm, want_qnorm=False)
+        lat[i] = time.perf_counter() - t0
+    it.close()
+    us = lat * 1e6
+    return {"workload": "cfg4: 1024 modes, 64 moving listeners, FFAT re-evaluated every 256-sample buffer, host in/out",
+            "buffers": n_buffers, "p50_us": float(np.percentile(us, 50)), "p99_us": float(np.percentile(us, 99)),
+            "max_us": float(us.max()), "mode_samples_per_s": float(N * BUF / np.mean(lat)),
+            "listener_mode_samples_per_s": float(N * BUF * L / np.mean(lat)), "dtype": "f64",
             "budget_us": 1e6 * BUF / synth.SAMPLE_RATE}
 
 
@@ -430,6 +470,7 @@ def run_ours(args):
                                     cores, args.modes, n_samples, model, dt)}
     if not args.no_realtime:
         line["realtime"] = realtime_latency(pbso, synth)
+        line["moving_listeners"] = moving_listeners_latency(pbso, synth)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -88,6 +88,12 @@ int pbso_integrator_set_transfer(pbso_integrator* it, const double* transfer, in
                                  int L);
 int pbso_render_buffer(pbso_integrator* it, const double* space, const double* time, int T,
                        double* y_out, double* qnorm_out);
+/* Moving listeners: computeTransfer(pos, T*) for L positions (modal_solver.h:303-315; batched call
+ * site tools/real_time_modal_sound.cpp:921-927) evaluated by kernel K3 straight into the resident transfer table on
+ * the integrator's stream -- the n_transfer x L table never visits the host.  pos is L x 3; maps must hold mode ids
+ * 0..n_transfer-1 (PBSO_ERR_RANGE otherwise, like _ffat_maps->at()).  Takes effect for the next render call. */
+int pbso_integrator_set_transfer_ffat(pbso_integrator* it, const pbso_ffat* maps, int n_transfer,
+                                      const double* pos, int L);
 /* Same, enqueue-only on the handle's stream with device-resident inputs/outputs (no copies,
  * no sync).  d_y must hold L*T doubles. */
 int pbso_render_buffer_device(pbso_integrator* it, const double* d_space, const double* d_time,

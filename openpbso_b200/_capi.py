@@ -60,6 +60,7 @@ def lib():
             "pbso_integrator_set_state": [vp, c_dp, c_dp],
             "pbso_integrator_set_transfer": [vp, c_dp, C.c_int, C.c_int],
             "pbso_render_buffer": [vp, c_dp, c_dp, C.c_int, c_dp, c_dp],
+            "pbso_integrator_set_transfer_ffat": [vp, vp, C.c_int, c_dp, C.c_int],
             "pbso_render_buffer_device": [vp, vp, vp, C.c_int, vp, vp],
             "pbso_integrator_sync": [vp],
             "pbso_ffat_load_dir": [C.c_char_p, c_vpp],

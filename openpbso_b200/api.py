@@ -86,6 +86,12 @@ class ModalIntegrator:
         self.L = L
         check(lib().pbso_integrator_set_transfer(self._h, dp(t), t.shape[1] if L > 0 else 0, L))
 
+    def set_transfer_ffat(self, maps, pos, n_transfer=None):
+        """computeTransfer for L listener positions evaluated on the device into the resident table (cfg4)."""
+        pos = f64(pos).reshape(-1, 3)
+        self.L = len(pos)
+        check(lib().pbso_integrator_set_transfer_ffat(self._h, maps._h, self.N if n_transfer is None else n_transfer, dp(pos), self.L))
+
     def render_buffer(self, space, time, want_qnorm=True):
         """ModalSolver::step hot loop (modal_solver.h:261-272): returns (y[L][T], qnorm[N])."""
         space = f64(space); time = f64(time); T = len(time)

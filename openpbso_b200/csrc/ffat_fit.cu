@@ -20,7 +20,11 @@
 // quad (triangle pairs) of which one is read, so every 32-byte sector is half used; algorithmic bytes per mode
 // = 16 * N_elements_total + 8 * N_directions, DRAM traffic ~ 32 * N_elements_total + 8 * N_directions.
 // The power-scaling sums are reduced per block in a fixed order and finished by k_fit_scale (deterministic).
-// All arithmetic is FP64.
+// All arithmetic is FP64.  The one-column least squares is folded into the stencil: with b_s = 1/(k r_s),
+//   psi = (b . |p|) / (b . b) = k * sum_s c_s |p_s|,   c_s = (1/r_s) / sum_t (1/r_t)^2   (geometry only),
+// so the per-mode work has no division (the reference's form costs S + 2 of them per direction, and FP64 division
+// plus hypot made the first version of this kernel issue-bound at 0.44 of HBM peak); results differ from the
+// reference's evaluation order by a few ulp (tests hold 1e-12).
 // =============================================================================
 #include "common.cuh"
 #include "ffat_geom.cuh"
@@ -51,7 +55,8 @@ struct pbso_ffat_fitter {
     // stencil table, SoA over directions
     int* d_idx = nullptr;            // [S][4][n_dir]  element index into one mode's complex pressure vector
     double* d_w = nullptr;           // [S][4][n_dir]
-    double* d_r = nullptr;           // [S][n_dir]
+    double* d_c = nullptr;           // [S][n_dir]  least-squares weight of shell s
+    double* d_inv_r0 = nullptr;      // [n_dir]     1 / r on shell 0 (power scaling)
     // staging for the host-pointer entry
     double *d_k = nullptr, *d_p = nullptr, *d_psi = nullptr, *d_scale = nullptr, *d_partial = nullptr;
     size_t cap_maps = 0, cap_partial = 0;
@@ -63,7 +68,7 @@ struct pbso_ffat_fitter {
 __global__ void __launch_bounds__(FIT_THREADS)
 k_fit_stencil(int S, int n_dir, const double* __restrict__ geom, const int* __restrict__ igeom,
               const int* __restrict__ shell_strides, int* __restrict__ st_idx, double* __restrict__ st_w,
-              double* __restrict__ st_r) {
+              double* __restrict__ st_c, double* __restrict__ st_inv_r0) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_dir) return;
     Geo outer; load_geo(outer, geom + 2 * 32, igeom + 2 * 18);
@@ -81,38 +86,50 @@ k_fit_stencil(int S, int n_dir, const double* __restrict__ geom, const int* __re
     double pos0[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) pos0[a] = outer.low[face][a] + ijk[a] * outer.cell;         // :1035-1036
+    double inv_r[FIT_MAX_SHELLS], sum2 = 0.0;
     for (int s = 0; s < S; ++s) {
         Geo g; load_geo(g, geom + (size_t)s * 32, igeom + (size_t)s * 18);
         int idx[4]; double w[4], surf[3];
         ffat_locate_surf(g, pos0, idx, w, surf);                                             // :1043, :1051
         const double dx = surf[0] - outer.c1[0], dy = surf[1] - outer.c1[1], dz = surf[2] - outer.c1[2];
-        st_r[(size_t)s * n_dir + d] = sqrt(dx * dx + dy * dy + dz * dz);                     // :1046, _center = shell 2's (:982)
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);                                  // :1046, _center = shell 2's (:982)
+        inv_r[s] = 1.0 / r; sum2 += inv_r[s] * inv_r[s];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             st_idx[((size_t)s * 4 + kk) * n_dir + d] = 2 * shell_strides[s] + 2 * idx[kk];   // :1054-1056
             st_w[((size_t)s * 4 + kk) * n_dir + d] = w[kk];
         }
     }
+    for (int s = 0; s < S; ++s) st_c[(size_t)s * n_dir + d] = inv_r[s] / sum2;               // least-squares weights (:881-895)
+    st_inv_r0[d] = inv_r[0];                                                                 // Scaling reads shell 0 (:918-921)
 }
 
-// Per (direction, mode): interpolated pressure on each shell, one-column least squares, optional scaling sums.
+// |z| for the interpolated pressure: sqrt(re^2 + im^2) when that cannot over/underflow, hypot() (what std::abs of a
+// complex uses, :885) otherwise.
+__device__ __forceinline__ double cabs_fast(double re, double im) {
+    const double s = re * re + im * im;
+    if (s > 1e-280 && s < 1e280) return sqrt(s);
+    return hypot(re, im);
+}
+
+// Per (direction, mode): interpolated pressure on each shell, folded least squares, optional scaling sums.
 // S_T > 0: stencil held in registers across the block's modes.  S_T == 0: any shell count, stencil re-read (L2).
 template <int S_T>
 __global__ void __launch_bounds__(FIT_THREADS)
 k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, const int* __restrict__ st_idx,
-            const double* __restrict__ st_w, const double* __restrict__ st_r, const double* __restrict__ kvec,
-            const double2* __restrict__ pressure, double* __restrict__ psi_out, int power_scaling,
-            double2* __restrict__ partial) {
+            const double* __restrict__ st_w, const double* __restrict__ st_c, const double* __restrict__ st_inv_r0,
+            const double* __restrict__ kvec, const double2* __restrict__ pressure, double* __restrict__ psi_out,
+            int power_scaling, double2* __restrict__ partial) {
     const int S = S_T ? S_T : S_rt;
     const int d = blockIdx.x * FIT_THREADS + threadIdx.x;
     const bool live = d < n_dir;
     const int dc = live ? d : n_dir - 1;
     constexpr int SR = S_T ? S_T : 1;
-    int idx[SR][4]; double w[SR][4], r[SR];
+    int idx[SR][4]; double w[SR][4], c[SR];
     if (S_T) {
 #pragma unroll
         for (int s = 0; s < SR; ++s) {
-            r[s] = st_r[(size_t)s * n_dir + dc];
+            c[s] = st_c[(size_t)s * n_dir + dc];
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 idx[s][kk] = st_idx[((size_t)s * 4 + kk) * n_dir + dc];
@@ -120,52 +137,53 @@ k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, co
             }
         }
     }
+    const double inv_r0 = st_inv_r0[dc];
     __shared__ double2 s_red[FIT_THREADS / 32];
     const int m0 = blockIdx.y * maps_per_block, m1 = min(n_maps, m0 + maps_per_block);
     for (int m = m0; m < m1; ++m) {
         const double k = kvec[m];
         const double2* P = pressure + (size_t)m * 2 * n_total;
-        double ss2 = 0.0, ub = 0.0, pa0 = 0.0, kr0 = 1.0;
+        double acc = 0.0, pa0 = 0.0;
+        if (S_T) {
+            double2 v[SR][4];
 #pragma unroll
-        for (int s = 0; s < (S_T ? S_T : FIT_MAX_SHELLS); ++s) {
-            if (!S_T && s >= S) break;
-            int id[4]; double ww[4], rr;
-            if (S_T) {
+            for (int s = 0; s < SR; ++s)
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) { id[kk] = idx[S_T ? s : 0][kk]; ww[kk] = w[S_T ? s : 0][kk]; }
-                rr = r[S_T ? s : 0];
-            } else {
-                rr = st_r[(size_t)s * n_dir + dc];
+                for (int kk = 0; kk < 4; ++kk) v[s][kk] = __ldg(P + idx[s][kk]);       // all gathers in flight first
+#pragma unroll
+            for (int s = 0; s < SR; ++s) {
+                double pre = 0.0, pim = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) { pre += w[s][kk] * v[s][kk].x; pim += w[s][kk] * v[s][kk].y; }   // ffat_solver.h:1052-1057
+                const double p2 = cabs_fast(pre, pim);                                 // :885
+                acc += c[s] * p2;
+                if (s == 0) pa0 = p2;
+            }
+        } else {
+            for (int s = 0; s < S; ++s) {
+                double pre = 0.0, pim = 0.0;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    id[kk] = st_idx[((size_t)s * 4 + kk) * n_dir + dc];
-                    ww[kk] = st_w[((size_t)s * 4 + kk) * n_dir + dc];
+                    const double2 v = __ldg(P + st_idx[((size_t)s * 4 + kk) * n_dir + dc]);
+                    const double ww = st_w[((size_t)s * 4 + kk) * n_dir + dc];
+                    pre += ww * v.x; pim += ww * v.y;
                 }
+                const double p2 = cabs_fast(pre, pim);
+                acc += st_c[(size_t)s * n_dir + dc] * p2;
+                if (s == 0) pa0 = p2;
             }
-            double pre = 0.0, pim = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {                                   // ffat_solver.h:1052-1057
-                const double2 v = __ldg(P + id[kk]);
-                pre += ww[kk] * v.x; pim += ww[kk] * v.y;
-            }
-            const double p2 = hypot(pre, pim);                                 // :885 std::abs(complex)
-            const double kr = rr * k;                                          // :882
-            const double basis = 1.0 / kr;                                     // :883
-            ss2 += basis * basis; ub += basis * p2;
-            if (s == 0) { pa0 = p2; kr0 = kr; }
         }
-        const double sigma = sqrt(ss2);
-        const double psi = (ub / sigma) / sigma;                               // :888-895 (one-column SVD solve)
+        const double psi = k * acc;                                                    // :888-895, folded
         if (live) psi_out[(size_t)m * n_dir + d] = psi;
-        if (power_scaling) {                                                   // :918-923, shell 0
-            const double q = psi / kr0;
-            double2 acc = live ? make_double2(pa0 * pa0, q * q) : make_double2(0.0, 0.0);
+        if (power_scaling) {                                                           // :918-923, shell 0
+            const double q = acc * inv_r0;                                             // psi / (k r_0)
+            double2 t2 = live ? make_double2(pa0 * pa0, q * q) : make_double2(0.0, 0.0);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                acc.x += __shfl_down_sync(0xffffffffu, acc.x, o);
-                acc.y += __shfl_down_sync(0xffffffffu, acc.y, o);
+                t2.x += __shfl_down_sync(0xffffffffu, t2.x, o);
+                t2.y += __shfl_down_sync(0xffffffffu, t2.y, o);
             }
-            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t2;
             __syncthreads();
             if (threadIdx.x == 0) {
                 double2 t = s_red[0];
@@ -221,10 +239,10 @@ static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, cons
     const double2* P = reinterpret_cast<const double2*>(d_p);
     double2* part = reinterpret_cast<double2*>(f->d_partial);
     if (f->S == 3)
-        k_fit_solve<3><<<grid, FIT_THREADS, 0, s>>>(3, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w, f->d_r, d_k, P,
+        k_fit_solve<3><<<grid, FIT_THREADS, 0, s>>>(3, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w, f->d_c, f->d_inv_r0, d_k, P,
                                                     d_psi, power_scaling, part);
     else
-        k_fit_solve<0><<<grid, FIT_THREADS, 0, s>>>(f->S, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w, f->d_r, d_k, P,
+        k_fit_solve<0><<<grid, FIT_THREADS, 0, s>>>(f->S, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w, f->d_c, f->d_inv_r0, d_k, P,
                                                     d_psi, power_scaling, part);
     PBSO_CUDA(cudaGetLastError());
     if (power_scaling) {
@@ -303,12 +321,13 @@ int pbso_ffat_fitter_create(double cell_size, const double* V, int n_rows, const
     if (e == cudaSuccess) e = cudaMalloc(&d_ss, n_shells * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&f->d_idx, nd * 4 * n_shells * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&f->d_w, nd * 4 * n_shells * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_r, nd * n_shells * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_c, nd * n_shells * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_inv_r0, nd * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_geom, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice, f->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_igeom, igeom.data(), igeom.size() * sizeof(int), cudaMemcpyHostToDevice, f->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_ss, f->shell_strides.data(), n_shells * sizeof(int), cudaMemcpyHostToDevice, f->stream);
     if (e == cudaSuccess) {
-        k_fit_stencil<<<div_up(f->n_dir, FIT_THREADS), FIT_THREADS, 0, f->stream>>>(n_shells, f->n_dir, d_geom, d_igeom, d_ss, f->d_idx, f->d_w, f->d_r);
+        k_fit_stencil<<<div_up(f->n_dir, FIT_THREADS), FIT_THREADS, 0, f->stream>>>(n_shells, f->n_dir, d_geom, d_igeom, d_ss, f->d_idx, f->d_w, f->d_c, f->d_inv_r0);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
@@ -323,7 +342,7 @@ int pbso_ffat_fitter_destroy(pbso_ffat_fitter* f) {
     if (f->stream) {
         DeviceGuard g(f->device);
         cudaStreamSynchronize(f->stream);
-        cudaFree(f->d_idx); cudaFree(f->d_w); cudaFree(f->d_r);
+        cudaFree(f->d_idx); cudaFree(f->d_w); cudaFree(f->d_c); cudaFree(f->d_inv_r0);
         cudaFree(f->d_k); cudaFree(f->d_p); cudaFree(f->d_psi); cudaFree(f->d_scale); cudaFree(f->d_partial);
         if (f->ev0) cudaEventDestroy(f->ev0);
         if (f->ev1) cudaEventDestroy(f->ev1);

@@ -32,6 +32,8 @@ struct pbso_integrator {
     double* d_in = nullptr;       // staging: space[N] | time[Tcap]
     double* d_out = nullptr;      // staging: y[L*Tcap] | qnorm[N]
     double* d_trans = nullptr;    // transfer[L][n_transfer]
+    double* d_pos = nullptr;      // listener positions for set_transfer_ffat
+    int pos_cap = 0;
     int n_transfer = 0, L = 0, Tcap = 0, Lcap = 0;
     double* h_in = nullptr;       // pinned mirrors of d_in / d_out
     double* h_out = nullptr;
@@ -270,7 +272,7 @@ int pbso_integrator_destroy(pbso_integrator* it) {
     DeviceGuard g(it->device);
     if (it->stream) cudaStreamSynchronize(it->stream);
     cudaFree(it->d_c); cudaFree(it->d_q); cudaFree(it->d_q_alt); cudaFree(it->d_in); cudaFree(it->d_out);
-    cudaFree(it->d_trans);
+    cudaFree(it->d_trans); cudaFree(it->d_pos);
     if (it->h_in) cudaFreeHost(it->h_in);
     if (it->h_out) cudaFreeHost(it->h_out);
     if (it->stream) cudaStreamDestroy(it->stream);
@@ -339,11 +341,37 @@ int pbso_integrator_set_transfer(pbso_integrator* it, const double* transfer, in
     PBSO_CUDA(cudaStreamSynchronize(it->stream));
     const size_t need = (size_t)L * n_transfer;
     if (need > (size_t)it->Lcap) {
-        cudaFree(it->d_trans);
+        cudaFree(it->d_trans); cudaFree(it->d_pos);
         PBSO_CUDA(cudaMalloc(&it->d_trans, sizeof(double) * need));
         it->Lcap = (int)need;
     }
     if (need) PBSO_CUDA(cudaMemcpy(it->d_trans, transfer, sizeof(double) * need, cudaMemcpyHostToDevice));
+    it->n_transfer = n_transfer; it->L = L;
+    return PBSO_OK;
+}
+
+int pbso_integrator_set_transfer_ffat(pbso_integrator* it, const pbso_ffat* maps, int n_transfer, const double* pos, int L) {
+    PBSO_REQUIRE(it && maps, PBSO_ERR_INVALID, "null handle");
+    PBSO_REQUIRE(L > 0 && pos, PBSO_ERR_INVALID, "need at least one listener position");
+    PBSO_REQUIRE(n_transfer > 0 && n_transfer <= it->N, PBSO_ERR_INVALID,
+                 "transfer size must be <= N (q.head(n).dot(transfer), modal_solver.h:268)");
+    DeviceGuard g(it->device);
+    const size_t need = (size_t)L * n_transfer;
+    if (need > (size_t)it->Lcap) {                       // grow: wait for renders that still read the old table
+        PBSO_CUDA(cudaStreamSynchronize(it->stream));
+        cudaFree(it->d_trans); it->d_trans = nullptr; it->Lcap = 0;
+        PBSO_CUDA(cudaMalloc(&it->d_trans, sizeof(double) * need));
+        it->Lcap = (int)need;
+    }
+    if (3 * L > it->pos_cap) {
+        PBSO_CUDA(cudaStreamSynchronize(it->stream));
+        cudaFree(it->d_pos); it->d_pos = nullptr; it->pos_cap = 0;
+        PBSO_CUDA(cudaMalloc(&it->d_pos, sizeof(double) * 3 * L));
+        it->pos_cap = 3 * L;
+    }
+    // stream order does the rest: K3 writes the table after earlier renders have read it and before the next one
+    PBSO_CUDA(cudaMemcpyAsync(it->d_pos, pos, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, it->stream));
+    if (int rc = pbso_ffat_eval_device(maps, n_transfer, it->d_pos, L, it->d_trans, it->stream)) return rc;
     it->n_transfer = n_transfer; it->L = L;
     return PBSO_OK;
 }

@@ -165,6 +165,35 @@ def test_render_buffer_many_listeners(pbso, orc):
         assert np.max(np.abs(y - yr)) <= 1e-9 * np.max(np.abs(yr))
 
 
+def test_moving_listeners_transfer_stays_on_device(pbso, orc):
+    """cfg4: per buffer, computeTransfer for every listener (K3) lands in the integrator's transfer table without a host
+    round trip, then one IIR pass renders all listeners.  Against the oracle's ffat_eval + integrator."""
+    N, L, T = 200, 64, 256
+    f = synth.mode_frequencies(N, 1004); a, b = synth.ab_from_material(f, synth.MATERIALS["low_damping"])
+    maps = synth.ffat_maps(f, 2000, n=8)
+    fm = pbso.FFATMaps.from_dicts(maps)
+    it = pbso.ModalIntegrator(N, H, a, b); ref = orc.Integrator(H, a, b)
+    rng = np.random.default_rng(8)
+    pos = synth.listeners(L, 21)
+    for rep in range(4):
+        pos = pos + 0.05 * rng.standard_normal(pos.shape)                 # listeners move every buffer
+        it.set_transfer_ffat(fm, pos)
+        tr = orc.ffat_eval(maps, pos)                                     # [L][N]
+        sp = rng.standard_normal(N); tm = np.zeros(T); tm[0] = 1.0 if rep % 2 == 0 else 0.0
+        y, _ = it.render_buffer(sp, tm)
+        q = np.array([ref.step(sp * tm[i]) for i in range(T)])
+        yr = (q @ tr.T).T
+        assert y.shape == (L, T)
+        assert np.max(np.abs(y - yr)) <= 1e-9 * np.max(np.abs(yr))
+    it.set_transfer_ffat(fm, pos[:3], n_transfer=150)                     # fewer listeners / modes: q.head(n).dot(transfer)
+    y, _ = it.render_buffer(np.zeros(N), np.zeros(T))
+    q = np.array([ref.step() for i in range(T)])
+    assert np.max(np.abs(y - (q[:, :150] @ orc.ffat_eval(maps[:150], pos[:3]).T).T)) <= 1e-9 * np.max(np.abs(q))
+    with pytest.raises(pbso.PbsoError) as e:                              # _ffat_maps->at(ii) past the last map
+        it.set_transfer_ffat(pbso.FFATMaps.from_dicts(maps[:10]), pos)
+    assert e.value.code == 5
+
+
 # --------------------------------------------------------------------------- K3 FFAT
 def test_ffat_shared_geometry(pbso, orc):
     freqs = synth.mode_frequencies(200, 1004)
