@@ -56,6 +56,10 @@ struct pbso_ffat {
     cudaStream_t stream = nullptr;
     double* d_pos = nullptr; double* d_out = nullptr; size_t pos_cap = 0, out_cap = 0;
     void* d_loc = nullptr; size_t loc_cap = 0;          // per-listener stencils (shared-geometry path)
+    void* d_tile_rec = nullptr; size_t tile_rec_cap = 0;    // [n_tiles][L] stencil records binned by texel tile (texel-tile path)
+    double* d_psi_tiles = nullptr;                          // [slab][tile][FT_H*FT_H + 1][FT_MS]: each work item's texels contiguous (built on first use)
+    int* d_tile_cnt = nullptr; int cnt_parity = 0;          // [2][n_tiles] ping-pong counters: a call fills one, zeroes the other
+    int tiles_y[6] = {0}, tile_base[7] = {0};           // texel tiles of FT_T x FT_T per face (shared geometry)
     int n_uncompressed = 0, n_compressed = 0;
     int sm_count = 148;           // leading maps with is_compressed == false / true
 };
@@ -85,19 +89,34 @@ k_ffat_eval_general(int n_modes, int L, const double* __restrict__ geom, const i
 //  k_ffat_gather: block = 256 modes x FG_LPB listeners; the stencil sits in shared memory, every thread gathers its
 //                 mode's four texels from the texel-major table -- a warp reads 32 consecutive doubles per texel
 //                 row, fully coalesced -- and writes out[l][m] coalesced.  k differs per mode (geom[m][31]).
-struct __align__(16) FfatLoc { int idx[4]; double w[4]; double r; double pad; };   // 64 B: int4 + 3 x double2 loads
+struct __align__(16) FfatLoc { int idx[4]; double w[4]; double r; int tile; int lxy; };   // 64 B: int4 + 3 x double2 loads
+// lxy: position of the stencil's low corner inside its texel tile and the clamp flags: lx | ly << 4 | (xp - x) << 8 | (yp - y) << 9
+constexpr int FT_T = 8;                 // texel tile edge
+struct TileTable { int tiles_y[6]; int tile_base[7]; };
+// What k_ffat_tiles needs of one listener, stored in its tile's bin: bilinear weights, 1/r, listener id, lxy.
+struct __align__(16) TileRec { double w[4]; double inv_r; int l; int lxy; };   // 48 B
 
-__global__ void __launch_bounds__(128)
-k_ffat_locate(int L, const double* __restrict__ geom, const int* __restrict__ igeom,
-              const double* __restrict__ pos, FfatLoc* __restrict__ loc) {
+__global__ void __launch_bounds__(64)
+k_ffat_locate(int L, const __grid_constant__ Geo g,        // the shared geometry rides in the parameter bank: no global round trip
+              const double* __restrict__ pos, FfatLoc* __restrict__ loc, TileTable tt, TileRec* __restrict__ tile_rec,
+              int* __restrict__ cnt_cur, int* __restrict__ cnt_next) {
+    // programmatic dependent launch: let k_ffat_tiles start staging its texel tiles now; it waits (griddepcontrol.wait)
+    // for this grid to finish before it reads the bins
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile_rec && l <= tt.tile_base[6]) cnt_next[l] = 0;                // the NEXT call's counters (ping-pong, no extra launch)
     if (l >= L) return;
-    Geo g; load_geo(g, geom, igeom);
     const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
-    FfatLoc o;
-    ffat_locate(g, p, o.idx, o.w, o.r);
-    o.pad = 0.0;
-    loc[l] = o;
+    FfatLoc o; int fxy[5];
+    ffat_locate(g, p, o.idx, o.w, o.r, fxy);
+    o.tile = tt.tile_base[fxy[0]] + (fxy[1] / FT_T) * tt.tiles_y[fxy[0]] + fxy[2] / FT_T;
+    o.lxy = (fxy[1] % FT_T) | (fxy[2] % FT_T) << 4 | fxy[3] << 8 | fxy[4] << 9;
+    if (tile_rec) {                                                      // bin by tile; order within a bin is irrelevant
+        TileRec t; t.w[0] = o.w[0]; t.w[1] = o.w[1]; t.w[2] = o.w[2]; t.w[3] = o.w[3]; t.inv_r = 1.0 / o.r; t.l = l; t.lxy = o.lxy;
+        tile_rec[(size_t)o.tile * L + atomicAdd(&cnt_cur[o.tile], 1)] = t;
+    } else {
+        loc[l] = o;
+    }
 }
 
 constexpr int FG_LPB = 8;
@@ -119,6 +138,176 @@ k_ffat_gather(int n_modes, int L, const double* __restrict__ geom, const double*
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * psi_tm[(size_t)q.idx[kk] * n_stride + m];    // ffat_solver.h:1198-1204
         out[(size_t)(l0 + i) * n_modes + m] = fabs(psi0 / (k * q.r));                                  // :904-905
+    }
+}
+
+// Many listeners, texel-stationary (default for L >= FT_MIN_L): when 4 L exceeds the texel count, gathering per
+// listener re-reads every texel row from L2 several times (4 L M 8 bytes: 335 MB for 10 242 listeners x 1024 modes, the
+// bound of k_ffat_gather).  Here a CTA owns one FT_T x FT_T texel tile (plus the one-texel halo the bilinear stencil
+// reaches into) of FT_MS consecutive modes: the item's texels are ONE contiguous block of a tiled copy of Psi and are
+// pulled into shared memory with a single bulk async copy (cp.async.bulk + mbarrier, SASS UBLKCP; 41 KB -- issuing the
+// tile as 81 row copies from the texel-major table made the producer the bottleneck); k_ffat_locate has already binned the
+// listeners' stencil records by the tile their stencil starts in (one global atomic each), so the tile's records are
+// one contiguous run that rides in with the same barrier.  Then one warp per listener: lanes
+// own four modes each, read the four texels from shared memory conflict-free, and store |psi/(k r)| as two coalesced
+// 512-byte runs of out[l][*].  HBM traffic: the table once (x 81/64 for the halo) plus the output.
+constexpr int FT_H = FT_T + 1;          // tile edge incl. halo
+#ifndef PBSO_FT_MS
+#define PBSO_FT_MS 128
+#endif
+constexpr int FT_MS = PBSO_FT_MS;       // modes per CTA (64 or 128): lanes own FT_MS / 32 modes
+constexpr int FT_CW = 16;               // consumer warps
+constexpr int FT_CTAS_PER_SM = 1;       // 2 x (81 KB tile + 12 KB records) of shared memory per CTA
+constexpr int FT_THREADS = (FT_CW + 1) * 32;   // + one producer warp
+constexpr int FT_MIN_L = 2048;
+constexpr int FT_REC = 256;             // listener records staged per pass (12 KB)
+constexpr int FT_BLK = (FT_H * FT_H + 1) * FT_MS;   // doubles per work item in the tiled table: texel rows + one row of 1/k
+
+// Persistent, warp-specialised: FT_CW consumer warps + one producer warp per CTA, one CTA per SM.  The producer claims
+// work items (tile, mode slab) from a global counter, stages the item's texel rows into one of two tile buffers and its
+// listener records (FT_REC at a time) into one of two record buffers, all with bulk async copies that complete on
+// "full" mbarriers; consumers release buffers through "empty" mbarriers.  Loads of item i+1 overlap the arithmetic and
+// the output stores of item i.
+__device__ __forceinline__ void ft_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+struct FtItem { int tile, m0, cnt, pad; };
+
+__global__ void __launch_bounds__(FT_THREADS, FT_CTAS_PER_SM)
+k_ffat_tiles(int n_modes, int L, int n_items, int n_tiles,
+             const double* __restrict__ psi_tiles, const TileRec* __restrict__ tile_rec,
+             const int* __restrict__ tile_cnt, int* __restrict__ work_counter, double* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char ft_smem[];
+    constexpr size_t PSI_BYTES = (size_t)FT_BLK * sizeof(double);
+    double* s_psi0 = reinterpret_cast<double*>(ft_smem);                                  // [2][FT_H * FT_H + 1][FT_MS]: texels, then 1/k
+    TileRec* s_rec0 = reinterpret_cast<TileRec*>(ft_smem + 2 * PSI_BYTES);                // [2][FT_REC]
+    __shared__ __align__(8) unsigned long long s_bar[8];    // full_psi[2], empty_psi[2], full_rec[2], empty_rec[2]
+    __shared__ FtItem s_item[2];
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
+    auto full_psi = [&](int b) { return bar0 + 8u * b; };
+    auto empty_psi = [&](int b) { return bar0 + 16u + 8u * b; };
+    auto full_rec = [&](int b) { return bar0 + 32u + 8u * b; };
+    auto empty_rec = [&](int b) { return bar0 + 48u + 8u * b; };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_psi(b)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_psi(b)), "r"(FT_CW));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_rec(b)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_rec(b)), "r"(FT_CW));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == FT_CW) {
+        // ------------------------------------------------------------------ producer warp
+        int rec_it = 0;                                                   // record chunks issued so far
+        bool dep_waited = false;
+        // Work items are claimed from a global counter (listener counts per tile differ by ~5x between face centres
+        // and corners, so a static split leaves a long tail).  The claim and the listener count of the NEXT item are
+        // requested one iteration ahead, so neither global round trip sits on the producer's critical path.
+        int item = blockIdx.x, cnt_next = 0, next_item = 0;
+        if (lane == 0) next_item = atomicAdd(work_counter, 1) + gridDim.x;
+        for (int it = 0;; ++it) {
+            const int pb = it & 1;
+            if (it >= 2) ft_wait(empty_psi(pb), (unsigned)(((it >> 1) - 1) & 1));
+            if (item >= n_items) {
+                if (lane == 0) {
+                    s_item[pb].tile = -1;
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_psi(pb)) : "memory");
+                }
+                break;
+            }
+            const int tile = item % n_tiles, m0 = (item / n_tiles) * FT_MS;
+            // the item's texels (tile + halo, FT_MS modes) are one contiguous block of the tiled table: a single bulk
+            // copy.  They do not depend on the listeners: on the first item the copy is requested before
+            // k_ffat_locate (the grid this one is launched behind) has finished
+            if (lane == 0) {
+                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full_psi(pb)), "r"((unsigned)PSI_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((unsigned)__cvta_generic_to_shared(s_psi0 + (size_t)pb * FT_BLK)),
+                               "l"(psi_tiles + (size_t)item * FT_BLK), "r"((unsigned)PSI_BYTES), "r"(full_psi(pb)) : "memory");
+            }
+            if (!dep_waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); dep_waited = true; }
+            int cnt = cnt_next;
+            if (it == 0) { if (lane == 0) cnt = tile_cnt[tile]; cnt = __shfl_sync(0xffffffffu, cnt, 0); }
+            if (lane == 0) {
+                s_item[pb].tile = tile; s_item[pb].m0 = m0; s_item[pb].cnt = cnt;
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_psi(pb)) : "memory");   // + tx bytes => phase done
+            }
+            const TileRec* rec = tile_rec + (size_t)tile * L;
+            for (int r0 = 0; r0 < cnt; r0 += FT_REC, ++rec_it) {
+                const int rb = rec_it & 1, nrec = min(FT_REC, cnt - r0);
+                if (rec_it >= 2) ft_wait(empty_rec(rb), (unsigned)(((rec_it >> 1) - 1) & 1));
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_rec(rb)), "r"((unsigned)(nrec * sizeof(TileRec))) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((unsigned)__cvta_generic_to_shared(s_rec0 + (size_t)rb * FT_REC)), "l"(rec + r0),
+                                   "r"((unsigned)(nrec * sizeof(TileRec))), "r"(full_rec(rb)) : "memory");
+                }
+            }
+            item = __shfl_sync(0xffffffffu, next_item, 0);                 // claimed one iteration ago
+            cnt_next = 0;
+            if (lane == 0) {
+                if (item < n_items) cnt_next = tile_cnt[item % n_tiles];   // used next iteration
+                next_item = atomicAdd(work_counter, 1) + gridDim.x;
+            }
+            cnt_next = __shfl_sync(0xffffffffu, cnt_next, 0);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const bool vec = (n_modes & 1) == 0;
+    int rec_it = 0;
+    for (int it = 0;; ++it) {
+        const int pb = it & 1;
+        ft_wait(full_psi(pb), (unsigned)((it >> 1) & 1));
+        const int tile = s_item[pb].tile;
+        if (tile < 0) break;
+        const int m0 = s_item[pb].m0, cnt = s_item[pb].cnt;
+        const int live = min(FT_MS, n_modes - m0);
+        const double* s_psi = s_psi0 + (size_t)pb * FT_BLK;
+        // this lane's modes: m0 + 64 h + 2 lane + {0, 1}, h < FT_MS / 64; their 1/k rides in the item's block
+        double inv_k[FT_MS / 32];
+#pragma unroll
+        for (int j = 0; j < FT_MS / 32; ++j) inv_k[j] = s_psi[FT_H * FT_H * FT_MS + (j >> 1) * 64 + 2 * lane + (j & 1)];
+        for (int r0 = 0; r0 < cnt; r0 += FT_REC, ++rec_it) {
+            const int rb = rec_it & 1, nrec = min(FT_REC, cnt - r0);
+            ft_wait(full_rec(rb), (unsigned)((rec_it >> 1) & 1));
+            const TileRec* s_rec = s_rec0 + (size_t)rb * FT_REC;
+#pragma unroll 2
+            for (int i = warp; i < nrec; i += FT_CW) {
+                const TileRec q = s_rec[i];
+                const int lx = q.lxy & 15, ly = (q.lxy >> 4) & 15, dx = (q.lxy >> 8) & 1, dy = (q.lxy >> 9) & 1;
+                const double* t00 = s_psi + (size_t)(lx * FT_H + ly) * FT_MS;
+                const double* t10 = t00 + (size_t)dx * FT_H * FT_MS;                       // (xp, y)
+                const double* t01 = t00 + (size_t)dy * FT_MS;                              // (x, yp)
+                const double* t11 = t10 + (size_t)dy * FT_MS;                              // (xp, yp)
+                double* o = out + (size_t)q.l * n_modes + m0;
+#pragma unroll
+                for (int h = 0; h < FT_MS / 64; ++h) {
+                    const int c = h * 64 + 2 * lane;
+                    const double2 a = *reinterpret_cast<const double2*>(t00 + c), b = *reinterpret_cast<const double2*>(t10 + c);
+                    const double2 cc = *reinterpret_cast<const double2*>(t01 + c), d = *reinterpret_cast<const double2*>(t11 + c);
+                    double v0 = 0.0, v1 = 0.0;                                             // ffat_solver.h:1198-1204, same order
+                    v0 += q.w[0] * a.x; v0 += q.w[1] * b.x; v0 += q.w[2] * cc.x; v0 += q.w[3] * d.x;
+                    v1 += q.w[0] * a.y; v1 += q.w[1] * b.y; v1 += q.w[2] * cc.y; v1 += q.w[3] * d.y;
+                    v0 = fabs(v0 * inv_k[2 * h] * q.inv_r); v1 = fabs(v1 * inv_k[2 * h + 1] * q.inv_r);   // |psi / (k r)|, :904-905
+                    if (vec && c + 1 < live) *reinterpret_cast<double2*>(o + c) = make_double2(v0, v1);
+                    else { if (c < live) o[c] = v0; if (c + 1 < live) o[c + 1] = v1; }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_rec(rb)) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_psi(pb)) : "memory");
     }
 }
 
@@ -259,8 +448,8 @@ static int load_one(const char* filename, HostMap& hm) {
 }
 
 static void free_device(pbso_ffat* f) {
-    cudaFree(f->d_geom); cudaFree(f->d_igeom); cudaFree(f->d_psi_mm); cudaFree(f->d_psi_tm); cudaFree(f->d_psi_off);
-    f->d_geom = nullptr; f->d_igeom = nullptr; f->d_psi_mm = nullptr; f->d_psi_tm = nullptr; f->d_psi_off = nullptr;
+    cudaFree(f->d_geom); cudaFree(f->d_igeom); cudaFree(f->d_psi_mm); cudaFree(f->d_psi_tm); cudaFree(f->d_psi_off); cudaFree(f->d_psi_tiles);
+    f->d_psi_tiles = nullptr; f->d_geom = nullptr; f->d_igeom = nullptr; f->d_psi_mm = nullptr; f->d_psi_tm = nullptr; f->d_psi_off = nullptr;
 }
 
 static int ensure_device(pbso_ffat* f) {
@@ -309,6 +498,16 @@ static int ensure_device(pbso_ffat* f) {
         PBSO_CUDA(cudaMalloc(&f->d_psi_tm, tm.size() * sizeof(double)));
         PBSO_CUDA(cudaMemcpy(f->d_psi_tm, tm.data(), tm.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    if (f->shared_geom) {
+        int tb = 0;
+        for (int fc = 0; fc < 6; ++fc) {
+            const int nx = first.igeom[2 * fc], ny = first.igeom[2 * fc + 1];
+            f->tiles_y[fc] = (ny + FT_T - 1) / FT_T;
+            f->tile_base[fc] = tb;
+            tb += ((nx + FT_T - 1) / FT_T) * f->tiles_y[fc];
+        }
+        f->tile_base[6] = tb;
+    }
     f->n_uncompressed = 0; while (f->n_uncompressed < n && !f->maps.at(f->n_uncompressed).is_compressed) ++f->n_uncompressed;
     f->n_compressed = 0; while (f->n_compressed < n && f->maps.at(f->n_compressed).is_compressed) ++f->n_compressed;
     f->dirty = false;
@@ -318,18 +517,80 @@ static int ensure_device(pbso_ffat* f) {
 static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, double* d_out, cudaStream_t s) {
     if (f->shared_geom) {
         if ((size_t)L > f->loc_cap) {
-            cudaFree(f->d_loc);
+            cudaFree(f->d_loc); f->d_loc = nullptr; f->loc_cap = 0;
             PBSO_CUDA(cudaMalloc(&f->d_loc, sizeof(FfatLoc) * (size_t)L));
             f->loc_cap = L;
         }
-        k_ffat_locate<<<div_up(L, 128), 128, 0, s>>>(L, f->d_geom, f->d_igeom, d_pos, (FfatLoc*)f->d_loc);
+        TileTable tt;
+        std::memcpy(tt.tiles_y, f->tiles_y, sizeof(tt.tiles_y)); std::memcpy(tt.tile_base, f->tile_base, sizeof(tt.tile_base));
+        const char* env = getenv("PBSO_FFAT_STAGED");
+        const bool staged = env && env[0] == '1';
+        const char* env_g = getenv("PBSO_FFAT_GATHER");
+        const int n_tiles = f->tile_base[6];
+        const size_t list_need = (size_t)n_tiles * L;
+        const bool tiles = L >= FT_MIN_L && 4ll * L >= f->D && list_need * sizeof(TileRec) <= ((size_t)512 << 20) && !staged && !(env_g && env_g[0] == '1');
+        int *cnt_cur = nullptr, *cnt_next = nullptr;
+        if (tiles && !f->d_psi_tiles) {
+            // tiled copy of Psi: [mode slab][tile][FT_H x FT_H texels incl. the high-side halo][FT_MS modes], zero-filled
+            // outside the face / past the last mode, so that one work item is one contiguous 16-byte-aligned block
+            const int n = f->n_dense, n_slabs = div_up(n, FT_MS);
+            std::vector<double> tl((size_t)n_slabs * n_tiles * FT_BLK, 0.0);
+            const HostMap& first = f->maps.at(0);
+            for (int m = 0; m < n; ++m) {
+                const std::vector<double>& c = f->maps.at(m).psi[0];
+                const int slab = m / FT_MS, mm = m % FT_MS;
+                for (int fc = 0; fc < 6; ++fc) {
+                    const int nx = first.igeom[2 * fc], ny = first.igeom[2 * fc + 1], st = first.igeom[12 + fc];
+                    const int txn = div_up(nx, FT_T);
+                    for (int tx = 0; tx < txn; ++tx)
+                        for (int ty = 0; ty < f->tiles_y[fc]; ++ty) {
+                            const size_t item = (size_t)slab * n_tiles + f->tile_base[fc] + tx * f->tiles_y[fc] + ty;
+                            for (int a = 0; a < FT_H && tx * FT_T + a < nx; ++a)
+                                for (int b = 0; b < FT_H && ty * FT_T + b < ny; ++b)
+                                    tl[item * FT_BLK + (size_t)(a * FT_H + b) * FT_MS + mm] = c[(size_t)st + (tx * FT_T + a) * ny + ty * FT_T + b];
+                            tl[item * FT_BLK + (size_t)FT_H * FT_H * FT_MS + mm] = 1.0 / f->maps.at(m).geom[31];
+                        }
+                }
+            }
+            PBSO_CUDA(cudaMalloc(&f->d_psi_tiles, tl.size() * sizeof(double)));
+            PBSO_CUDA(cudaMemcpy(f->d_psi_tiles, tl.data(), tl.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        if (tiles) {
+            if (list_need > f->tile_rec_cap) {
+                cudaFree(f->d_tile_rec); f->d_tile_rec = nullptr; f->tile_rec_cap = 0;
+                PBSO_CUDA(cudaMalloc(&f->d_tile_rec, sizeof(TileRec) * list_need));
+                f->tile_rec_cap = list_need;
+            }
+            if (!f->d_tile_cnt) {
+                PBSO_CUDA(cudaMalloc(&f->d_tile_cnt, sizeof(int) * 2 * (n_tiles + 1)));
+                PBSO_CUDA(cudaMemsetAsync(f->d_tile_cnt, 0, sizeof(int) * 2 * (n_tiles + 1), s));
+                f->cnt_parity = 0;
+            }
+            cnt_cur = f->d_tile_cnt + (size_t)f->cnt_parity * (n_tiles + 1);
+            cnt_next = f->d_tile_cnt + (size_t)(f->cnt_parity ^ 1) * (n_tiles + 1);
+            f->cnt_parity ^= 1;
+        }
+        Geo g0; load_geo(g0, f->maps.at(0).geom, f->maps.at(0).igeom);
+        k_ffat_locate<<<div_up(std::max(L, tiles ? n_tiles + 1 : 0), 64), 64, 0, s>>>(L, g0, d_pos, (FfatLoc*)f->d_loc, tt,
+                                                                                tiles ? (TileRec*)f->d_tile_rec : nullptr, cnt_cur, cnt_next);
         const size_t stage_bytes = (size_t)FS_G * f->D * sizeof(double);
         // Measured on B200 (profiles/r1_ffat.md): for 1024 maps x 10 242 listeners the staged kernel is bound by LSU
         // wavefronts (scattered 8-byte shared-memory gathers + 32-byte output segments) at ~100 us, the coalesced
         // texel-major gather by L2 bandwidth at ~54 us -- so the gather is the default and staging is opt-in.
-        const char* env = getenv("PBSO_FFAT_STAGED");
-        const bool staged = env && env[0] == '1';
-        if (staged && L >= 1024 && (f->D % 2 == 0) && stage_bytes <= 200 * 1024) {
+        if (tiles) {
+            static bool attr_set_t = false;
+            const size_t tile_bytes = 2 * ((size_t)FT_BLK * sizeof(double) + (size_t)FT_REC * sizeof(TileRec));
+            if (!attr_set_t) { PBSO_CUDA(cudaFuncSetAttribute(k_ffat_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); attr_set_t = true; }
+            const int n_items = n_tiles * div_up(n_modes, FT_MS);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(std::min(n_items, FT_CTAS_PER_SM * f->sm_count)); cfg.blockDim = dim3(FT_THREADS);
+            cfg.dynamicSmemBytes = tile_bytes; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;                      // may start while k_ffat_locate runs (griddepcontrol)
+            PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_ffat_tiles, n_modes, L, n_items, n_tiles,
+                                         (const double*)f->d_psi_tiles, (const TileRec*)f->d_tile_rec, (const int*)cnt_cur, cnt_cur + n_tiles, d_out));
+        } else if (staged && L >= 1024 && (f->D % 2 == 0) && stage_bytes <= 200 * 1024) {
             // whole maps in shared memory; listeners split so that the grid is ~7 waves of SMs
             static bool attr_set = false;
             if (!attr_set) { PBSO_CUDA(cudaFuncSetAttribute(k_ffat_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
@@ -420,7 +681,7 @@ int pbso_ffat_destroy(pbso_ffat* f) {
     if (f->stream) {
         DeviceGuard g(f->device);
         cudaStreamSynchronize(f->stream);
-        free_device(f); cudaFree(f->d_pos); cudaFree(f->d_out); cudaFree(f->d_loc);
+        free_device(f); cudaFree(f->d_pos); cudaFree(f->d_out); cudaFree(f->d_loc); cudaFree(f->d_tile_rec); cudaFree(f->d_tile_cnt);
         cudaStreamDestroy(f->stream);
     }
     delete f;

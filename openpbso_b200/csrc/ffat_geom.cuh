@@ -9,7 +9,7 @@ struct Geo {           // one map's geometry in registers / local
     double cell, low[6][3], c1[3], blo[3], bhi[3], c3[3], k;
     int ne[6][2], st[6];
 };
-__device__ __forceinline__ void load_geo(Geo& g, const double* __restrict__ geom, const int* __restrict__ igeom) {
+__host__ __device__ __forceinline__ void load_geo(Geo& g, const double* __restrict__ geom, const int* __restrict__ igeom) {
     g.cell = geom[0];
 #pragma unroll
     for (int f = 0; f < 6; ++f)
@@ -23,7 +23,8 @@ __device__ __forceinline__ void load_geo(Geo& g, const double* __restrict__ geom
 }
 
 // Intersect + Interpolate: returns the four Psi indices, the bilinear weights and the surface point.
-__device__ __forceinline__ void ffat_locate_surf(const Geo& g, const double p[3], int idx[4], double w[4], double surf[3]) {
+// fxy (optional): {face, x, y, xp - x, yp - y} of the stencil's low corner.
+__device__ __forceinline__ void ffat_locate_surf(const Geo& g, const double p[3], int idx[4], double w[4], double surf[3], int* fxy = nullptr) {
     double d[3], t_en = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -66,11 +67,12 @@ __device__ __forceinline__ void ffat_locate_surf(const Geo& g, const double p[3]
     idx[2] = base + x * Ny + yp;  idx[3] = base + xp * Ny + yp;
     w[0] = (1.0 - tx) * (1.0 - ty); w[1] = tx * (1.0 - ty);             // :799-802
     w[2] = (1.0 - tx) * ty;         w[3] = tx * ty;
+    if (fxy) { fxy[0] = face; fxy[1] = x; fxy[2] = y; fxy[3] = xp - x; fxy[4] = yp - y; }
 }
 // GetMapVal's use (ffat_solver.h:1180-1206): stencil at the listener's direction, r = |p - centre|.
-__device__ __forceinline__ void ffat_locate(const Geo& g, const double p[3], int idx[4], double w[4], double& r) {
+__device__ __forceinline__ void ffat_locate(const Geo& g, const double p[3], int idx[4], double w[4], double& r, int* fxy = nullptr) {
     double surf[3];
-    ffat_locate_surf(g, p, idx, w, surf);
+    ffat_locate_surf(g, p, idx, w, surf, fxy);
     const double dx = p[0] - g.c3[0], dy = p[1] - g.c3[1], dz = p[2] - g.c3[2];
     r = sqrt(dx * dx + dy * dy + dz * dz);                              // :1205 (p-_center).norm()
 }

@@ -9,14 +9,22 @@ import torch
 import openpbso_b200 as pbso
 from openpbso_b200 import synth
 
+_sweep = torch.ones(64 << 20, dtype=torch.float32, device="cuda")      # 256 MiB read sweep
+
 def ev_time(fn, iters=10, warm=3, flush=True):
     s = torch.cuda.current_stream()
     for _ in range(warm): fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        if flush: pbso.flush_l2(256 << 20); torch.cuda.synchronize()
+        if flush:
+            # evict with a 256 MiB write, then sweep a second buffer with reads so that what is left in L2 is CLEAN:
+            # dirty flush lines would otherwise be written back during the timed kernel and bill it for their traffic
+            pbso.flush_l2(256 << 20); _sweep.sum(); torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        # a ~50 us spin ahead of the first event lets the host enqueue fn()'s launches while the GPU is still busy, so the
+        # event pair brackets device execution (incl. gaps between dependent kernels), not host launch latency
+        torch.cuda._sleep(100000)
         e0.record(s); fn(); e1.record(s); e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     return float(np.median(ts)), float(np.min(ts))
@@ -73,7 +81,13 @@ for L in ([] if fit_only else [10242] if ffat_only else [64] if quick else [1, 6
     med, best = ev_time(fn, iters=10)
     D = 6144
     bytes_alg = Mf * (min(D, 4 * L) * 8 + L * 8)
-    k3.append({"L": L, "us": med * 1e3, "algorithmic_MB": bytes_alg / 1e6, "GBps": bytes_alg / (med * 1e-3) / 1e9, "frac_of_hbm": bytes_alg / (med * 1e-3) / 1e9 / hbm})
+    k3.append({"L": L, "us": med * 1e3, "us_best": best * 1e3, "algorithmic_MB": bytes_alg / 1e6, "GBps": bytes_alg / (med * 1e-3) / 1e9, "frac_of_hbm": bytes_alg / (med * 1e-3) / 1e9 / hbm,
+               "kernel": "k_ffat_locate + k_ffat_tiles" if L >= 2048 else "k_ffat_locate + k_ffat_gather"})
+    if L >= 2048:
+        os.environ["PBSO_FFAT_GATHER"] = "1"
+        med_g, _ = ev_time(fn, iters=10)
+        del os.environ["PBSO_FFAT_GATHER"]
+        k3[-1]["per_listener_gather_us"] = med_g * 1e3
 out["K3_ffat_eval"] = {"modes": Mf, "texels": 6144, "runs": k3}
 
 # ---- K6: FFAT map construction (FFAT_Map<T,3>::Solve for all modes of an object at once) -------------

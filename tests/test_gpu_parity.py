@@ -235,9 +235,30 @@ def test_ffat_many_listeners_staged(pbso, orc):
     finally:
         del os.environ["PBSO_FFAT_STAGED"]
     assert np.allclose(got, ref, rtol=1e-13)
-    assert np.allclose(pbso.FFATMaps.from_dicts(maps).computeTransfer(pos), ref, rtol=1e-13)   # default gather path
+    assert np.allclose(pbso.FFATMaps.from_dicts(maps).computeTransfer(pos), ref, rtol=1e-13)   # default path (texel tiles at this size)
     got1 = pbso.FFATMaps.from_dicts(maps).computeTransfer(pos[:100])            # small-L path, same numbers
     assert np.allclose(got1, got[:100], rtol=1e-14)
+
+
+@pytest.mark.parametrize("n_modes,n_tex,L", [(37, 16, 2500), (200, 12, 3000), (256, 32, 4500), (130, 9, 2100)])
+def test_ffat_many_listeners_texel_tiles(pbso, orc, n_modes, n_tex, L):
+    """L >= 2048 and 4 L >= texels: the texel-stationary kernel (tile rows staged with bulk async copies).  Odd mode
+    counts take the non-bulk / scalar-store tails, 12- and 9-texel faces leave partial tiles, 200/256 modes span two
+    mode slabs, and 4500 listeners need two scan passes.  Same numbers as the per-listener gather."""
+    freqs = synth.mode_frequencies(n_modes, 78)
+    maps = synth.ffat_maps(freqs, 2000, n=n_tex)
+    pos = synth.listeners(L, 14)
+    pos[:64] = 3.0 * synth.texel_centres(maps[0])[:64]          # exact texel centres / face corners: clamped stencils
+    ref = orc.ffat_eval(maps, pos)
+    got = pbso.FFATMaps.from_dicts(maps).computeTransfer(pos)
+    assert got.shape == (L, n_modes)
+    assert np.allclose(got, ref, rtol=1e-13)
+    os.environ["PBSO_FFAT_GATHER"] = "1"
+    try:
+        gat = pbso.FFATMaps.from_dicts(maps).computeTransfer(pos)
+    finally:
+        del os.environ["PBSO_FFAT_GATHER"]
+    assert np.allclose(gat, ref, rtol=1e-13) and np.allclose(gat, got, rtol=1e-14)
 
 
 def test_ffat_full_size_properties(pbso):
