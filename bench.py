@@ -86,6 +86,37 @@ def cpu_render_sample(n_threads, obj_per_thread, n_modes, n_buf, seed):
     return float(n) * n_modes * n_buf * BUF, dt
 
 
+def cpu_render_sample_ref(n_threads, n_modes, n_buf, seed):
+    """The same loop run by the reference's OWN headers (oracle/_ref: ModalSolver<double,256>::step compiled in place
+    against the Eigen shim), one object per host thread.  Returns (mode_samples, seconds) or None when _ref is absent.
+    Reported beside the port: the shim's eager temporaries make it ~4-5x slower than the port, so the port (the
+    faster, i.e. conservative, CPU number) stays the headline baseline."""
+    from oracle import oracle as orc
+    from openpbso_b200 import synth
+    if orc.ref() is None:
+        return None
+    w = synth.batch_workload(n_threads, n_modes, n_buf, seed)
+
+    def work(t):
+        orc.ref_batch_render(synth.H, w["a"][t:t + 1], w["b"][t:t + 1], w["space"][t:t + 1], w["trans"][t:t + 1],
+                             w["imp_buf"][t:t + 1], n_buf)
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    t0 = time.perf_counter()
+    for th in threads: th.start()
+    for th in threads: th.join()
+    return float(n_threads) * n_modes * n_buf * BUF, time.perf_counter() - t0
+
+
+def reference_headers_entry(cores, n_modes):
+    n_buf = 173                                   # 1 s of audio per object (cfg1's length), impulse in buffer 0..171
+    r = cpu_render_sample_ref(cores, n_modes, n_buf, 1007)
+    if r is None:
+        return None
+    return {"value": r[0] / r[1], "unit": "mode-samples/s", "cores": cores, "kind": "reference",
+            "sample": "%d objects x %d modes x %d samples (1 object per host thread), the reference's own ModalSolver::step "
+                      "compiled in place against the Eigen shim (oracle/_ref), %.1f s" % (cores, n_modes, n_buf * BUF, r[1])}
+
+
 def cpu_info():
     model = "unknown"
     try:
@@ -121,6 +152,9 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "mode-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    rh = reference_headers_entry(cores, args.modes)
+    if rh:
+        line["cpu_baseline"]["reference_headers"] = rh
     print(json.dumps(line), flush=True)
 
 
@@ -468,6 +502,9 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": ms / dt, "unit": "mode-samples/s", "cores": cores, "kind": "port",
                                 "sample": "%d objects x %d modes x %d samples (1 object per host thread, %s), %.1f s" % (
                                     cores, args.modes, n_samples, model, dt)}
+        rh = reference_headers_entry(cores, args.modes)
+        if rh:
+            line["cpu_baseline"]["reference_headers"] = rh
     if not args.no_realtime:
         line["realtime"] = realtime_latency(pbso, synth)
         line["moving_listeners"] = moving_listeners_latency(pbso, synth)
