@@ -165,6 +165,25 @@ def test_render_buffer_many_listeners(pbso, orc):
         assert np.max(np.abs(y - yr)) <= 1e-9 * np.max(np.abs(yr))
 
 
+@pytest.mark.parametrize("N,n_tr,L,T", [(300, 257, 13, 513), (1024, 1024, 5, 256), (70, 70, 33, 64), (513, 1, 9, 31)])
+def test_render_buffer_many_listeners_ragged(pbso, orc, N, n_tr, L, T):
+    """More than 4 listeners take the shared-recurrence path (k_iir_history + k_modal_sum): odd transfer lengths, listener
+    counts and buffer sizes off the tile sizes, state carried across buffers, qnorm."""
+    f = synth.mode_frequencies(N, 1004); a, b = synth.ab_from_material(f, synth.MATERIALS["high_damping"])
+    rng = np.random.default_rng(11)
+    tr = np.abs(rng.standard_normal((L, n_tr))) + 0.1
+    it = pbso.ModalIntegrator(N, H, a, b); ref = orc.Integrator(H, a, b)
+    it.set_transfer(tr, L)
+    for rep in range(3):
+        sp = rng.standard_normal(N); tm = rng.standard_normal(T) if rep == 1 else np.eye(1, T, 0)[0] * (rep == 0)
+        y, qn = it.render_buffer(sp, tm)
+        q = np.array([ref.step(sp * tm[i]) for i in range(T)])
+        yr = (q[:, :n_tr] @ tr.T).T
+        assert y.shape == (L, T)
+        assert np.max(np.abs(y - yr)) <= 1e-9 * max(np.max(np.abs(yr)), 1e-300)
+        assert np.allclose(qn, np.sqrt((q * q).sum(axis=0)), rtol=1e-12, atol=0)
+
+
 def test_moving_listeners_transfer_stays_on_device(pbso, orc):
     """cfg4: per buffer, computeTransfer for every listener (K3) lands in the integrator's transfer table without a host
     round trip, then one IIR pass renders all listeners.  Against the oracle's ffat_eval + integrator."""
