@@ -576,7 +576,8 @@ def test_ffat_fit_many_modes_and_device_entry(pbso, orc):
     dp = torch.from_numpy(np.ascontiguousarray(w["pressure"]).view(np.float64)).cuda()
     dpsi = torch.empty(300, ft.n_directions, dtype=torch.float64, device="cuda")
     dscale = torch.empty(300, dtype=torch.float64, device="cuda")
-    st = torch.cuda.current_stream()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()              # an explicit stream: a NULL handle would select the fitter's own stream
     ft.solve_device(300, dk.data_ptr(), dp.data_ptr(), dpsi.data_ptr(), True, dscale.data_ptr(), st.cuda_stream)
     st.synchronize()
     assert np.array_equal(dpsi.cpu().numpy(), psi) and np.array_equal(dscale.cpu().numpy(), scale)
