@@ -34,6 +34,9 @@ struct pbso_integrator {
     double* d_trans = nullptr;    // transfer[L][n_transfer]
     double* d_pos = nullptr;      // listener positions for set_transfer_ffat
     int pos_cap = 0;
+    double* d_acc = nullptr;      // [L][T] cross-slab accumulators of K1 (all zero between launches)
+    unsigned* d_cnt = nullptr;    // per listener group: slabs that have finished (zero between launches)
+    size_t acc_cap = 0; int cnt_cap = 0;
     int n_transfer = 0, L = 0, Tcap = 0, Lcap = 0;
     double* h_in = nullptr;       // pinned mirrors of d_in / d_out
     double* h_out = nullptr;
@@ -117,10 +120,12 @@ __global__ void __launch_bounds__(K1_TPB)
 k_render_f64(int N, int T, int n_transfer, int L,
              const double* __restrict__ c, const double* __restrict__ q, double* __restrict__ q_next,
              const double* __restrict__ space, const double* __restrict__ time,
-             const double* __restrict__ trans, double* __restrict__ y, double* __restrict__ qnorm) {
+             const double* __restrict__ trans, double* __restrict__ y, double* __restrict__ qnorm,
+             double* __restrict__ acc, unsigned* __restrict__ cnt) {
     extern __shared__ double smem[];
     double* s_time = smem;                                  // [T]
     double* s_part = smem + T;                              // [LPB][K1_TPB/32][32] per tile
+    __shared__ bool s_last;
     const int m = blockIdx.x * K1_TPB + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l0 = blockIdx.y * LPB;
@@ -170,7 +175,7 @@ k_render_f64(int N, int T, int n_transfer, int L,
 #pragma unroll
                     for (int w = 0; w < K1_TPB / 32; ++w) s += s_part[(l * (K1_TPB / 32) + w) * 32 + j];
                     if (gridDim.x == 1) y[(size_t)(l0 + l) * T + t0 + j] = s;
-                    else atomicAdd(&y[(size_t)(l0 + l) * T + t0 + j], s);
+                    else atomicAdd(&acc[(size_t)(l0 + l) * T + t0 + j], s);
                 }
             }
             __syncthreads();
@@ -179,6 +184,25 @@ k_render_f64(int N, int T, int n_transfer, int L,
     if (live && blockIdx.y == 0) {
         q_next[m] = q1; q_next[N + m] = q2;
         if (qnorm) qnorm[m] = sqrt(qsum);                    // modal_solver.h:272
+    }
+    // Several mode slabs: the last slab to finish a listener group moves the sums to y (which may be host memory
+    // mapped into the device: no copy-engine launch on the way back) and leaves the accumulators zero for the next call.
+    if (gridDim.x > 1 && L > 0) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&cnt[blockIdx.y], 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int o = threadIdx.x; o < LPB * T; o += K1_TPB) {
+                const int l = l0 + o / T, i = o - (o / T) * T;
+                if (l < L) {
+                    y[(size_t)l * T + i] = __ldcg(&acc[(size_t)l * T + i]);
+                    acc[(size_t)l * T + i] = 0.0;
+                }
+            }
+            if (threadIdx.x == 0) cnt[blockIdx.y] = 0u;
+        }
     }
 }
 
@@ -206,16 +230,27 @@ static int launch_render(pbso_integrator* it, const double* d_space, const doubl
                          double* d_y, double* d_qnorm) {
     const int N = it->N, L = it->L;
     const int gx = div_up(N, K1_TPB);
-    if (L > 0 && gx > 1) PBSO_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * (size_t)L * T, it->stream));
+    if (L > 0 && gx > 1) {
+        const size_t need = (size_t)L * T; const int groups = L <= 1 ? 1 : div_up(L, 4);
+        if (need > it->acc_cap || groups > it->cnt_cap) {
+            PBSO_CUDA(cudaStreamSynchronize(it->stream));
+            cudaFree(it->d_acc); cudaFree(it->d_cnt); it->d_acc = nullptr; it->d_cnt = nullptr; it->acc_cap = 0; it->cnt_cap = 0;
+            PBSO_CUDA(cudaMalloc(&it->d_acc, need * sizeof(double)));
+            PBSO_CUDA(cudaMalloc(&it->d_cnt, groups * sizeof(unsigned)));
+            PBSO_CUDA(cudaMemsetAsync(it->d_acc, 0, need * sizeof(double), it->stream));   // once: every launch leaves them zero
+            PBSO_CUDA(cudaMemsetAsync(it->d_cnt, 0, groups * sizeof(unsigned), it->stream));
+            it->acc_cap = need; it->cnt_cap = groups;
+        }
+    }
     if (L <= 1) {
         size_t sm = sizeof(double) * ((size_t)T + 1 * (K1_TPB / 32) * 32);
         k_render_f64<1><<<dim3(gx, 1), K1_TPB, sm, it->stream>>>(
-            N, T, it->n_transfer, L, it->d_c, it->d_q, it->d_q_alt, d_space, d_time, it->d_trans, d_y, d_qnorm);
+            N, T, it->n_transfer, L, it->d_c, it->d_q, it->d_q_alt, d_space, d_time, it->d_trans, d_y, d_qnorm, it->d_acc, it->d_cnt);
     } else {
         constexpr int LPB = 4;
         size_t sm = sizeof(double) * ((size_t)T + LPB * (K1_TPB / 32) * 32);
         k_render_f64<LPB><<<dim3(gx, div_up(L, LPB)), K1_TPB, sm, it->stream>>>(
-            N, T, it->n_transfer, L, it->d_c, it->d_q, it->d_q_alt, d_space, d_time, it->d_trans, d_y, d_qnorm);
+            N, T, it->n_transfer, L, it->d_c, it->d_q, it->d_q_alt, d_space, d_time, it->d_trans, d_y, d_qnorm, it->d_acc, it->d_cnt);
     }
     PBSO_CUDA(cudaGetLastError());
     std::swap(it->d_q, it->d_q_alt);
@@ -276,7 +311,7 @@ int pbso_integrator_destroy(pbso_integrator* it) {
     DeviceGuard g(it->device);
     if (it->stream) cudaStreamSynchronize(it->stream);
     cudaFree(it->d_c); cudaFree(it->d_q); cudaFree(it->d_q_alt); cudaFree(it->d_in); cudaFree(it->d_out);
-    cudaFree(it->d_trans); cudaFree(it->d_pos);
+    cudaFree(it->d_trans); cudaFree(it->d_pos); cudaFree(it->d_acc); cudaFree(it->d_cnt);
     if (it->h_in) cudaFreeHost(it->h_in);
     if (it->h_out) cudaFreeHost(it->h_out);
     if (it->stream) cudaStreamDestroy(it->stream);
@@ -345,7 +380,7 @@ int pbso_integrator_set_transfer(pbso_integrator* it, const double* transfer, in
     PBSO_CUDA(cudaStreamSynchronize(it->stream));
     const size_t need = (size_t)L * n_transfer;
     if (need > (size_t)it->Lcap) {
-        cudaFree(it->d_trans); cudaFree(it->d_pos);
+        cudaFree(it->d_trans); cudaFree(it->d_pos); cudaFree(it->d_acc); cudaFree(it->d_cnt);
         PBSO_CUDA(cudaMalloc(&it->d_trans, sizeof(double) * need));
         it->Lcap = (int)need;
     }
@@ -397,12 +432,23 @@ int pbso_render_buffer(pbso_integrator* it, const double* space, const double* t
     if (int rc = ensure_staging(it, T, L)) return rc;
     std::memcpy(it->h_in, space, sizeof(double) * N);
     std::memcpy(it->h_in + N, time, sizeof(double) * T);
-    PBSO_CUDA(cudaMemcpyAsync(it->d_in, it->h_in, sizeof(double) * (N + T), cudaMemcpyHostToDevice, it->stream));
-    double* d_y = it->d_out;
-    double* d_qn = it->d_out + (size_t)(L > 0 ? L : 1) * T;
-    if (int rc = launch_render(it, it->d_in, it->d_in + N, T, d_y, qnorm_out ? d_qn : nullptr)) return rc;
+    // Zero-copy: the pinned staging buffers are mapped into the device (unified addressing), so K1 reads its 10 KB of
+    // input and writes y / qnorm straight across PCIe -- one launch and one synchronisation per buffer, no copy-engine
+    // operations (they cost more in launch latency than the bytes do in transfer time).  Larger outputs (many listeners)
+    // still go through the copy engine.
     const size_t out_n = (size_t)(L > 0 ? L : 1) * T + (qnorm_out ? N : 0);
-    PBSO_CUDA(cudaMemcpyAsync(it->h_out, it->d_out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, it->stream));
+    const bool zero_copy = out_n * sizeof(double) <= (64u << 10);
+    if (zero_copy) {
+        double* m_y = it->h_out;
+        double* m_qn = it->h_out + (size_t)(L > 0 ? L : 1) * T;
+        if (int rc = launch_render(it, it->h_in, it->h_in + N, T, m_y, qnorm_out ? m_qn : nullptr)) return rc;
+    } else {
+        PBSO_CUDA(cudaMemcpyAsync(it->d_in, it->h_in, sizeof(double) * (N + T), cudaMemcpyHostToDevice, it->stream));
+        double* d_y = it->d_out;
+        double* d_qn = it->d_out + (size_t)(L > 0 ? L : 1) * T;
+        if (int rc = launch_render(it, it->d_in, it->d_in + N, T, d_y, qnorm_out ? d_qn : nullptr)) return rc;
+        PBSO_CUDA(cudaMemcpyAsync(it->h_out, it->d_out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, it->stream));
+    }
     PBSO_CUDA(cudaStreamSynchronize(it->stream));
     if (L > 0) std::memcpy(y_out, it->h_out, sizeof(double) * (size_t)L * T);
     if (qnorm_out) std::memcpy(qnorm_out, it->h_out + (size_t)(L > 0 ? L : 1) * T, sizeof(double) * N);
