@@ -68,6 +68,21 @@ out["K4_gemv_f64"] = {"kernel_ms": float(np.median(kms)), "algorithmic_GB": alg 
                       "frac_of_hbm": alg / (np.median(kms) * 1e-3) / 1e9 / hbm, "hbm_peak_gbs": hbm,
                       "host_call_ms_incl_copies_and_flush": dt * 1e3}
 
+# ---- K4 sparse: the contact storm as vertex impulses (cfg3: 100k impulses/s = 580 per 256-sample buffer) ----------------
+if not ffat_only:
+    Vn = K // 3
+    k4s = []
+    for B in ([580] if quick else [1, 580, 4096]):
+        vids = rng.integers(0, Vn, B).astype(np.int32); vns = synth.unit_vectors(B, 1003)
+        md.project_vertices(M, vids, vns)
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter(); md.project_vertices(M, vids, vns); ts.append(time.perf_counter() - t0)
+        dt = float(np.median(ts))
+        k4s.append({"B": B, "host_call_us": dt * 1e6, "impulses_per_s": B / dt, "d2h_MB": B * M * 8 / 1e6,
+                    "note": "host pointers in and out: B x 2048 modal loads (doubles) returned per call"})
+    out["K4_project_sparse"] = {"M": M, "V": Vn, "runs": k4s}
+
 # ---- K3: cfg4 (1024 modes x 64 listeners) and the HUD sphere (10242 listeners) ---------------
 Mf = 1024
 freqs = synth.mode_frequencies(Mf, 1004)
