@@ -57,6 +57,7 @@ struct pbso_ffat {
     double* d_pos = nullptr; double* d_out = nullptr; size_t pos_cap = 0, out_cap = 0;
     void* d_loc = nullptr; size_t loc_cap = 0;          // per-listener stencils (shared-geometry path)
     void* d_tile_rec = nullptr; size_t tile_rec_cap = 0;    // [n_tiles][L] stencil records binned by texel tile (texel-tile path)
+    int* d_tile_order = nullptr;                            // tiles by decreasing solid angle (listeners per tile, for directions uniform on the sphere)
     double* d_psi_tiles = nullptr;                          // [slab][tile][FT_H*FT_H + 1][FT_MS]: each work item's texels contiguous (built on first use)
     int* d_tile_cnt = nullptr; int cnt_parity = 0;          // [2][n_tiles] ping-pong counters: a call fills one, zeroes the other
     int tiles_y[6] = {0}, tile_base[7] = {0};           // texel tiles of FT_T x FT_T per face (shared geometry)
@@ -179,7 +180,8 @@ struct FtItem { int tile, m0, cnt, pad; };
 __global__ void __launch_bounds__(FT_THREADS, FT_CTAS_PER_SM)
 k_ffat_tiles(int n_modes, int L, int n_items, int n_tiles,
              const double* __restrict__ psi_tiles, const TileRec* __restrict__ tile_rec,
-             const int* __restrict__ tile_cnt, int* __restrict__ work_counter, double* __restrict__ out) {
+             const int* __restrict__ tile_cnt, const int* __restrict__ tile_order, int n_slabs, int* __restrict__ work_counter,
+             double* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char ft_smem[];
     constexpr size_t PSI_BYTES = (size_t)FT_BLK * sizeof(double);
     double* s_psi0 = reinterpret_cast<double*>(ft_smem);                                  // [2][FT_H * FT_H + 1][FT_MS]: texels, then 1/k
@@ -223,7 +225,8 @@ k_ffat_tiles(int n_modes, int L, int n_items, int n_tiles,
                 }
                 break;
             }
-            const int tile = item % n_tiles, m0 = (item / n_tiles) * FT_MS;
+            // heaviest tiles first (longest-processing-time order keeps the tail short): item -> (tile rank, mode slab)
+            const int slab = item % n_slabs, tile = tile_order[item / n_slabs], m0 = slab * FT_MS;
             // the item's texels (tile + halo, FT_MS modes) are one contiguous block of the tiled table: a single bulk
             // copy.  They do not depend on the listeners: on the first item the copy is requested before
             // k_ffat_locate (the grid this one is launched behind) has finished
@@ -231,7 +234,7 @@ k_ffat_tiles(int n_modes, int L, int n_items, int n_tiles,
                 asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full_psi(pb)), "r"((unsigned)PSI_BYTES) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"((unsigned)__cvta_generic_to_shared(s_psi0 + (size_t)pb * FT_BLK)),
-                               "l"(psi_tiles + (size_t)item * FT_BLK), "r"((unsigned)PSI_BYTES), "r"(full_psi(pb)) : "memory");
+                               "l"(psi_tiles + ((size_t)slab * n_tiles + tile) * FT_BLK), "r"((unsigned)PSI_BYTES), "r"(full_psi(pb)) : "memory");
             }
             if (!dep_waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); dep_waited = true; }
             int cnt = cnt_next;
@@ -254,7 +257,7 @@ k_ffat_tiles(int n_modes, int L, int n_items, int n_tiles,
             item = __shfl_sync(0xffffffffu, next_item, 0);                 // claimed one iteration ago
             cnt_next = 0;
             if (lane == 0) {
-                if (item < n_items) cnt_next = tile_cnt[item % n_tiles];   // used next iteration
+                if (item < n_items) cnt_next = tile_cnt[tile_order[item / n_slabs]];   // used next iteration
                 next_item = atomicAdd(work_counter, 1) + gridDim.x;
             }
             cnt_next = __shfl_sync(0xffffffffu, cnt_next, 0);
@@ -448,8 +451,8 @@ static int load_one(const char* filename, HostMap& hm) {
 }
 
 static void free_device(pbso_ffat* f) {
-    cudaFree(f->d_geom); cudaFree(f->d_igeom); cudaFree(f->d_psi_mm); cudaFree(f->d_psi_tm); cudaFree(f->d_psi_off); cudaFree(f->d_psi_tiles);
-    f->d_psi_tiles = nullptr; f->d_geom = nullptr; f->d_igeom = nullptr; f->d_psi_mm = nullptr; f->d_psi_tm = nullptr; f->d_psi_off = nullptr;
+    cudaFree(f->d_geom); cudaFree(f->d_igeom); cudaFree(f->d_psi_mm); cudaFree(f->d_psi_tm); cudaFree(f->d_psi_off); cudaFree(f->d_psi_tiles); cudaFree(f->d_tile_order);
+    f->d_psi_tiles = nullptr; f->d_tile_order = nullptr; f->d_geom = nullptr; f->d_igeom = nullptr; f->d_psi_mm = nullptr; f->d_psi_tm = nullptr; f->d_psi_off = nullptr;
 }
 
 static int ensure_device(pbso_ffat* f) {
@@ -552,6 +555,29 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
                         }
                 }
             }
+            // work order: a tile's expected listener count for directions uniform on the sphere is its solid angle seen from
+            // the centre, sum over texels of (p . n) / |p|^3 with p = texel centre - centre
+            std::vector<std::pair<double, int>> wt(n_tiles);
+            for (int fc = 0; fc < 6; ++fc) {
+                const int nx = first.igeom[2 * fc], ny = first.igeom[2 * fc + 1];
+                const int dk = fc / 2, di = (dk + 1) % 3, dj = (dk + 2) % 3;
+                const double h = first.geom[0];
+                for (int x = 0; x < nx; ++x)
+                    for (int y = 0; y < ny; ++y) {
+                        double p[3];
+                        p[dk] = first.geom[1 + 3 * fc + dk] - first.geom[28 + dk];
+                        p[di] = first.geom[1 + 3 * fc + di] + (x + 0.5) * h - first.geom[28 + di];
+                        p[dj] = first.geom[1 + 3 * fc + dj] + (y + 0.5) * h - first.geom[28 + dj];
+                        const double r2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+                        const int t = f->tile_base[fc] + (x / FT_T) * f->tiles_y[fc] + y / FT_T;
+                        wt[t].first += std::fabs(p[dk]) / (r2 * std::sqrt(r2)); wt[t].second = t;
+                    }
+            }
+            std::sort(wt.begin(), wt.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+            std::vector<int> order(n_tiles);
+            for (int i = 0; i < n_tiles; ++i) order[i] = wt[i].second;
+            PBSO_CUDA(cudaMalloc(&f->d_tile_order, order.size() * sizeof(int)));
+            PBSO_CUDA(cudaMemcpy(f->d_tile_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
             PBSO_CUDA(cudaMalloc(&f->d_psi_tiles, tl.size() * sizeof(double)));
             PBSO_CUDA(cudaMemcpy(f->d_psi_tiles, tl.data(), tl.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
@@ -589,7 +615,8 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = 1;                      // may start while k_ffat_locate runs (griddepcontrol)
             PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_ffat_tiles, n_modes, L, n_items, n_tiles,
-                                         (const double*)f->d_psi_tiles, (const TileRec*)f->d_tile_rec, (const int*)cnt_cur, cnt_cur + n_tiles, d_out));
+                                         (const double*)f->d_psi_tiles, (const TileRec*)f->d_tile_rec, (const int*)cnt_cur, (const int*)f->d_tile_order,
+                                         div_up(n_modes, FT_MS), cnt_cur + n_tiles, d_out));
         } else if (staged && L >= 1024 && (f->D % 2 == 0) && stage_bytes <= 200 * 1024) {
             // whole maps in shared memory; listeners split so that the grid is ~7 waves of SMs
             static bool attr_set = false;
