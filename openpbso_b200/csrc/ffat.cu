@@ -157,7 +157,7 @@ constexpr int FT_H = FT_T + 1;          // tile edge incl. halo
 #define PBSO_FT_MS 128
 #endif
 constexpr int FT_MS = PBSO_FT_MS;       // modes per CTA (64 or 128): lanes own FT_MS / 32 modes
-constexpr int FT_CW = 16;               // consumer warps
+constexpr int FT_CW = 16;               // consumer warps (24 measured the same: not bound by consumer latency)
 constexpr int FT_CTAS_PER_SM = 1;       // 2 x (81 KB tile + 12 KB records) of shared memory per CTA
 constexpr int FT_THREADS = (FT_CW + 1) * 32;   // + one producer warp
 constexpr int FT_MIN_L = 2048;
