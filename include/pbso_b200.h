@@ -127,6 +127,9 @@ int pbso_ffat_save_file(const pbso_ffat* f, int mode_id, const char* filename);
  * pos is L x 3.  A missing mode id in [0, n_modes) returns PBSO_ERR_RANGE (.at() throws). */
 int pbso_ffat_eval(const pbso_ffat* f, int n_modes, const double* pos, int L, int use_compressed,
                    double* out);
+/* Device-resident variant, enqueue only (cuda_stream NULL = the handle's own stream).  A handle keeps per-call scratch
+ * (listener stencils, per-tile bins and their ping-pong counters), so calls on one handle must come from one thread and
+ * must not overlap on different streams; successive calls on one stream are ordered by the stream. */
 int pbso_ffat_eval_device(const pbso_ffat* f, int n_modes, const double* d_pos, int L,
                           double* d_out, void* cuda_stream);
 
