@@ -155,7 +155,7 @@ def run_reference(args):
     rh = reference_headers_entry(cores, args.modes)
     if rh:
         line["cpu_baseline"]["reference_headers"] = rh
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -528,12 +528,29 @@ def run_ours(args):
     if not args.no_realtime:
         line["realtime"] = realtime_latency(pbso, synth)
         line["moving_listeners"] = moving_listeners_latency(pbso, synth)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 if __name__ == "__main__":
+    # Libraries write banners to stdout (NCCL prints "NCCL version ..." when the first communicator is created): keep the
+    # original stdout for the JSON line only and send everything else to stderr.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
