@@ -90,6 +90,7 @@ k_ffat_eval_general(int n_modes, int L, const double* __restrict__ geom, const i
 //  k_ffat_gather: block = 256 modes x FG_LPB listeners; the stencil sits in shared memory, every thread gathers its
 //                 mode's four texels from the texel-major table -- a warp reads 32 consecutive doubles per texel
 //                 row, fully coalesced -- and writes out[l][m] coalesced.  k differs per mode (geom[m][31]).
+constexpr int FL_THREADS = 64;          // listeners per CTA of k_ffat_locate (latency-bound; 32 measured the same)
 struct __align__(16) FfatLoc { int idx[4]; double w[4]; double r; int tile; int lxy; };   // 64 B: int4 + 3 x double2 loads
 // lxy: position of the stencil's low corner inside its texel tile and the clamp flags: lx | ly << 4 | (xp - x) << 8 | (yp - y) << 9
 constexpr int FT_T = 8;                 // texel tile edge
@@ -97,7 +98,7 @@ struct TileTable { int tiles_y[6]; int tile_base[7]; };
 // What k_ffat_tiles needs of one listener, stored in its tile's bin: bilinear weights, 1/r, listener id, lxy.
 struct __align__(16) TileRec { double w[4]; double inv_r; int l; int lxy; };   // 48 B
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(FL_THREADS)
 k_ffat_locate(int L, const __grid_constant__ Geo g,        // the shared geometry rides in the parameter bank: no global round trip
               const double* __restrict__ pos, FfatLoc* __restrict__ loc, TileTable tt, TileRec* __restrict__ tile_rec,
               int* __restrict__ cnt_cur, int* __restrict__ cnt_next) {
@@ -597,7 +598,7 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
             f->cnt_parity ^= 1;
         }
         Geo g0; load_geo(g0, f->maps.at(0).geom, f->maps.at(0).igeom);
-        k_ffat_locate<<<div_up(std::max(L, tiles ? n_tiles + 1 : 0), 64), 64, 0, s>>>(L, g0, d_pos, (FfatLoc*)f->d_loc, tt,
+        k_ffat_locate<<<div_up(std::max(L, tiles ? n_tiles + 1 : 0), FL_THREADS), FL_THREADS, 0, s>>>(L, g0, d_pos, (FfatLoc*)f->d_loc, tt,
                                                                                 tiles ? (TileRec*)f->d_tile_rec : nullptr, cnt_cur, cnt_next);
         const size_t stage_bytes = (size_t)FS_G * f->D * sizeof(double);
         // Measured on B200 (profiles/r1_ffat.md): for 1024 maps x 10 242 listeners the staged kernel is bound by LSU
