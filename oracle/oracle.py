@@ -146,6 +146,7 @@ def ref():
         R.ref_ffat_load_save.argtypes = [C.c_char_p, C.c_char_p, c_ip, c_dp]
         R.ref_list_dir_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         R.ref_batch_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp]
+        R.ref_cubemap_mesh.argtypes = [c_ip, c_ip, C.c_double, c_dp, c_ip, c_dp, C.c_int, c_ip, c_ip]
         R.ref_ffat_fit.argtypes = [C.c_int, C.c_double, c_dp, C.c_int, c_ip, C.c_int, C.c_double, c_dp, C.c_int,
                                    c_dp, c_dp, C.c_char_p]
         _REF = R
@@ -426,6 +427,19 @@ def ref_ffat_fit(mode_id, cell_size, V, n_elements, k, pressure, power_scaling=F
                        P.view(np.float64).ctypes.data_as(c_dp), int(bool(power_scaling)), _dp(psi), _dp(centre),
                        None if save_to is None else os.fsencode(save_to))
     return psi, centre
+
+
+def ref_cubemap_mesh(bbox_low_r, bbox_top_r, cell_size, grid_low, dim):
+    """The reference's own FFAT_Map<double,1>::CubemapMesh (ffat_solver.h:334-397), compiled in place.
+    Returns (V [4*n_quads][3], n_elements [6][2], data_indices [2*n_quads])."""
+    lo = np.ascontiguousarray(bbox_low_r, dtype=np.int32); hi = np.ascontiguousarray(bbox_top_r, dtype=np.int32)
+    dm = np.ascontiguousarray(dim, dtype=np.int32); gl = _f64(grid_low)
+    n = hi - lo + 1
+    quads = 2 * int(n[0] * n[1] + n[1] * n[2] + n[2] * n[0])
+    V = np.empty((4 * quads, 3)); ne = np.empty((6, 2), dtype=np.int32); idx = np.empty(2 * quads, dtype=np.int32)
+    rows = ref().ref_cubemap_mesh(_ip(lo), _ip(hi), float(cell_size), _dp(gl), _ip(dm), _dp(V), len(V), _ip(ne), _ip(idx))
+    assert rows == len(V), rows
+    return V, ne, idx
 
 
 def num_modes_audible(omega2, density, freq, cache=None):

