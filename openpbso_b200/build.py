@@ -50,18 +50,24 @@ def build(force=False, verbose=False):
     return OUT
 
 
-def build_tools():
-    """tools/pbso_render.cpp (headless driver) -> openpbso_b200/bin/pbso_render, against the header mirror."""
+def _build_tool(name):
     root = os.path.dirname(HERE)
     inc = os.path.join(root, "include", "openpbso")
-    src = os.path.join(root, "tools", "pbso_render.cpp")
-    out = os.path.join(HERE, "bin", "pbso_render")
+    src = os.path.join(root, "tools", name + ".cpp")
+    out = os.path.join(HERE, "bin", name)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(OUT)):
         return out
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(inc, "eigen_shim"), "-I" + inc, src,
                            "-L" + HERE, "-lpbso_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/..", "-o", out])
     return out
+
+
+def build_tools():
+    """tools/pbso_render.cpp (headless driver) and tools/pbso_fit_ffat.cpp (headless FFAT map
+    construction, rank 3) -> openpbso_b200/bin/, against the header mirror.  Returns the path of pbso_render."""
+    _build_tool("pbso_fit_ffat")
+    return _build_tool("pbso_render")
 
 
 if __name__ == "__main__":

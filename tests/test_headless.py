@@ -26,6 +26,85 @@ def render_exe(pbso, tmp_path_factory):
 
 
 @pytest.fixture(scope="module")
+def fit_exe(pbso, tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("tools") / "pbso_fit_ffat")
+    r = subprocess.run(GXX + [os.path.join(ROOT, "tools", "pbso_fit_ffat.cpp"), "-L" + LIBDIR, "-lpbso_b200",
+                              "-Wl,-rpath," + LIBDIR, "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+def _write_fit_inputs(tmp_path, w, binary):
+    nfile = str(tmp_path / "n_elements.txt")
+    with open(nfile, "w") as f:
+        for shell in w["n_elements"]:
+            f.write(" ".join("%d %d" % (a, b) for a, b in shell) + "\n")
+    vfile = str(tmp_path / "V.f64"); np.ascontiguousarray(w["V"]).tofile(vfile)
+    kfile = str(tmp_path / "k.txt")
+    with open(kfile, "w") as f:
+        for k in w["k"]:
+            f.write("%.17g\n" % k)
+    for m, P in enumerate(w["pressure"]):
+        if binary:
+            with open(str(tmp_path / ("p-%d.bin" % (m + 3))), "wb") as f:
+                f.write(np.int32(2 * len(P)).tobytes()); f.write(np.ascontiguousarray(P).view(np.float64).tobytes())
+        else:
+            with open(str(tmp_path / ("p-%d.txt" % (m + 3))), "w") as f:
+                for z in P:
+                    f.write("%.17g %.17g\n" % (z.real, z.imag))
+    return nfile, vfile, kfile
+
+
+def test_fit_tool_arguments(fit_exe, tmp_path):
+    r = subprocess.run([fit_exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    r = subprocess.run([fit_exe, "-n", str(tmp_path / "none.txt"), "-v", "x", "-c", "0.1", "-k", "k", "-p", "p%d", "-o", str(tmp_path / "o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 3 and "cannot open" in r.stderr
+
+
+def test_fit_tool_refuses_to_run_without_gpu(pbso, fit_exe, tmp_path):
+    if pbso.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    w = synth.ffat_fit_workload(1, 5, half_cells=(1, 2, 3), cell_size=0.5)
+    nfile, vfile, kfile = _write_fit_inputs(tmp_path, w, True)
+    r = subprocess.run([fit_exe, "-n", nfile, "-v", vfile, "-c", "0.5", "-k", kfile, "-p", str(tmp_path / "p-%d.bin"), "-o", str(tmp_path / "o"),
+                        "-first", "3", "-b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU path" in r.stderr          # no fallback: the fit runs on the B200 or not at all
+    assert not os.path.exists(str(tmp_path / "o"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary,scaling", [(True, False), (False, True)])
+def test_fit_tool_writes_the_maps_the_oracle_fits(pbso, orc, fit_exe, tmp_path, binary, scaling):
+    """pbso_fit_ffat end to end: files in the reference's formats -> one batched fit on the GPU -> a .fatcube directory that
+    LoadAll reads back; Psi and geometry against the oracle's constructor + Solve."""
+    w = synth.ffat_fit_workload(4, 61, half_cells=((2, 3, 4), (3, 5, 6), (5, 6, 8)), cell_size=0.2, noise=0.02)
+    nfile, vfile, kfile = _write_fit_inputs(tmp_path, w, binary)
+    out = str(tmp_path / "maps")
+    cmd = [fit_exe, "-n", nfile, "-v", vfile, "-c", repr(w["cell_size"]), "-k", kfile, "-p", str(tmp_path / ("p-%d." + ("bin" if binary else "txt"))),
+           "-o", out, "-first", "3"] + (["-b"] if binary else []) + (["-s"] if scaling else [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "4 modes, 3 shells" in r.stdout
+    fit = orc.ffat_fit_geometry(w["cell_size"], w["V"], w["n_elements"])
+    want, _ = orc.ffat_fit_solve(fit, w["k"], w["pressure"], scaling)
+    fm = pbso.FFATMaps.LoadAll(out)
+    assert list(fm.mode_ids()) == [3, 4, 5, 6]
+    for m in range(4):
+        d = fm.get_map(3 + m)
+        assert d["k"] == w["k"][m] and np.allclose(d["psi"], want[m], rtol=1e-12, atol=0)
+        g, ig = fit["geom"][2], fit["igeom"][2]
+        assert np.array_equal(np.asarray(d["lowcorners"]).ravel(), g[1:19]) and np.array_equal(d["bboxlow"], g[22:25])
+        assert np.array_equal(d["strides"], ig[12:]) and np.array_equal(np.asarray(d["n_elements"]).ravel(), ig[:12])
+    short = str(tmp_path / ("p-3." + ("bin" if binary else "txt")))
+    with open(short, "wb") as f:                                  # a truncated pressure file: Solve's size assert
+        f.write(np.int32(0).tobytes() if binary else b"")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 4 and "wrong size" in r.stderr
+
+
+@pytest.fixture(scope="module")
 def units_exe(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("tools") / "headless_units")
     r = subprocess.run(GXX + [os.path.join(ROOT, "tests", "cpp", "headless_units.cpp"), "-o", out], capture_output=True, text=True)
