@@ -293,3 +293,38 @@ def test_driver_renders_script_like_the_oracle(pbso, orc, render_exe, tmp_path, 
     assert fmt[:3] == (3, 2, 44100)
     want = (y / 1e10).astype(np.float32)
     assert np.array_equal(data[0::2], want) and np.array_equal(data[1::2], want)
+
+
+@pytest.mark.gpu
+def test_fit_tool_feeds_the_render_tool(pbso, orc, fit_exe, render_exe, tmp_path):
+    """The two headless tools chained: shell pressures -> pbso_fit_ffat -> .fatcube directory -> pbso_render (-m -s -t -p),
+    against the oracle's own chain (fit -> GetMapVal -> ModalSolver::step)."""
+    d = str(tmp_path); case = _write_object(d, "bell", orc)
+    M = case["M"]
+    w = synth.ffat_fit_workload(M, 67, half_cells=(3, 5, 6), cell_size=0.25)
+    mat = case["mat"]
+    freqs = np.sqrt(case["w2"] / mat["density"]) / (2 * np.pi)
+    w["k"] = 2 * np.pi * freqs / synth.SPEED_OF_SOUND                        # the object's own wavenumbers
+    fitdir = tmp_path / "fit"; fitdir.mkdir()
+    nfile, vfile, kfile = _write_fit_inputs(fitdir, w, True)
+    maps_dir = str(tmp_path / "fitted_maps")
+    # the helper names the pressure files from mode id 3; this object's modes are 0..M-1
+    for m in range(M):
+        os.rename(str(fitdir / ("p-%d.bin" % (m + 3))), str(fitdir / ("q-%d.bin" % m)))
+    r = subprocess.run([fit_exe, "-n", nfile, "-v", vfile, "-c", repr(w["cell_size"]), "-k", kfile, "-p", str(fitdir / "q-%d.bin"),
+                        "-o", maps_dir, "-b", "-s"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    script = os.path.join(d, "s.txt"); open(script, "w").write(SCRIPT)
+    raw = os.path.join(d, "out.f64")
+    r = subprocess.run([render_exe, "-m", os.path.join(d, "bell.tet.obj"), "-s", os.path.join(d, "bell_surf.modes"),
+                        "-t", os.path.join(d, "bell_material.txt"), "-p", maps_dir, "-script", script, "-buf", "256", "-raw", raw],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    fit = orc.ffat_fit_geometry(w["cell_size"], w["V"], w["n_elements"])
+    psi, _ = orc.ffat_fit_solve(fit, w["k"], w["pressure"], True)
+    g, ig = fit["geom"][2], fit["igeom"][2]
+    case["maps"] = [dict(cellsize=g[0], lowcorners=g[1:19].reshape(6, 3), center1=g[19:22], bboxlow=g[22:25], bboxtop=g[25:28],
+                         center=g[28:31], k=w["k"][m], n_elements=ig[:12].reshape(6, 2), strides=ig[12:], psi=psi[m], modeid=m) for m in range(M)]
+    y = np.fromfile(raw); ref = _oracle_script(case, orc, 256)
+    assert y.size == ref.size
+    assert np.max(np.abs(y - ref)) <= 1e-9 * np.max(np.abs(ref))
