@@ -143,6 +143,39 @@ k_ffat_gather(int n_modes, int L, const double* __restrict__ geom, const double*
     }
 }
 
+// Few listeners (L <= FG_FUSED_MAX: the per-buffer cases cfg2 / cfg4): one launch.  The first FG_LPB threads of every block
+// solve their listeners' ray/box + bilinear stencil themselves (geometry from the parameter bank) instead of reading it from
+// a k_ffat_locate launch: a few microseconds of redundant FP64 per block buy back a dependent kernel launch, which is what
+// a 2.6 MB problem costs most.
+constexpr int FG_FUSED_MAX = 256;
+__global__ void __launch_bounds__(256)
+k_ffat_gather_fused(int n_modes, int L, const __grid_constant__ Geo g, const double* __restrict__ geom,
+                    const double* __restrict__ psi_tm, int n_stride, const double* __restrict__ pos, double* __restrict__ out) {
+    __shared__ FfatLoc s_loc[FG_LPB];
+    const int l0 = blockIdx.y * FG_LPB;
+    if (threadIdx.x < FG_LPB && l0 + threadIdx.x < L) {
+        const int l = l0 + threadIdx.x;
+        const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
+        FfatLoc o;
+        ffat_locate(g, p, o.idx, o.w, o.r);
+        o.tile = 0; o.lxy = 0;
+        s_loc[threadIdx.x] = o;
+    }
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const double k = m < n_modes ? geom[(size_t)m * 32 + 31] : 1.0;      // in flight while the stencils are solved
+    __syncthreads();
+    if (m >= n_modes) return;
+#pragma unroll
+    for (int i = 0; i < FG_LPB; ++i) {
+        if (l0 + i >= L) break;
+        const FfatLoc& q = s_loc[i];
+        double psi0 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * psi_tm[(size_t)q.idx[kk] * n_stride + m];    // ffat_solver.h:1198-1204
+        out[(size_t)(l0 + i) * n_modes + m] = fabs(psi0 / (k * q.r));                                  // :904-905
+    }
+}
+
 // Many listeners, texel-stationary (default for L >= FT_MIN_L): when 4 L exceeds the texel count, gathering per
 // listener re-reads every texel row from L2 several times (4 L M 8 bytes: 335 MB for 10 242 listeners x 1024 modes, the
 // bound of k_ffat_gather).  Here a CTA owns one FT_T x FT_T texel tile (plus the one-texel halo the bilinear stencil
@@ -598,6 +631,12 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
             f->cnt_parity ^= 1;
         }
         Geo g0; load_geo(g0, f->maps.at(0).geom, f->maps.at(0).igeom);
+        if (L <= FG_FUSED_MAX && !staged) {
+            k_ffat_gather_fused<<<dim3(div_up(n_modes, 256), div_up(L, FG_LPB)), 256, 0, s>>>(n_modes, L, g0, f->d_geom, f->d_psi_tm, f->n_dense,
+                                                                                          d_pos, d_out);
+            PBSO_CUDA(cudaGetLastError());
+            return PBSO_OK;
+        }
         k_ffat_locate<<<div_up(std::max(L, tiles ? n_tiles + 1 : 0), FL_THREADS), FL_THREADS, 0, s>>>(L, g0, d_pos, (FfatLoc*)f->d_loc, tt,
                                                                                 tiles ? (TileRec*)f->d_tile_rec : nullptr, cnt_cur, cnt_next);
         const size_t stage_bytes = (size_t)FS_G * f->D * sizeof(double);

@@ -97,7 +97,7 @@ for L in ([] if fit_only else [10242] if ffat_only else [64] if quick else [1, 6
     D = 6144
     bytes_alg = Mf * (min(D, 4 * L) * 8 + L * 8)
     k3.append({"L": L, "us": med * 1e3, "us_best": best * 1e3, "algorithmic_MB": bytes_alg / 1e6, "GBps": bytes_alg / (med * 1e-3) / 1e9, "frac_of_hbm": bytes_alg / (med * 1e-3) / 1e9 / hbm,
-               "kernel": "k_ffat_locate + k_ffat_tiles" if L >= 2048 else "k_ffat_locate + k_ffat_gather"})
+               "kernel": "k_ffat_locate + k_ffat_tiles" if L >= 2048 else "k_ffat_gather_fused" if L <= 256 else "k_ffat_locate + k_ffat_gather"})
     if L >= 2048:
         os.environ["PBSO_FFAT_GATHER"] = "1"
         med_g, _ = ev_time(fn, iters=10)
