@@ -448,10 +448,10 @@ int pbso_render_buffer(pbso_integrator* it, const double* space, const double* t
         double* m_qn = it->h_out + (size_t)(L > 0 ? L : 1) * T;
         if (int rc = launch_render(it, it->h_in, it->h_in + N, T, m_y, qnorm_out ? m_qn : nullptr)) return rc;
     } else {
-        // inputs are still read in place (10 KB); only the large result goes through the copy engine
+        PBSO_CUDA(cudaMemcpyAsync(it->d_in, it->h_in, sizeof(double) * (N + T), cudaMemcpyHostToDevice, it->stream));
         double* d_y = it->d_out;
         double* d_qn = it->d_out + (size_t)(L > 0 ? L : 1) * T;
-        if (int rc = launch_render(it, it->h_in, it->h_in + N, T, d_y, qnorm_out ? d_qn : nullptr)) return rc;
+        if (int rc = launch_render(it, it->d_in, it->d_in + N, T, d_y, qnorm_out ? d_qn : nullptr)) return rc;
         PBSO_CUDA(cudaMemcpyAsync(it->h_out, it->d_out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, it->stream));
     }
     PBSO_CUDA(cudaStreamSynchronize(it->stream));
