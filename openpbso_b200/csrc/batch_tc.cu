@@ -685,8 +685,9 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     const int grid = st->grid;
 #define PBSO_TC_LAUNCH(S, C)                                                                                         \
     do {                                                                                                             \
-        static bool attr = false;                                                                                    \
-        if (!attr) { PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_TS)); attr = true; } \
+        static bool attr[64] = {};      /* per device: function attributes do not carry across devices */          \
+        int dev_ = 0; cudaGetDevice(&dev_);                                                                          \
+        if (!attr[dev_ & 63]) { PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_TS)); attr[dev_ & 63] = true; } \
         k_batch_tc<S, C><<<grid, TCB_THREADS, TCB_SMEM_TS, a.stream>>>(a.n_obj, a.n_modes, n_tiles, st->cta_first, st->units, st->tabA, \
             st->tabB, st->Vbase, a.c3, a.cot, st->ev_row, a.d_ev_space, a.d_mix, flush_units);                     \
     } while (0)

@@ -59,6 +59,7 @@ struct pbso_ffat {
     void* d_tile_rec = nullptr; size_t tile_rec_cap = 0;    // [n_tiles][L] stencil records binned by texel tile (texel-tile path)
     int* d_tile_order = nullptr;                            // tiles by decreasing solid angle (listeners per tile, for directions uniform on the sphere)
     double* d_psi_tiles = nullptr;                          // [slab][tile][FT_H*FT_H + 1][FT_MS]: each work item's texels contiguous (built on first use)
+    bool tiles_attr_set = false, staged_attr_set = false;   // per handle = per device: function attributes are per device
     int* d_tile_cnt = nullptr; int cnt_parity = 0;          // [2][n_tiles] ping-pong counters: a call fills one, zeroes the other
     int tiles_y[6] = {0}, tile_base[7] = {0};           // texel tiles of FT_T x FT_T per face (shared geometry)
     int n_uncompressed = 0, n_compressed = 0;
@@ -486,6 +487,7 @@ static int load_one(const char* filename, HostMap& hm) {
 
 static void free_device(pbso_ffat* f) {
     cudaFree(f->d_geom); cudaFree(f->d_igeom); cudaFree(f->d_psi_mm); cudaFree(f->d_psi_tm); cudaFree(f->d_psi_off); cudaFree(f->d_psi_tiles); cudaFree(f->d_tile_order);
+    cudaFree(f->d_tile_rec); cudaFree(f->d_tile_cnt); f->d_tile_rec = nullptr; f->tile_rec_cap = 0; f->d_tile_cnt = nullptr;   // sized by the tile count
     f->d_psi_tiles = nullptr; f->d_tile_order = nullptr; f->d_geom = nullptr; f->d_igeom = nullptr; f->d_psi_mm = nullptr; f->d_psi_tm = nullptr; f->d_psi_off = nullptr;
 }
 
@@ -644,9 +646,8 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
         // wavefronts (scattered 8-byte shared-memory gathers + 32-byte output segments) at ~100 us, the coalesced
         // texel-major gather by L2 bandwidth at ~54 us -- so the gather is the default and staging is opt-in.
         if (tiles) {
-            static bool attr_set_t = false;
             const size_t tile_bytes = 2 * ((size_t)FT_BLK * sizeof(double) + (size_t)FT_REC * sizeof(TileRec));
-            if (!attr_set_t) { PBSO_CUDA(cudaFuncSetAttribute(k_ffat_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); attr_set_t = true; }
+            if (!f->tiles_attr_set) { PBSO_CUDA(cudaFuncSetAttribute(k_ffat_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); f->tiles_attr_set = true; }
             const int n_items = n_tiles * div_up(n_modes, FT_MS);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(std::min(n_items, FT_CTAS_PER_SM * f->sm_count)); cfg.blockDim = dim3(FT_THREADS);
@@ -659,8 +660,7 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
                                          div_up(n_modes, FT_MS), cnt_cur + n_tiles, d_out));
         } else if (staged && L >= 1024 && (f->D % 2 == 0) && stage_bytes <= 200 * 1024) {
             // whole maps in shared memory; listeners split so that the grid is ~7 waves of SMs
-            static bool attr_set = false;
-            if (!attr_set) { PBSO_CUDA(cudaFuncSetAttribute(k_ffat_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+            if (!f->staged_attr_set) { PBSO_CUDA(cudaFuncSetAttribute(k_ffat_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); f->staged_attr_set = true; }
             const int groups = div_up(n_modes, FS_G);
             // one pass over the listeners per staged group unless there are too few groups to occupy the SMs
             int l_split = std::max(1, std::min(div_up(f->sm_count, groups), div_up(L, FS_THREADS)));

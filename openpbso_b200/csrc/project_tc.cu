@@ -242,10 +242,11 @@ int tc_project(const float* d_Uhi, const float* d_Ulo, int M, const float* d_Fhi
     if (int rc = encode_map(&mAl, d_Ulo, M, pitch)) return rc;
     if (int rc = encode_map(&mBh, d_Fhi, B, pitch)) return rc;
     if (int rc = encode_map(&mBl, d_Flo, B, pitch)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};        // per device: function attributes do not carry across devices
+    int dev_ = 0; cudaGetDevice(&dev_);
+    if (!attr_set[dev_ & 63]) {
         PBSO_CUDA(cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev_ & 63] = true;
     }
     const int mt = div_up(M, TC_BM), nt = div_up(B, TC_BN), kb_total = pitch / TC_BK;
     // split K: smallest split count whose grid fills whole waves of SMs to >= 90 % (1 CTA per SM), every split
