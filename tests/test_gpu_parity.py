@@ -259,11 +259,12 @@ def test_ffat_many_listeners_staged(pbso, orc):
     assert np.allclose(got1, got[:100], rtol=1e-14)
 
 
-@pytest.mark.parametrize("n_modes,n_tex,L", [(37, 16, 2500), (200, 12, 3000), (256, 32, 4500), (130, 9, 2100)])
+@pytest.mark.parametrize("n_modes,n_tex,L", [(37, 16, 2500), (200, 12, 3000), (256, 32, 4500), (130, 9, 2100), (66, 8, 6100)])
 def test_ffat_many_listeners_texel_tiles(pbso, orc, n_modes, n_tex, L):
     """L >= 2048 and 4 L >= texels: the texel-stationary kernel (tile rows staged with bulk async copies).  Odd mode
     counts take the non-bulk / scalar-store tails, 12- and 9-texel faces leave partial tiles, 200/256 modes span two
-    mode slabs, and 4500 listeners need two scan passes.  Same numbers as the per-listener gather."""
+    mode slabs, and with 8-texel faces (one tile per face) 6100 listeners put ~1000 records in a tile: four record chunks
+    through the two record buffers.  Same numbers as the per-listener gather."""
     freqs = synth.mode_frequencies(n_modes, 78)
     maps = synth.ffat_maps(freqs, 2000, n=n_tex)
     pos = synth.listeners(L, 14)
