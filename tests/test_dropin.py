@@ -112,3 +112,31 @@ def test_drop_in_caller_matches_oracle(pbso, orc, drop_in_exe, tmp_path):
     tr = np.frombuffer(raw[off:off + 8 * N])
     assert np.allclose(tr, orc.ffat_eval(case["maps"], np.array([2.0, -3.0, 4.0]))[0], rtol=1e-12)
     assert n_buf == len(SCRIPT) - 1
+
+
+def test_ffat_construction_mirror_compiles_and_refuses_to_run_without_gpu(pbso, tmp_path):
+    """tests/cpp/ffat_fit_main.cpp -- FFAT_Map<double,3>(modeId, cellSize, V, N_elements), Solve, ReadNElementsFile,
+    ReadComplexVector, FFAT_Map_Serialize::Save/Load/Check, GetMapVal through the header mirror -- builds on a machine
+    without a GPU, and there the constructor throws instead of falling back to a CPU path."""
+    from openpbso_b200 import synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include", "openpbso"); libdir = os.path.join(root, "openpbso_b200")
+    exe = str(tmp_path / "ffat_fit_main")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wno-sign-compare", "-I" + os.path.join(inc, "eigen_shim"), "-I" + inc,
+                        os.path.join(root, "tests", "cpp", "ffat_fit_main.cpp"), "-L" + libdir, "-lpbso_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if pbso.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    w = synth.ffat_fit_workload(1, 5, half_cells=(1, 2, 3), cell_size=0.5)
+    nfile = str(tmp_path / "n.txt")
+    with open(nfile, "w") as f:
+        for shell in w["n_elements"]:
+            f.write(" ".join("%d %d" % (a, b) for a, b in shell) + "\n")
+    vfile = str(tmp_path / "V.f64"); np.ascontiguousarray(w["V"]).tofile(vfile)
+    pfile = str(tmp_path / "p.bin")
+    with open(pfile, "wb") as f:
+        f.write(np.int32(2 * w["pressure"].shape[1]).tobytes()); f.write(np.ascontiguousarray(w["pressure"][0]).view(np.float64).tobytes())
+    r = subprocess.run([exe, nfile, vfile, "0.5", "0", repr(float(w["k"][0])), pfile, "1", "0", str(tmp_path / "o.fatcube"), "1", "2", "3"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU path" in r.stderr
