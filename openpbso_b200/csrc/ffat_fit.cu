@@ -326,15 +326,29 @@ k_fit_scale(int n_dir, int n_blocks, const double2* __restrict__ partial, double
             double* __restrict__ scale_out) {
     __shared__ double s_scale;
     const int m = blockIdx.x;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // lane j takes partials j, j + 32, ... in order, then a fixed shuffle tree: the same summation order every run
         double numer = 0.0, denom = 0.0;
-        for (int b = 0; b < n_blocks; ++b) { const double2 t = partial[(size_t)m * n_blocks + b]; numer += t.x; denom += t.y; }
-        s_scale = sqrt(numer / denom);
-        if (scale_out) scale_out[m] = s_scale;
+        for (int b = threadIdx.x; b < n_blocks; b += 32) { const double2 t = partial[(size_t)m * n_blocks + b]; numer += t.x; denom += t.y; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            numer += __shfl_down_sync(0xffffffffu, numer, o);
+            denom += __shfl_down_sync(0xffffffffu, denom, o);
+        }
+        if (threadIdx.x == 0) {
+            s_scale = sqrt(numer / denom);
+            if (scale_out) scale_out[m] = s_scale;
+        }
     }
     __syncthreads();
     const double sc = s_scale;
-    for (int d = threadIdx.x; d < n_dir; d += blockDim.x) psi[(size_t)m * n_dir + d] *= sc;
+    double* row = psi + (size_t)m * n_dir;
+    int d = threadIdx.x;
+    for (; d + 3 * 256 < n_dir; d += 4 * 256) {                       // four independent read-modify-writes in flight
+        const double a0 = row[d], a1 = row[d + 256], a2 = row[d + 512], a3 = row[d + 768];
+        row[d] = a0 * sc; row[d + 256] = a1 * sc; row[d + 512] = a2 * sc; row[d + 768] = a3 * sc;
+    }
+    for (; d < n_dir; d += 256) row[d] *= sc;
 }
 
 __global__ void k_fit_fill(int n, double v, double* __restrict__ out) {
