@@ -124,3 +124,49 @@ def test_argument_validation_without_device(pbso):
             pbso.FFATFitter(0.5, np.concatenate([V] * rows), np.stack([ne] * shells))
         assert e.value.code == 1
     assert L.pbso_ffat_fitter_destroy(None) == 0
+
+
+def test_fit_input_formats_match_the_reference_parsers(pbso, tmp_path):
+    """ReadComplexVector / WriteComplexVector (io.h:24-92) and FFAT_Map<T,3>::ReadNElementsFile (ffat_solver.h:1100-1118): the
+    mirror's versions against the reference's own, each compiled into the same small program (tests/cpp/io_formats_main.cpp)."""
+    import subprocess
+    ref_root = "/root/reference"
+    if not os.path.isdir(ref_root):
+        pytest.skip("no /root/reference here")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include", "openpbso"); libdir = os.path.join(root, "openpbso_b200")
+    src = os.path.join(root, "tests", "cpp", "io_formats_main.cpp")
+    mirror = str(tmp_path / "io_mirror"); refexe = str(tmp_path / "io_ref")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(inc, "eigen_shim"), "-I" + inc, src, "-L" + libdir, "-lpbso_b200",
+                        "-Wl,-rpath," + libdir, "-o", mirror], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-w", "-I" + os.path.join(root, "oracle", "ref_stubs"), "-I" + os.path.join(inc, "eigen_shim"),
+                        "-I" + ref_root, src, os.path.join(ref_root, "io.cpp"), "-o", refexe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rng = np.random.default_rng(21)
+    z = rng.standard_normal(37) * 10.0 ** rng.integers(-8, 8, 37) + 1j * rng.standard_normal(37)
+    pbin = str(tmp_path / "p.bin"); ptxt = str(tmp_path / "p.txt"); nfile = str(tmp_path / "n.txt")
+    with open(pbin, "wb") as f:
+        f.write(np.int32(2 * len(z)).tobytes()); f.write(np.ascontiguousarray(z).view(np.float64).tobytes())
+    with open(ptxt, "w") as f:
+        for v in z:
+            f.write("%.17g %.17g\n" % (v.real, v.imag))
+    open(nfile, "w").write("4 5 4 5 5 6 5 6 6 4 6 4\n8 9 8 9 9 10 9 10 10 8 10 8\n12 12 12 12 12 12 12 12 12 12 12 12\n")
+    for pfile, binary in ((pbin, "1"), (ptxt, "0")):
+        outs = []
+        for exe in (mirror, refexe):
+            d = str(tmp_path / (os.path.basename(exe) + binary + ".f64"))
+            assert subprocess.run([exe, "read", pfile, binary, nfile, d]).returncode == 0
+            outs.append(np.fromfile(d))
+        assert np.array_equal(outs[0], outs[1])
+        assert outs[0][0] == len(z) and np.array_equal(outs[0][1:1 + 2 * len(z)].view(np.complex128), z)
+        assert outs[0][1 + 2 * len(z)] == 3 and outs[0][-1] == 12
+    # writers: the same bytes from both, and readable back
+    dump = str(tmp_path / "z.f64"); np.ascontiguousarray(z).view(np.float64).tofile(dump)
+    for binary in ("1", "0"):
+        files = []
+        for exe in (mirror, refexe):
+            o = str(tmp_path / (os.path.basename(exe) + "_w" + binary))
+            assert subprocess.run([exe, "write", dump, binary, o]).returncode == 0
+            files.append(open(o, "rb").read())
+        assert files[0] == files[1] and len(files[0]) > 0
