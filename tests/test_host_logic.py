@@ -170,3 +170,40 @@ def test_fit_input_formats_match_the_reference_parsers(pbso, tmp_path):
             assert subprocess.run([exe, "write", dump, binary, o]).returncode == 0
             files.append(open(o, "rb").read())
         assert files[0] == files[1] and len(files[0]) > 0
+
+
+def test_host_side_headers_match_the_reference(pbso, orc, tmp_path):
+    """forces.h (Point / Gaussian / autoregressive profiles at BUF 64 / 256 / 513, SetParam), ModeData (read, write,
+    numModesAudible incl. its cached branch), ModalMaterial (Read, xi, omega_di, missing file): the mirror's headers against
+    the reference's own, from one source file compiled against each (tests/cpp/host_parts_main.cpp).  Bit for bit."""
+    import subprocess
+    ref_root = "/root/reference"
+    if not os.path.isdir(ref_root):
+        pytest.skip("no /root/reference here")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include", "openpbso"); libdir = os.path.join(root, "openpbso_b200")
+    src = os.path.join(root, "tests", "cpp", "host_parts_main.cpp")
+    exes = {}
+    for name, flags in (("mirror", ["-I" + os.path.join(inc, "eigen_shim"), "-I" + inc, "-L" + libdir, "-lpbso_b200", "-Wl,-rpath," + libdir]),
+                        ("reference", ["-w", "-I" + os.path.join(inc, "eigen_shim"), "-I" + ref_root])):
+        exe = str(tmp_path / ("host_" + name))
+        r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", src, "-o", exe] + flags, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        exes[name] = exe
+    M, K = 7, 12
+    f = synth.mode_frequencies(M, 3, 100.0, 15000.0)
+    w2 = synth.omega_squared(f, 2600.0)
+    U = synth.mode_shapes(M, K, 4)
+    mfile = str(tmp_path / "o_surf.modes"); orc.modes_write(mfile, w2, U)
+    tfile = str(tmp_path / "mat.txt"); open(tfile, "w").write("# density E nu alpha beta\n# second comment\n2600 6.2e10 0.2 30 5e-7\n")
+    dumps = {}; rewritten = {}
+    for name, exe in exes.items():
+        d = str(tmp_path / (name + ".f64")); mw = str(tmp_path / (name + ".modes"))
+        r = subprocess.run([exe, mfile, tfile, d, mw], capture_output=True, text=True)
+        if name == "mirror" and r.returncode != 0 and "no CPU path" in r.stderr:
+            pytest.skip("the mirror's ModeData uploads to the device; no GPU here")
+        assert r.returncode == 0, r.stderr
+        dumps[name] = np.fromfile(d); rewritten[name] = open(mw, "rb").read()
+    assert dumps["mirror"].size == dumps["reference"].size and dumps["mirror"].size > 3 * 5 * 4 * 65
+    assert np.array_equal(dumps["mirror"], dumps["reference"])
+    assert rewritten["mirror"] == rewritten["reference"] == open(mfile, "rb").read()
