@@ -207,3 +207,23 @@ def test_host_side_headers_match_the_reference(pbso, orc, tmp_path):
     assert dumps["mirror"].size == dumps["reference"].size and dumps["mirror"].size > 3 * 5 * 4 * 65
     assert np.array_equal(dumps["mirror"], dumps["reference"])
     assert rewritten["mirror"] == rewritten["reference"] == open(mfile, "rb").read()
+
+
+def test_message_queue_matches_the_reference_queue(tmp_path):
+    """external/readerwriterqueue.h: the mirror's queue against the reference's (moodycamel) on capacity for every maxSize
+    modal_solver.h uses (512 / 2 / 1 / 2 / 1 ...), FIFO order across wrap-around, size_approx and empty dequeues."""
+    import subprocess
+    ref_root = "/root/reference"
+    if not os.path.isdir(ref_root):
+        pytest.skip("no /root/reference here")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cpp", "queue_main.cpp")
+    outs = []
+    for name, incdir in (("mirror", os.path.join(root, "include", "openpbso", "external")), ("reference", os.path.join(ref_root, "external"))):
+        exe = str(tmp_path / ("queue_" + name))
+        r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-w", "-I" + incdir, src, "-o", exe, "-pthread"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and "maxSize 1023 capacity 1023" in outs[0]
