@@ -659,3 +659,17 @@ def test_ffat_fit_header_mirror_caller(pbso, orc, tmp_path):
             m = dict(cellsize=g[0], lowcorners=g[1:19].reshape(6, 3), center1=g[19:22], bboxlow=g[22:25], bboxtop=g[25:28],
                      center=g[28:31], k=w["k"][0], n_elements=ig[:12].reshape(6, 2), strides=ig[12:], psi=want[0], modeid=0)
             assert np.isclose(float(v1), orc.ffat_eval([m], [probe])[0, 0], rtol=1e-11)
+
+
+def test_ffat_fit_reproduces_the_reference_fixture(pbso, golden_dir):
+    """K6 against Psi computed by the reference's OWN Solve (tests/golden/ffat_fit.npz, generated here with oracle/_ref):
+    no oracle in between.  Non-cubic shells, four modes with wavenumbers from 1.5 to 120, unread odd entries filled with noise."""
+    g = np.load(os.path.join(golden_dir, "ffat_fit.npz"))
+    ft = pbso.FFATFitter(float(g["cell_size"]), g["V"], g["n_elements"])
+    geom, igeom = ft.shell(2)
+    assert np.array_equal(geom[1:19], g["shell2_lowcorners"].ravel()) and np.array_equal(igeom[12:], g["shell2_strides"])
+    assert np.array_equal(geom[22:25], g["shell2_bboxlow"]) and np.array_equal(geom[25:28], g["shell2_bboxtop"])
+    assert np.array_equal(geom[28:31], g["centre"])
+    for scaling, key in ((False, "psi"), (True, "psi_scaled")):
+        psi, _ = ft.Solve(g["k"], g["pressure"], scaling)
+        assert np.allclose(psi, g[key], rtol=1e-12, atol=0)

@@ -220,3 +220,16 @@ def test_ffat_fit_single_shell_weighting(orc):
     assert np.allclose(Pabs[0, :, 2], np.abs(vals), rtol=1e-14) and np.all(Pabs[0, :, :2] == 0)
     want = (np.abs(vals) / (k * R[:, 2])) / np.sum(1 / (k * R) ** 2, axis=1)
     assert np.allclose(psi[0], want, rtol=1e-13)
+
+
+def test_ffat_fit_oracle_reproduces_the_reference_fixture(orc, golden_dir):
+    """tests/golden/ffat_fit.npz was produced by the reference's own CubemapMesh + FFAT_Map<double,3> constructor + Solve
+    (tests/golden/make_golden_fit.py); the restatement must reproduce it without the reference being present."""
+    g = np.load(os.path.join(golden_dir, "ffat_fit.npz"))
+    fit = orc.ffat_fit_geometry(float(g["cell_size"]), g["V"], g["n_elements"])
+    assert np.array_equal(fit["geom"][2][1:19], g["shell2_lowcorners"].ravel())
+    assert np.array_equal(fit["geom"][2][22:25], g["shell2_bboxlow"]) and np.array_equal(fit["geom"][2][25:28], g["shell2_bboxtop"])
+    assert np.array_equal(fit["igeom"][2][12:], g["shell2_strides"]) and np.array_equal(fit["geom"][2][28:31], g["centre"])
+    for scaling, key in ((False, "psi"), (True, "psi_scaled")):
+        psi, _ = orc.ffat_fit_solve(fit, g["k"], g["pressure"], scaling)
+        assert np.allclose(psi, g[key], rtol=1e-13, atol=0)
