@@ -673,3 +673,20 @@ def test_ffat_fit_reproduces_the_reference_fixture(pbso, golden_dir):
     for scaling, key in ((False, "psi"), (True, "psi_scaled")):
         psi, _ = ft.Solve(g["k"], g["pressure"], scaling)
         assert np.allclose(psi, g[key], rtol=1e-12, atol=0)
+
+
+def test_ffat_eval_reproduces_the_reference_fixture(pbso, golden_dir):
+    """K3 against |GetMapVal| computed by the reference's OWN code (tests/golden/ffat_eval.npz): the per-map kernel on the
+    committed .fatcube files, and on 24 maps sharing one geometry the fused few-listener kernel, the locate + gather pair and
+    the texel-stationary kernel -- probe positions incl. face axes, edge / corner ties and points inside the box."""
+    g = np.load(os.path.join(golden_dir, "ffat_eval.npz"))
+    got = pbso.FFATMaps.LoadAll(os.path.join(golden_dir, "fatcube")).computeTransfer(g["files_pos"])
+    ref = g["files_out"]
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    fin = np.isfinite(ref)
+    assert np.allclose(got[fin], ref[fin], rtol=1e-12, atol=0)
+    fm = pbso.FFATMaps.from_dicts(synth.ffat_maps(g["shared_freqs"], 2000, n=8))
+    pos, want = g["shared_pos"], g["shared_out"]
+    assert np.allclose(fm.computeTransfer(pos[:80]), want[:80], rtol=1e-12, atol=0)          # fused single launch (L <= 256)
+    assert np.allclose(fm.computeTransfer(pos[:700]), want[:700], rtol=1e-12, atol=0)        # locate + gather
+    assert np.allclose(fm.computeTransfer(pos), want, rtol=1e-12, atol=0)                    # texel tiles (L >= 2048)

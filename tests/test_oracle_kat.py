@@ -233,3 +233,18 @@ def test_ffat_fit_oracle_reproduces_the_reference_fixture(orc, golden_dir):
     for scaling, key in ((False, "psi"), (True, "psi_scaled")):
         psi, _ = orc.ffat_fit_solve(fit, g["k"], g["pressure"], scaling)
         assert np.allclose(psi, g[key], rtol=1e-13, atol=0)
+
+
+def test_ffat_eval_oracle_reproduces_the_reference_fixture(orc, golden_dir):
+    """tests/golden/ffat_eval.npz holds |GetMapVal| computed by the reference's own LoadAll + GetMapVal
+    (tests/golden/make_golden_ffat_eval.py) at probe positions incl. face axes, edge / corner ties and interior points."""
+    from oracle import fatcube
+    g = np.load(os.path.join(golden_dir, "ffat_eval.npz"))
+    maps = fatcube.load_all(os.path.join(golden_dir, "fatcube"))
+    got = np.concatenate([orc.ffat_eval([maps[i]], g["files_pos"]) for i in range(3)], axis=1)
+    ref = g["files_out"]
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    fin = np.isfinite(ref)
+    assert np.allclose(got[fin], ref[fin], rtol=1e-13, atol=0)
+    shared = synth.ffat_maps(g["shared_freqs"], 2000, n=8)
+    assert np.allclose(orc.ffat_eval(shared, g["shared_pos"]), g["shared_out"], rtol=1e-13, atol=0)
