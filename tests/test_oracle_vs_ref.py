@@ -378,3 +378,45 @@ def test_cubemap_vertices_match_reference_mesh(orc, ref, lo, hi, cell, grid_low)
         assert np.allclose(face[:, dk], plane, atol=1e-14)
         assert np.allclose(face[0, [di, dj]], [grid_low[di] + cell * lo[di], grid_low[dj] + cell * lo[dj]], atol=1e-14)
         off += ne[f][0] * ne[f][1]
+
+
+def test_projection_matches_the_reference_tool_functions(orc, ref, tmp_path):
+    """GetModalForceVertex / GetModalForceFace are defined inside the reference's GUI program
+    (tools/real_time_modal_sound.cpp:236-295), which cannot be built here.  The two function templates are cut out of the
+    reference file at test time into a temporary include (nothing is stored in the repository) and compiled with the
+    reference's headers in place around a small harness (tests/cpp/ref_modal_force_main.cpp); the oracle's restatement -- the
+    checker of kernel K4 -- must give the same numbers."""
+    import os, subprocess
+    ref_root = "/root/reference"
+    src = open(os.path.join(ref_root, "tools", "real_time_modal_sound.cpp")).read()
+    a = src.index("template<typename T>\nvoid GetModalForceFace(")
+    b = src.index("template<typename T>\nModalMaterial<T> *ReadMaterial(")
+    extract = str(tmp_path / "ref_modal_force_extract.h")
+    open(extract, "w").write(src[a:b])
+    assert "GetModalForceVertex" in src[a:b] and src[a:b].count("template<typename T>") == 2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "ref_modal_force")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-w", '-DREF_MODAL_FORCE_EXTRACT="%s"' % extract,
+                        "-I" + os.path.join(root, "oracle", "ref_stubs"), "-I" + os.path.join(root, "include", "openpbso", "eigen_shim"), "-I" + ref_root,
+                        os.path.join(root, "tests", "cpp", "ref_modal_force_main.cpp"), os.path.join(ref_root, "io.cpp"), "-o", exe, "-pthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    M, V = 23, 40
+    U = synth.mode_shapes(M, 3 * V, 5)
+    w2 = synth.omega_squared(synth.mode_frequencies(M, 6), 2600.0)
+    mfile = str(tmp_path / "o_surf.modes"); orc.modes_write(mfile, w2, U)
+    rng = np.random.default_rng(7)
+    cmds = []; want = []
+    for forceDim in (M, 9):
+        cmds.clear(); want.clear()
+        for _ in range(12):
+            vid = int(rng.integers(0, V)); vn = synth.unit_vectors(1, int(rng.integers(1 << 30)))[0]
+            cmds.append("vertex %d %.17g %.17g %.17g" % (vid, vn[0], vn[1], vn[2])); want.append(orc.project_vertex(U, vid, vn, forceDim))
+            vids = rng.integers(0, V, 3); bc = rng.random(3); bc /= bc.sum()
+            cmds.append("face %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g" % (vids[0], vids[1], vids[2], bc[0], bc[1], bc[2], vn[0], vn[1], vn[2]))
+            want.append(orc.project_face(U, vids, bc, vn, forceDim))
+        out = str(tmp_path / "out.f64")
+        r = subprocess.run([exe, mfile, str(forceDim), out], input="\n".join(cmds) + "\n", capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = np.fromfile(out).reshape(len(cmds), forceDim)
+        # same three / nine products; the oracle is built -march=native (FMA contraction), the reference harness is not
+        assert np.allclose(got, np.array(want), rtol=1e-13, atol=1e-15)
