@@ -13,8 +13,10 @@
 // headers compiled from /root/reference (oracle/Makefile target `ref` ->
 // oracle/_ref/libpbso_ref.so; Eigen is absent in the image so those headers
 // are compiled against the minimal shim include/openpbso/eigen_shim/Eigen/Dense).
-// Rows without that mark are "parity unpinned": they are anchored only on
-// analytic known-answer tests (tests/test_oracle_kat.py).
+// Rows without that mark would be "parity unpinned" (anchored only on analytic
+// known-answer tests, tests/test_oracle_kat.py); at the end of round 1 every row
+// carries the mark except libigl's per_vertex_normals (oracle.py), whose
+// source is not in the reference tree.
 //
 // Each function cites the reference file:line it follows (paths relative to
 // /root/reference).  No Eigen: every Eigen expression on the path is an
@@ -173,8 +175,8 @@ struct AutoregressiveForce : Force {                                // forces.h:
 };
 
 // -----------------------------------------------------------------------------
-// ModalSolver   (modal_solver.h)   [parity unpinned: state machine restated;
-//  the arithmetic inside is Integrator::step + forces, which are pinned]
+// ModalSolver   (modal_solver.h)   [pinned:_ref -- the reference's own ModalSolver<double,BUF>::step and queues,
+//  buffer by buffer on the committed force script, cfg1 and a cfg5-style batch: tests/test_oracle_vs_ref.py]
 // -----------------------------------------------------------------------------
 struct ForceMessage {                                               // modal_solver.h:27-77
     std::vector<double> data;
@@ -281,7 +283,8 @@ struct Solver {
 
 // -----------------------------------------------------------------------------
 // Impulse projection U^T f   (tools/real_time_modal_sound.cpp:236-295)
-// [parity unpinned -- three/nine-term dot products]
+// [pinned: the reference tool's own GetModalForceVertex/Face, cut out at test time and compiled in place:
+//  tests/test_oracle_vs_ref.py::test_projection_matches_the_reference_tool_functions]
 // U is mode-major: U[m*nDOF + d]  (ModeData.h:23-24, 61-83)
 // -----------------------------------------------------------------------------
 static void project_vertex(int forceDim, const double* U, int nDOF, int vid,
@@ -307,8 +310,9 @@ static void project_face(int forceDim, const double* U, int nDOF, const int vids
 }
 
 // -----------------------------------------------------------------------------
-// FFAT map evaluation   (ffat_solver.h)   [parity unpinned -- KATs:
-//  texel-centre identity, 1/r law, continuity; see tests/test_oracle_kat.py]
+// FFAT map evaluation   (ffat_solver.h)   [pinned:_ref -- the reference's own LoadAll + |GetMapVal| at ~1000 probe
+//  positions incl. ties, tests/test_oracle_vs_ref.py, and the reference-generated fixture tests/golden/ffat_eval.npz;
+//  KATs (texel-centre identity, 1/r law, continuity) in tests/test_oracle_kat.py]
 // -----------------------------------------------------------------------------
 struct FFATMap {                 // fields kept by ffat_map_serialize.h:55-79
     double k;                    // FFAT_Map<T,3>::_k
