@@ -15,8 +15,8 @@
 // are compiled against the minimal shim include/openpbso/eigen_shim/Eigen/Dense).
 // Rows without that mark would be "parity unpinned" (anchored only on analytic
 // known-answer tests, tests/test_oracle_kat.py); at the end of round 1 every row
-// carries the mark except libigl's per_vertex_normals (oracle.py), whose
-// source is not in the reference tree.
+// carries the mark except libigl's per_vertex_normals (oracle.py): libigl
+// needs the real Eigen, which is absent, so it cannot be compiled here.
 //
 // Each function cites the reference file:line it follows (paths relative to
 // /root/reference).  No Eigen: every Eigen expression on the path is an
