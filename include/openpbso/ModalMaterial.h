@@ -1,3 +1,12 @@
+// ---------------------------------------------------------------------------------------------------------
+// Derived from openpbso (https://github.com/jhwang7628/openpbso), ModalMaterial.h
+//   Copyright (C) 2018 Jui-Hsien Wang <juiwang@alumni.stanford.edu>
+// This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0.  If a copy of the MPL
+// was not distributed with this file, You can obtain one at https://mozilla.org/MPL/2.0/.
+// The host-side bodies below restate the reference's statements so that a drop-in caller sees bit-identical
+// host behaviour (same libstdc++ RNG stream, same state machine); what is new here is the forwarding of the
+// hot loops to the B200 C ABI (include/pbso_b200.h).
+// ---------------------------------------------------------------------------------------------------------
 // openpbso drop-in: ModalMaterial<REAL> (reference ModalMaterial.h:19-56).  Host-only carrier; nothing here
 // needs the device.
 #ifndef MODAL_MATERIAL_H

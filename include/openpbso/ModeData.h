@@ -1,3 +1,12 @@
+// ---------------------------------------------------------------------------------------------------------
+// Derived from openpbso (https://github.com/jhwang7628/openpbso), ModeData.h
+//   Copyright (C) 2018 Jui-Hsien Wang <juiwang@alumni.stanford.edu>
+// This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0.  If a copy of the MPL
+// was not distributed with this file, You can obtain one at https://mozilla.org/MPL/2.0/.
+// The host-side bodies below restate the reference's statements so that a drop-in caller sees bit-identical
+// host behaviour (same libstdc++ RNG stream, same state machine); what is new here is the forwarding of the
+// hot loops to the B200 C ABI (include/pbso_b200.h).
+// ---------------------------------------------------------------------------------------------------------
 // openpbso drop-in: ModeData<REAL> (reference ModeData.h:19-148).  Same public members and file format;
 // additionally keeps a lazily created device copy of the mode shapes for the impulse projection kernels
 // (GetModalForceVertex / GetModalForceFace in modal_force.h).

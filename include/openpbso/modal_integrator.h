@@ -1,3 +1,12 @@
+// ---------------------------------------------------------------------------------------------------------
+// Derived from openpbso (https://github.com/jhwang7628/openpbso), modal_integrator.h
+//   Copyright (C) 2018 Jui-Hsien Wang <juiwang@alumni.stanford.edu>
+// This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0.  If a copy of the MPL
+// was not distributed with this file, You can obtain one at https://mozilla.org/MPL/2.0/.
+// The host-side bodies below restate the reference's statements so that a drop-in caller sees bit-identical
+// host behaviour (same libstdc++ RNG stream, same state machine); what is new here is the forwarding of the
+// hot loops to the B200 C ABI (include/pbso_b200.h).
+// ---------------------------------------------------------------------------------------------------------
 // openpbso drop-in: ModalIntegrator<T> (reference modal_integrator.h:19-123) over the C ABI.
 // Solves  q'' + a q' + b q = f  per mode with the DyRT two-pole IIR; coefficients (kernel K2), state and
 // Step() live on the B200.  Same constructor / Build / Step signatures and the same ownership: Build returns
@@ -24,7 +33,9 @@ public:
         assert(b.size() == N && "Vec b has wrong size");
         std::vector<double> da(N), db(N);
         for (int i = 0; i < N; ++i) { da[i] = (double)a(i); db[i] = (double)b(i); }
-        pbso_mirror::check(pbso_integrator_create(N, (double)h, da.data(), db.data(), &_h), "ModalIntegrator");
+        // an empty integrator (every mode culled by freq_threshold, tools/...cpp:309-345) is legal in the
+        // reference and renders silence: it owns no device handle
+        if (N > 0) pbso_mirror::check(pbso_integrator_create(N, (double)h, da.data(), db.data(), &_h), "ModalIntegrator");
         _q_k.setZero(N); _in.resize(N); _out.resize(N);
     }
     ~ModalIntegrator() { pbso_integrator_destroy(_h); }
@@ -47,12 +58,14 @@ public:
     }
     const ModalVec& Step(const ModalVec& Q) {
         assert(Q.size() == _N && "input force incorrect dimension");
+        if (_N == 0) return _q_k;
         for (int i = 0; i < _N; ++i) _in[i] = (double)Q(i);
         pbso_mirror::check(pbso_integrator_step(_h, _in.data(), _out.data()), "ModalIntegrator::Step");
         for (int i = 0; i < _N; ++i) _q_k(i) = (T)_out[i];
         return _q_k;
     }
     const ModalVec& Step() {
+        if (_N == 0) return _q_k;
         pbso_mirror::check(pbso_integrator_step(_h, nullptr, _out.data()), "ModalIntegrator::Step");
         for (int i = 0; i < _N; ++i) _q_k(i) = (T)_out[i];
         return _q_k;

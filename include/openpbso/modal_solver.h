@@ -1,3 +1,12 @@
+// ---------------------------------------------------------------------------------------------------------
+// Derived from openpbso (https://github.com/jhwang7628/openpbso), modal_solver.h
+//   Copyright (C) 2018 Jui-Hsien Wang <juiwang@alumni.stanford.edu>
+// This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0.  If a copy of the MPL
+// was not distributed with this file, You can obtain one at https://mozilla.org/MPL/2.0/.
+// The host-side bodies below restate the reference's statements so that a drop-in caller sees bit-identical
+// host behaviour (same libstdc++ RNG stream, same state machine); what is new here is the forwarding of the
+// hot loops to the B200 C ABI (include/pbso_b200.h).
+// ---------------------------------------------------------------------------------------------------------
 // openpbso drop-in: ModalSolver<T, BUF_SIZE> (reference modal_solver.h:22-399) -- the per-buffer scheduler.
 // Message types, queue capacities and the force / transfer state machine of step() follow the reference; the
 // hot loop (BUF_SIZE integrator steps + transfer-weighted modal sum + per-mode RMS, :261-272) is one launch of
@@ -96,6 +105,7 @@ class ModalSolver {
     bool _useTransferCache = true;
     bool _sustainedForces = false;
     bool _transferDirty = true;                       // device copy of _latest_transfer is stale
+    bool _latestIsUnit = true;                        // _latest_transfer currently holds setToUnit()'s values
     std::vector<double> _stage_space, _stage_time, _stage_trans, _stage_y, _stage_qnorm;
 
 public:
@@ -150,13 +160,22 @@ public:
         if (_useTransferMutex.try_lock()) { useTransfer = _useTransfer; _useTransferMutex.unlock(); }
         if (useTransfer) {
             TransMessage<T> trans;
-            if (dequeueTransMessage(trans)) { _latest_transfer = trans; _transferDirty = true; }
-        } else {
-            _latest_transfer.setToUnit(); _transferDirty = true;
+            if (dequeueTransMessage(trans)) { _latest_transfer = trans; _transferDirty = true; _latestIsUnit = false; }
+        } else if (!_latestIsUnit) {
+            // the reference re-fills the unit vector every buffer (:254); its values never change, so the device
+            // table is refreshed only on the switch from a real transfer to the unit one
+            _latest_transfer.setToUnit(); _transferDirty = true; _latestIsUnit = true;
         }
         _useTransferCache = useTransfer;
         assert(_forceSpreadBufferSpace.size() == _N_modes && "dimension of force message incorrect");
 
+        if (_N_modes == 0) {                                   // empty solver: the reference's loop yields zeros
+            _mess_sound.data.setZero();
+            _mess_qnorm.data.resize(0);
+            _queue_qnorm.try_enqueue(_mess_qnorm);
+            enqueueSoundMessageNoFail(_mess_sound, -1);
+            return;
+        }
         // -- hot loop on the B200: BUF_SIZE x (Step + dot + q^2), then sqrt --
         pbso_integrator* h = _integrator->handle();
         if (_transferDirty) {

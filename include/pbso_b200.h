@@ -236,6 +236,16 @@ int pbso_batch_last_kernel_ms(pbso_batch* bt, float* ms, int* launches);
  * 3: FFMA with three distinct registers; 4: fma.rn.f32x2 with three distinct register pairs.
  * Returns measured TFLOP/s. */
 int pbso_measure_fma_peak(int kind, double* tflops, double* sm_mhz_est);
+/* Bare tcgen05.mma loop (A operand in TMEM, B in shared memory), one persistent CTA (cta_group 1) or CTA pair
+ * (cta_group 2) per SM: the measured tensor-pipe peak that the tensor rooflines of the batch renderer and the
+ * batched projection divide by.  kind 0: kind::tf32 (K = 8 per MMA), 1: kind::f16 (K = 16); n = MMA N (128 / 256);
+ * stress != 0 also runs four warps of conflict-free shared-memory stores beside the MMAs and reports how many
+ * wavefronts per cycle per SM they sustained.  Outputs: TFLOP/s of the whole device, median cycles per MMA. */
+int pbso_measure_tc_peak(int kind, int cta_group, int n, int stress, double* tflops,
+                         double* cycles_per_mma, double* stress_wavefronts_per_cycle);
+/* One [256 x 128] x K product on a CTA pair (tcgen05.mma cta_group::2, A from TMEM) with integer-valued operands:
+ * max |D - A B^T| (0 when the operand placement assumed by the pair kernels is right). */
+int pbso_tc_selftest(int kind, double* max_err);
 /* STREAM-style device copy bandwidth in GB/s (read+write bytes). */
 int pbso_measure_copy_bw(size_t bytes, double* gbs);
 /* Writes `bytes` to a scratch buffer to evict L2 between timed iterations. */

@@ -101,6 +101,8 @@ def lib():
             "pbso_batch_set_stream": [vp, vp],
             "pbso_batch_last_kernel_ms": [vp, c_fp, c_ip],
             "pbso_measure_fma_peak": [C.c_int, c_dp, c_dp],
+            "pbso_measure_tc_peak": [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp],
+            "pbso_tc_selftest": [C.c_int, c_dp],
             "pbso_measure_copy_bw": [C.c_size_t, c_dp],
             "pbso_flush_l2": [C.c_size_t],
         }

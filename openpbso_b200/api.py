@@ -27,6 +27,19 @@ def measure_fma_peak(kind):
     return t.value, mhz.value
 
 
+def measure_tc_peak(kind, cta_group=1, n=128, stress=0):
+    """(TFLOP/s, cycles per MMA, stress wavefronts per cycle per SM) of a bare tcgen05.mma loop."""
+    t = C.c_double(); cyc = C.c_double(); wf = C.c_double()
+    check(lib().pbso_measure_tc_peak(kind, cta_group, n, stress, C.byref(t), C.byref(cyc), C.byref(wf)))
+    return t.value, cyc.value, wf.value
+
+
+def tc_selftest(kind):
+    e = C.c_double()
+    check(lib().pbso_tc_selftest(kind, C.byref(e)))
+    return e.value
+
+
 def measure_copy_bw(nbytes):
     g = C.c_double()
     check(lib().pbso_measure_copy_bw(nbytes, C.byref(g)))

@@ -60,12 +60,6 @@ constexpr int TCB_FLUSH_UNITS = 4;         // units between FP64 flushes of the 
 
 struct Unit { int it, obj, ev, pad; };     // ev < 0: carry unit (state from Vbase); else impulse index
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
 struct Cplx { double x, y; };
 __device__ __forceinline__ Cplx cmul(const Cplx a, const Cplx b) {
     Cplx r;
@@ -225,19 +219,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 32 lanes x 32 consecutive TMEM columns <- 32 registers per thread (thread = lane of the warp's quarter)
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
-          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
-          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -264,7 +245,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1)
 k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_first, const Unit* __restrict__ units,
            const float2* __restrict__ tabA, const float2* __restrict__ tabB, const float2* __restrict__ Vbase,
            const double* __restrict__ c3a, const double* __restrict__ cota, const int* __restrict__ ev_row,
-           const double* __restrict__ ev_space, double* __restrict__ mix, int flush_units) {
+           const double* __restrict__ ev_space, double* __restrict__ mix, int flush_units, int ablate) {
     static_assert(TCB_SMALL_CHAIN % CHAIN == 0, "small chains end on main chain ends");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -333,6 +314,7 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                 mbar_wait(&b_full[sb], phb);
                 tcgen05_fence_after();
                 if (elect_one()) {
+                    if (!(ablate & 8)) {
                     const uint32_t acc_main = tmem_base + buf * TCB_L, acc_small = tmem_base + 256;
                     const uint32_t a_hi = tmem_base + 384 + sa * 64, a_lo = a_hi + 32;
                     const uint64_t dB = desc0 + (uint64_t)(sb * (TCB_BSTAGE_BYTES >> 4));
@@ -342,6 +324,7 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                         umma_tf32_ts(acc_main, a_hi + 8 * k, dBh, idesc, (chain_start && k == 0) ? 0u : 1u);
                         umma_tf32_ts(acc_small, a_hi + 8 * k, dBl, idesc, (small_start && k == 0) ? 0u : 1u);
                         umma_tf32_ts(acc_small, a_lo + 8 * k, dBh, idesc, 1u);
+                    }
                     }
                     umma_commit(&a_empty[sa]);
                     umma_commit(&b_empty[sb]);
@@ -463,6 +446,7 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                     const int buf = g & 1;
                     mbar_wait(&acc_full[buf], (g >> 1) & 1);
                     tcgen05_fence_after();
+                    if (!(ablate & 4))
 #pragma unroll
                     for (int qd = 0; qd < TCB_L / 32; ++qd) {
                         uint32_t vm[32];
@@ -478,6 +462,7 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
                 if (small_end) {
                     mbar_wait(small_full, gs & 1);
                     tcgen05_fence_after();
+                    if (!(ablate & 4))
 #pragma unroll
                     for (int qd = 0; qd < TCB_L / 32; ++qd) {
                         uint32_t vs[32];
@@ -523,6 +508,10 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
             const uint32_t sX = smem_u32(seeds) + slot * TCB_SEED_BYTES + blk * 8;
             const uint32_t sR = smem_u32(seeds) + slot * TCB_SEED_BYTES + TCB_KMODES * 64 + (jj < 0 ? 16 : jj) * 8;
             uint32_t hi[32], lo[32];
+            if (ablate & 2) {
+#pragma unroll
+                for (int m = 0; m < 32; ++m) hi[m] = lo[m] = 0u;
+            } else
 #pragma unroll
             for (int m = 0; m < TCB_KMODES; ++m) {
                 const float2 x = lds_f2(sX + m * 64), r = lds_f2(sR + m * TCB_RROW);
@@ -535,9 +524,11 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
             mbar_wait(&a_empty[sa], ((q / TCB_ASTAGES) & 1) ^ 1);
             tcgen05_fence_after();
             const uint32_t a_col = tmem_base + lane_off + 384 + sa * 64;
+            if (!(ablate & 2)) {
             tmem_st_32x32(a_col, hi);
             tmem_st_32x32(a_col + 32, lo);
             tmem_st_wait();
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[sa]);
@@ -555,7 +546,7 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
             const c32 rc[3] = {pk2(lds_f2(tB + 128 * 11)), pk2(lds_f2(tB + 128 * 12)), pk2(lds_f2(tB + 128 * 13))};
             mbar_wait(&b_empty[sb], ((q / TCB_BSTAGES) & 1) ^ 1);
             const uint32_t st = smem_u32(smem) + sb * TCB_BSTAGE_BYTES;
-            gen_block<SPLIT>(st, st + TCB_TILE_BYTES, blk, m_l, ra, rt, rc);
+            if (!(ablate & 1)) gen_block<SPLIT>(st, st + TCB_TILE_BYTES, blk, m_l, ra, rt, rc);
             fence_proxy_async_smem();
             __syncwarp();
             // the table slot is released only here: the loads above are certainly complete once their values have
@@ -682,6 +673,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     static const int split = getenv("PBSO_TC_SPLIT") ? atoi(getenv("PBSO_TC_SPLIT")) : 1;
     static const int chain = getenv("PBSO_TC_CHAIN") ? atoi(getenv("PBSO_TC_CHAIN")) : 2;
     static const int flush_units = getenv("PBSO_TC_FLUSH") ? atoi(getenv("PBSO_TC_FLUSH")) : TCB_FLUSH_UNITS;
+    static const int ablate = getenv("PBSO_TC_ABLATE") ? atoi(getenv("PBSO_TC_ABLATE")) : 0;
     const int grid = st->grid;
 #define PBSO_TC_LAUNCH(S, C)                                                                                         \
     do {                                                                                                             \
@@ -689,7 +681,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
         int dev_ = 0; cudaGetDevice(&dev_);                                                                          \
         if (!attr[dev_ & 63]) { PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_TS)); attr[dev_ & 63] = true; } \
         k_batch_tc<S, C><<<grid, TCB_THREADS, TCB_SMEM_TS, a.stream>>>(a.n_obj, a.n_modes, n_tiles, st->cta_first, st->units, st->tabA, \
-            st->tabB, st->Vbase, a.c3, a.cot, st->ev_row, a.d_ev_space, a.d_mix, flush_units);                     \
+            st->tabB, st->Vbase, a.c3, a.cot, st->ev_row, a.d_ev_space, a.d_mix, flush_units, ablate);                     \
     } while (0)
     if (split == 0 && chain == 2) PBSO_TC_LAUNCH(0, 2);
     else if (split == 2 && chain == 2) PBSO_TC_LAUNCH(2, 2);

@@ -72,17 +72,18 @@ k_ffat_eval_general(int n_modes, int L, const double* __restrict__ geom, const i
                     const double* __restrict__ psi, const size_t* __restrict__ psi_off,
                     const double* __restrict__ pos, double* __restrict__ out) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y;
     if (m >= n_modes) return;
     Geo g; load_geo(g, geom + (size_t)m * 32, igeom + (size_t)m * 18);
-    const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
-    int idx[4]; double w[4], r;
-    ffat_locate(g, p, idx, w, r);
     const double* P = psi + psi_off[m];
-    double psi0 = 0.0;
+    for (int l = blockIdx.y; l < L; l += gridDim.y) {                       // gridDim.y is capped at 65535
+        const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
+        int idx[4]; double w[4], r;
+        ffat_locate(g, p, idx, w, r);
+        double psi0 = 0.0;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) psi0 += w[kk] * P[idx[kk]];          // :1198-1204
-    out[(size_t)l * n_modes + m] = fabs(psi0 / (g.k * r));              // :904-905 + :295 std::abs
+        for (int kk = 0; kk < 4; ++kk) psi0 += w[kk] * P[idx[kk]];          // :1198-1204
+        out[(size_t)l * n_modes + m] = fabs(psi0 / (g.k * r));              // :904-905 + :295 std::abs
+    }
 }
 
 // Shared-geometry path, two launches.
@@ -671,7 +672,7 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
                                                                                      f->n_dense, (const FfatLoc*)f->d_loc, d_out);
         }
     } else {
-        dim3 grid(div_up(n_modes, 128), L);
+        dim3 grid(div_up(n_modes, 128), std::min(L, 65535));
         k_ffat_eval_general<<<grid, 128, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_psi_mm, f->d_psi_off, d_pos, d_out);
     }
     PBSO_CUDA(cudaGetLastError());

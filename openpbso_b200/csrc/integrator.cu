@@ -385,7 +385,9 @@ int pbso_integrator_set_transfer(pbso_integrator* it, const double* transfer, in
     PBSO_CUDA(cudaStreamSynchronize(it->stream));
     const size_t need = (size_t)L * n_transfer;
     if (need > (size_t)it->Lcap) {
-        cudaFree(it->d_trans); cudaFree(it->d_pos); cudaFree(it->d_acc); cudaFree(it->d_cnt);
+        // only the table grows here: d_pos / d_acc / d_cnt keep their own capacities (launch_render and
+        // set_transfer_ffat re-size them when they need to)
+        cudaFree(it->d_trans); it->d_trans = nullptr; it->Lcap = 0;
         PBSO_CUDA(cudaMalloc(&it->d_trans, sizeof(double) * need));
         it->Lcap = (int)need;
     }

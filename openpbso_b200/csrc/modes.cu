@@ -12,6 +12,7 @@
 // gather touches one 32-byte sector per (mode, vertex).
 // =============================================================================
 #include "common.cuh"
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <vector>
@@ -46,22 +47,23 @@ __global__ void __launch_bounds__(128)
 k_project_sparse(int M, int K, int B, int nv, const double* __restrict__ U, const int* __restrict__ vids,
                  const double* __restrict__ coords, const double* __restrict__ vn, double* __restrict__ out) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
     if (m >= M) return;
-    const double n0 = vn[3 * b], n1 = vn[3 * b + 1], n2 = vn[3 * b + 2];
     const double* mode = U + (size_t)m * K;
-    double acc = 0.0;
-    if (nv == 1) {
-        const int v = vids[b];
-        acc = n0 * mode[v * 3 + 0] + n1 * mode[v * 3 + 1] + n2 * mode[v * 3 + 2];
-    } else {
-        for (int j = 0; j < nv; ++j) {
-            const int v = vids[b * nv + j];
-            const double cj = coords[b * nv + j];
-            acc += n0 * mode[v * 3 + 0] * cj + n1 * mode[v * 3 + 1] * cj + n2 * mode[v * 3 + 2] * cj;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {      // gridDim.y is capped at 65535: stride over the batch
+        const double n0 = vn[3 * b], n1 = vn[3 * b + 1], n2 = vn[3 * b + 2];
+        double acc = 0.0;
+        if (nv == 1) {
+            const int v = vids[b];
+            acc = n0 * mode[v * 3 + 0] + n1 * mode[v * 3 + 1] + n2 * mode[v * 3 + 2];
+        } else {
+            for (int j = 0; j < nv; ++j) {
+                const int v = vids[(size_t)b * nv + j];
+                const double cj = coords[(size_t)b * nv + j];
+                acc += n0 * mode[v * 3 + 0] * cj + n1 * mode[v * 3 + 1] * cj + n2 * mode[v * 3 + 2] * cj;
+            }
         }
+        out[(size_t)b * M + m] = acc;
     }
-    out[(size_t)b * M + m] = acc;
 }
 
 // One block per mode row; 16-byte loads; FP64 accumulate; block reduce.
@@ -164,7 +166,7 @@ static int project_sparse(pbso_modes* md, int force_dim, int B, int nv, const in
     PBSO_CUDA(cudaMemcpyAsync(s, vids, nb_v, cudaMemcpyHostToDevice, md->stream));
     if (coords) PBSO_CUDA(cudaMemcpyAsync(s + off_c, coords, nb_c, cudaMemcpyHostToDevice, md->stream));
     PBSO_CUDA(cudaMemcpyAsync(s + off_n, vn, nb_n, cudaMemcpyHostToDevice, md->stream));
-    k_project_sparse<<<dim3(div_up(force_dim, 128), B), 128, 0, md->stream>>>(
+    k_project_sparse<<<dim3(div_up(force_dim, 128), std::min(B, 65535)), 128, 0, md->stream>>>(
         force_dim, md->K, B, nv, md->d_U, (const int*)s, (const double*)(s + off_c), (const double*)(s + off_n),
         (double*)(s + off_o));
     PBSO_CUDA(cudaGetLastError());

@@ -213,6 +213,37 @@ def test_moving_listeners_transfer_stays_on_device(pbso, orc):
     assert e.value.code == 5
 
 
+def test_transfer_table_grows_after_a_render(pbso, orc):
+    """Regression: growing the transfer table after a render with N > 256 (cross-slab scratch allocated), and
+    alternating set_transfer_ffat / set_transfer, must leave the renderer's scratch buffers alone."""
+    N, T = 600, 256
+    f = synth.mode_frequencies(N, 77); a, b = synth.ab_from_material(f, synth.MATERIALS["low_damping"])
+    maps = synth.ffat_maps(f, 2000, n=8)
+    fm = pbso.FFATMaps.from_dicts(maps)
+    it = pbso.ModalIntegrator(N, H, a, b); ref = orc.Integrator(H, a, b)
+    rng = np.random.default_rng(77)
+    pos = synth.listeners(40, 5)
+
+    def check(tr, rep):
+        sp = rng.standard_normal(N); tm = np.zeros(T); tm[0] = 1.0
+        y, _ = it.render_buffer(sp, tm)
+        q = np.array([ref.step(sp * tm[i]) for i in range(T)])
+        yr = (q[:, :tr.shape[1]] @ tr.T).T
+        assert y.shape == yr.shape, rep
+        assert np.max(np.abs(y - yr)) <= 1e-9 * np.max(np.abs(yr)), rep
+
+    tr1 = np.abs(rng.standard_normal((1, N))) + 0.1
+    it.set_transfer(tr1, 1); check(tr1, "L=1")
+    tr9 = np.abs(rng.standard_normal((9, N))) + 0.1
+    it.set_transfer(tr9, 9); check(tr9, "grown to L=9 after a render")
+    it.set_transfer_ffat(fm, pos[:3]); check(orc.ffat_eval(maps, pos[:3]), "ffat L=3")
+    tr40 = np.abs(rng.standard_normal((40, N))) + 0.1
+    it.set_transfer(tr40, 40); check(tr40, "grown to L=40 after set_transfer_ffat")
+    it.set_transfer_ffat(fm, pos); check(orc.ffat_eval(maps, pos), "ffat L=40")
+    it.set_transfer(tr9, 9); check(tr9, "shrunk to L=9")
+    it.close()
+
+
 # --------------------------------------------------------------------------- K3 FFAT
 def test_ffat_shared_geometry(pbso, orc):
     freqs = synth.mode_frequencies(200, 1004)
