@@ -228,6 +228,9 @@ int pbso_batch_sync(pbso_batch* bt);
 /* Run this handle's work on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the
  * handle's own stream) so that renders order with the caller's copies / NCCL calls without host syncs. */
 int pbso_batch_set_stream(pbso_batch* bt, void* cuda_stream);
+/* Accumulate-truncation gain of the tensor-core path on the current device, measured by the one-time self-calibration
+ * that the first PBSO_PREC_TC3X render runs (a synthetic batch against the FP64 kernel); 0 before that. */
+int pbso_tc_gain(double* gain);
 /* CUDA-event time of the last render kernel(s) on the handle's stream, and launches issued. */
 int pbso_batch_last_kernel_ms(pbso_batch* bt, float* ms, int* launches);
 

@@ -103,6 +103,7 @@ def lib():
             "pbso_measure_fma_peak": [C.c_int, c_dp, c_dp],
             "pbso_measure_tc_peak": [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp],
             "pbso_tc_selftest": [C.c_int, c_dp],
+            "pbso_tc_gain": [c_dp],
             "pbso_measure_copy_bw": [C.c_size_t, c_dp],
             "pbso_flush_l2": [C.c_size_t],
         }

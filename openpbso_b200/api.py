@@ -34,6 +34,12 @@ def measure_tc_peak(kind, cta_group=1, n=128, stress=0):
     return t.value, cyc.value, wf.value
 
 
+def tc_gain():
+    g = C.c_double()
+    check(lib().pbso_tc_gain(C.byref(g)))
+    return g.value
+
+
 def tc_selftest(kind):
     e = C.c_double()
     check(lib().pbso_tc_selftest(kind, C.byref(e)))

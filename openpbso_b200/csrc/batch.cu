@@ -688,6 +688,13 @@ int pbso_batch_set_stream(pbso_batch* bt, void* cuda_stream) {
     return PBSO_OK;
 }
 
+int pbso_tc_gain(double* gain) {
+    PBSO_REQUIRE(gain, PBSO_ERR_INVALID, "null output");
+    int dev = 0; PBSO_CUDA(cudaGetDevice(&dev));
+    *gain = tc_gain(dev);
+    return PBSO_OK;
+}
+
 int pbso_batch_last_kernel_ms(pbso_batch* bt, float* ms, int* launches) {
     PBSO_REQUIRE(bt && ms, PBSO_ERR_INVALID, "null argument");
     DeviceGuard g(bt->device);

@@ -6,41 +6,45 @@
 //     q_m[(i L) + j] = Re v_m(i) * Im(w_m^j) + Im v_m(i) * Re(w_m^j),      v_m(i) = state at the start of tile i
 // summed over modes with the transfer T_m (modal_solver.h:267-269) and over objects is ONE matrix product
 //     Y[i][j] = sum_k A[i][k] B[j][k],    k = (object, mode, component),
-//     A[i][(o,m,0..1)] = (Re, Im) v_{o,m}(i)          -- tile-start states  ("advance each mode with z^k")
-//     B[j][(o,m,0..1)] = T_{o,m} (Im, Re) w_{o,m}^j   -- precomputed pole powers
+//     A[i][(o,m,0..1)] = T_{o,m} (Re, Im) v_{o,m}(i)   -- tile-start states  ("advance each mode with z^k")
+//     B[j][(o,m,0..1)] = (Im, Re) w_{o,m}^j            -- pole powers
 // with i = tile index in time (L = 128 samples per tile), j = offset inside the tile.  For cfg5 that is a
-// [3446 x 128] output contracted over K = 4096*512*2 = 4.2 M.  Neither operand ever exists in HBM: both are
-// generated on the SM, straight into the UMMA shared-memory layout, and consumed by tcgen05.mma kind::tf32 with
-// accumulators in TMEM.  Generation is FP32 (packed fma.rn.f32x2 complex products) from three-level tables of
-// pole powers, row r = 16 blk + 4 t + c:  A[r] = v_base * W^(16 blk) * W^(4t) * W^c  with the table factors
-// computed in FP64 and rounded once (k_tc_tables), and v_base from the FP64 carrier pass (k_tc_carrier).  The
-// FP64 and F2F pipes are far too narrow to generate operands at tensor-core speed (first version: 3.9 k
-// cycles per K chunk against 768 of MMA time), FP32 products of exactly-rounded factors hold ~1.5e-7.
+// [3446 x 128] output contracted over K = 4096*512*2 = 4.2 M, run by tcgen05.mma kind::tf32 with accumulators in
+// TMEM.
 //
-// Precision ("3xTF32"): every FP32 element x is split x = hi + lo (hi = x truncated to TF32 -- the tensor core
-// ignores the low 13 mantissa bits itself, so the raw x is stored as the hi operand -- and lo = x - hi rounded to
-// nearest TF32), and three MMAs form hi*hi + hi*lo + lo*hi.  hi*hi goes to a "main" TMEM accumulator, the two
-// small products to a separate "small" accumulator: the tensor core truncates when it adds into the FP32
-// accumulator (~2.5e-8 relative per accumulating MMA, a coherent gain error), so main chains are kept to
-// CHAIN*4 MMAs and promoted into FP32 registers with round-to-nearest adds (two-level accumulation); the
-// registers are added to the FP64 mix every TCB_FLUSH_UNITS units (a longer FP32 running sum would lose
-// 2.4e-8 sqrt(adds)), with the known mean truncation bias compensated at that point.
+// Round-2 structure (profiles/r2_k_batch_tc_ablation.md: round 1 was latency-bound on its own five-role pipeline):
+//  * Operand B depends on the object only, not on time or on the impulse script: it is PRECOMPUTED once per
+//    handle (k_tc_btiles: FP64 pole powers, split into TF32 hi / lo, stored as ready-made UMMA tiles -- K-major,
+//    128-byte swizzle) and streamed into shared memory with bulk copies.  A CTA PAIR (cluster of 2) renders two
+//    M-tiles (128 time tiles each) of the SAME object and shares the stream: each CTA fetches half of every
+//    32 KB tile pair and multicasts it to both (cp.async.bulk ... .multicast::cluster), so L2 -> SM traffic is
+//    16 KB per 16-mode K chunk and CTA.  Work items are (window of 8 objects, M-tile pair), dealt round-robin to
+//    the clusters, so the 14 clusters rendering the 14 M-tile pairs of one object window read the same tiles
+//    at about the same time: HBM sees every tile about once per render (4.3 GB for cfg5), L2 serves the rest.
+//  * Operand A (tile-start states) is generated on the SM straight into TMEM (tcgen05.st, MMA in TS mode):
+//    A[row] = X[blk] * R[j] (row = 16 blk + j), X[blk] = v W^(16 blk) from a seed warp, R[j] = W^j, W = w^L, all
+//    FP32 complex products (fma.rn.f32x2) of table factors computed in FP64 and rounded once (k_tc_tabs); v comes
+//    from the FP64 carrier pass (k_tc_carrier, per render; impulses injected in FP64, transfer folded in).
+//    Everything a chunk needs -- 3 KB of table, 128 B of states -- rides the same bulk-copy ring as B: no role
+//    ever waits on a global load.
+//  * "3xTF32": every FP32 element x is split x = hi + lo (the tensor core ignores the low 13 mantissa bits itself,
+//    so the raw x is the hi operand; lo = x - trunc(x) rounded to nearest TF32); hi*lo + lo*hi + hi*hi.  The tensor
+//    core truncates when it adds into its FP32 accumulator, so accumulation is two-level: chains of two K chunks
+//    (16 small MMAs first -- their truncation is relative to a 2^-11 smaller sum -- then the 8 hi*hi MMAs on top,
+//    ONE accumulator) are promoted into FP32 registers with round-to-nearest packed adds, and the registers are
+//    added to the FP64 mix (RED.64) every few units.  The remaining mean truncation of a chain (a coherent gain
+//    error of ~2e-7) is measured once per device by tc_calibrate() -- the same kernel on a synthetic batch against
+//    the FP64 direct-form kernel -- and divided out at the flush.
 //
-// Work decomposition.  M-tile = 128 consecutive time tiles (16 384 samples).  A unit is (M-tile, object) --
-// the object's state at the M-tile start comes from the FP64 carrier pass k_tc_carrier -- or (M-tile, object,
-// impulse) for an impulse landing inside the M-tile (rows before it are zero; linear superposition).  Units
-// are sorted by M-tile and split evenly over one persistent CTA per SM; a CTA keeps its [128 x 128] partial
-// mix in registers across units and adds it to the FP64 mix (RED.64) only when the M-tile changes.
-//
-// CTA = 16 warps: warp 0 issues the MMAs; warps 4-7 drain TMEM (epilogue); warps 8-11 generate A, warps 12-15
-// generate B (thread = (mode of the 16-mode K chunk, 16-row block)); setmaxnreg moves registers from the idle
-// warps to the epilogue.  Stage = K chunk of 16 modes: A_hi A_lo B_hi B_lo, [128 rows][32 fp32] each, 128-byte
-// swizzle, K-major (64 KB; 3 stages).
+// CTA = 16 warps: warp 0 issues the MMAs, warp 1 lane 0 is the loader, warps 2-3 compute seeds (alternating
+// chunks), warps 4-7 drain TMEM (epilogue), warps 8-11 / 12-15 generate A for even / odd chunks.
+// TMEM (512 columns): accumulators 0..127 | 128..255, four A stages of 64 columns (hi 32 | lo 32) at 256.
 // =============================================================================
 #include "common.cuh"
 #include "umma.cuh"
 #include "batch_tc.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -54,11 +58,31 @@ constexpr int TCB_L = 128;                 // samples per tile = N of the MMA
 constexpr int TCB_ROWS = 128;              // tiles per M-tile = M of the MMA
 constexpr int TCB_KMODES = 16;             // modes per K chunk (K = 32 fp32 = one 128-byte swizzle row)
 constexpr int TCB_TILE_BYTES = 128 * 32 * 4;
+constexpr int TCB_BT_BYTES = 2 * TCB_TILE_BYTES;        // one chunk of operand B in shared memory: hi tile | lo tile
 constexpr int TCB_THREADS = 512;
-constexpr int TCB_TMEM_COLS = 512;         // main[2] | small[2], 128 columns each
-constexpr int TCB_FLUSH_UNITS = 4;         // units between FP64 flushes of the register accumulators
+constexpr int TCB_TMEM_COLS = 512;
+constexpr int TCB_NB = 4;                  // B stages
+constexpr int TCB_NA = 4;                  // A stages in TMEM
+constexpr int TCB_NT = 6;                  // table slots (requested well ahead: the copy latency is what the ring hides)
+constexpr int TCB_NS = 4;                  // seed slots
+constexpr int TCB_RSTRIDE = 144;                        // bytes between the R rows of a table block (128 + 16: 16 rows spread over all banks)
+constexpr int TCB_TABG_BYTES = 1024 + 17 * TCB_RSTRIDE + 2048;   // per chunk in HBM: P[8 blk][16 m] | R[16 j + a zero row][16 m (+pad)] | tabB[16 entries][16 m], float2
+constexpr int TCB_TAB_R = 1024, TCB_TAB_B = 1024 + 17 * TCB_RSTRIDE;
+constexpr int TCB_TAB_BYTES = TCB_TABG_BYTES + 128;     // + the chunk's 16 tile-start states
+constexpr int TCB_SEED_BYTES = 1024;                    // X[8 blk][16 m] float2: v W^(16 blk)
+constexpr int TCB_SMEM = TCB_NB * TCB_BT_BYTES + TCB_NT * TCB_TAB_BYTES + TCB_NS * TCB_SEED_BYTES + 512 + 1024;
+constexpr int TCB_WINDOW = 8;              // objects per work item
+constexpr int TCB_FLUSH_UNITS = 8;         // units between FP64 flushes of the register accumulators
+static_assert(TCB_SMEM <= 232448, "shared memory budget");
+static_assert(TCB_NA == TCB_NB, "A and B stages share their full / empty barriers");
 
-struct Unit { int it, obj, ev, pad; };     // ev < 0: carry unit (state from Vbase); else impulse index
+// One unit of work of a CTA: object `obj` over M-tile `it` (128 time tiles), from the state block `src` (tile-start
+// states of a carry unit, or the injected state of an impulse unit landing on row `re` of the M-tile).
+struct Unit {
+    int obj, it;
+    unsigned src;          // block index into the state buffer (blocks of mp float2)
+    short re, flush;       // re: impulse row inside the M-tile, -1 for a carry unit; flush: add the register accumulators to the mix after it
+};
 
 struct Cplx { double x, y; };
 __device__ __forceinline__ Cplx cmul(const Cplx a, const Cplx b) {
@@ -67,218 +91,168 @@ __device__ __forceinline__ Cplx cmul(const Cplx a, const Cplx b) {
     r.y = fma(a.x, b.y, a.y * b.x);
     return r;
 }
-
-// ---- static per-(object, mode) tables of pole powers, FP64-computed, rounded once to FP32 --------------------
-// tab[i][0..7] = P^(16 blk) (x T for operand B), [8..10] = P^4, P^8, P^12, [11..13] = P, P^2, P^3 with
-// P = w^L (operand A: tile-to-tile) or w (operand B: sample-to-sample).  Operand B holds (Im, Re) = i conj(z) in
-// its K columns; i conj(z1 z2) = (i conj z1) conj(z2), so tabB stores the block starts swapped and the step
-// powers conjugated and the generator runs the same recurrence for both operands.
-__device__ __forceinline__ float2 pole_pow(double le, double th, double k, double scale) {
+__device__ __forceinline__ Cplx pole_pow64(double le, double th, double k) {
     double s, c;
     sincos(k * th, &s, &c);
-    const double e = scale * exp(k * le);
-    return make_float2((float)(e * c), (float)(e * s));
+    const double e = exp(k * le);
+    return Cplx{e * c, e * s};
 }
-// Layout: [object][K chunk][entry 0..15][mode within the chunk 0..15] float2 -- one 2 KB block per K chunk, which
-// the kernel's loader thread brings into shared memory with a single bulk copy; entry-major so that the 16 lanes
-// of a half-warp (= 16 modes) read 128 consecutive bytes.  Modes past n_modes are zero.
-__global__ void k_tc_tables(int n_obj, int n_modes, int cpu, const double* __restrict__ lneps, const double* __restrict__ theta,
-                            const double* __restrict__ trans, float2* __restrict__ tabA, float2* __restrict__ tabB) {
+
+// byte offset of (row r, K-columns 2m..2m+1) inside a K-major SWIZZLE_128B tile with 128-byte rows
+__host__ __device__ __forceinline__ uint32_t sw128_pair(int r, int m) {
+    return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((m >> 1) ^ (r & 7)) << 4) + (uint32_t)(m & 1) * 8u;
+}
+__device__ __forceinline__ float tf32_rn(float x) {                   // round to nearest TF32 (10 explicit mantissa bits)
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+// ---- operand tables, once per handle (they depend on the poles only) -------------------------------------------
+// tab[(o * cpu + ch)]: 5.4 KB = P[8 blk][16 m] | R[16 j + zero row][16 m + pad] | tabB[16 entries][16 m], float2.
+//   operand A:  P[blk] = W^(16 blk), R[j] = W^j with W = w^L (tile to tile)
+//   operand B:  rows hold (Im, Re) w^j = i conj(w^j); i conj(z1 z2) = (i conj z1) conj(z2), so entries 0..7 are the
+//               16-row block starts i conj(w^(16 a)) and entries 8..10 / 11..13 the conjugated steps conj(w^(4 t)),
+//               conj(w^t), t = 1..3: the generator runs plain complex products.
+// Modes past n_modes are zero.
+__global__ void k_tc_tabs(int n_obj, int n_modes, int cpu, int obj0, const double* __restrict__ lneps, const double* __restrict__ theta,
+                          uint8_t* __restrict__ tab) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;       // (object, padded mode)
     const size_t n = (size_t)n_obj * cpu * TCB_KMODES;
     if (i >= n) return;
     const int o = (int)(i / ((size_t)cpu * TCB_KMODES)), mp = (int)(i % ((size_t)cpu * TCB_KMODES));
-    float2* ta = tabA + ((size_t)o * cpu + mp / TCB_KMODES) * 256 + (mp % TCB_KMODES);
-    float2* tb = tabB + ((size_t)o * cpu + mp / TCB_KMODES) * 256 + (mp % TCB_KMODES);
+    const int m_l = mp % TCB_KMODES;
+    uint8_t* blk = tab + ((size_t)o * cpu + mp / TCB_KMODES) * TCB_TABG_BYTES;
+    float2* P = reinterpret_cast<float2*>(blk) + m_l;                     // entry b at P[16 b]
+    uint8_t* Rb = blk + TCB_TAB_R + m_l * 8;                              // entry j at Rb + j * TCB_RSTRIDE
+    float2* TB = reinterpret_cast<float2*>(blk + TCB_TAB_B) + m_l;        // entry e at TB[16 e]
+    *reinterpret_cast<float2*>(Rb + 16 * TCB_RSTRIDE) = make_float2(0.f, 0.f);   // row 16 = 0: rows before an impulse
+    if (m_l == 0)                                                          // the pad column of every R row
+        for (int j = 0; j < 17; ++j) { float2* pad = reinterpret_cast<float2*>(blk + TCB_TAB_R + j * TCB_RSTRIDE + 128); pad[0] = pad[1] = make_float2(0.f, 0.f); }
     if (mp >= n_modes) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) ta[e * 16] = tb[e * 16] = make_float2(0.f, 0.f);
+        for (int b = 0; b < 8; ++b) P[16 * b] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { *reinterpret_cast<float2*>(Rb + j * TCB_RSTRIDE) = make_float2(0.f, 0.f); TB[16 * j] = make_float2(0.f, 0.f); }
         return;
     }
-    const size_t src = (size_t)o * n_modes + mp;
-    const double le = lneps[src], th = theta[src], T = trans[src];
+    const size_t src = (size_t)(obj0 + o) * n_modes + mp;
+    const double le = lneps[src], th = theta[src];
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        ta[a * 16] = pole_pow(le, th, 16.0 * a * TCB_L, 1.0);
-        { const float2 z = pole_pow(le, th, 16.0 * a, T); tb[a * 16] = make_float2(z.y, z.x); }
-    }
+    for (int b = 0; b < 8; ++b) { const Cplx z = pole_pow64(le, th, 16.0 * b * TCB_L); P[16 * b] = make_float2((float)z.x, (float)z.y); }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const Cplx z = pole_pow64(le, th, (double)j * TCB_L); *reinterpret_cast<float2*>(Rb + j * TCB_RSTRIDE) = make_float2((float)z.x, (float)z.y); }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) { const Cplx z = pole_pow64(le, th, 16.0 * a); TB[16 * a] = make_float2((float)z.y, (float)z.x); }
 #pragma unroll
     for (int t = 1; t < 4; ++t) {
-        ta[(7 + t) * 16] = pole_pow(le, th, 4.0 * t * TCB_L, 1.0);
-        ta[(10 + t) * 16] = pole_pow(le, th, (double)t * TCB_L, 1.0);
-        { const float2 z = pole_pow(le, th, 4.0 * t, 1.0); tb[(7 + t) * 16] = make_float2(z.x, -z.y); }
-        { const float2 z = pole_pow(le, th, (double)t, 1.0); tb[(10 + t) * 16] = make_float2(z.x, -z.y); }
+        { const Cplx z = pole_pow64(le, th, 4.0 * t); TB[16 * (7 + t)] = make_float2((float)z.x, (float)-z.y); }
+        { const Cplx z = pole_pow64(le, th, (double)t); TB[16 * (10 + t)] = make_float2((float)z.x, (float)-z.y); }
     }
-    ta[14 * 16] = ta[15 * 16] = tb[14 * 16] = tb[15 * 16] = make_float2(0.f, 0.f);
+    TB[16 * 14] = TB[16 * 15] = make_float2(0.f, 0.f);
 }
 
-// ---- FP64 carrier: state of every (object, mode) at the start of every M-tile -------------------------------
-// Vbase[it] excludes impulses landing at rows >= it*128 (those are impulse units of M-tile it).
-__global__ void k_tc_carrier(int n_obj, int n_modes, int n_it, int tiles_per_buf_num, int tiles_per_buf_den,
+// ---- FP64 carrier: T * state of every (object, mode) at the start of every M-tile -----------------------------
+// V[it] excludes impulses landing at rows >= it*128 (those are impulse units of M-tile it).  Layout: blocks of mp
+// float2 (mp = modes padded to whole chunks; pad entries stay zero), block it * n_obj + o.
+__global__ void k_tc_carrier(int n_obj, int n_modes, int n_it, int tiles_per_buf, int mp, int obj0,
                              const double* __restrict__ lneps, const double* __restrict__ theta,
-                             const double* __restrict__ c3a, const double* __restrict__ cota,
+                             const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
                              const int* __restrict__ ev_off, const int* __restrict__ ev_buf,
-                             const double* __restrict__ ev_space, float2* __restrict__ Vbase) {
+                             const double* __restrict__ ev_space, float2* __restrict__ V) {
     const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const size_t npm = (size_t)n_obj * n_modes;
-    if (idx >= npm) return;
+    if (idx >= (size_t)n_obj * n_modes) return;
     const int o = (int)(idx / n_modes), m = (int)(idx % n_modes);
-    const double le = lneps[idx], th = theta[idx];
-    double s, c;
-    sincos((double)(TCB_L * TCB_ROWS) * th, &s, &c);
-    const double e128 = exp((double)(TCB_L * TCB_ROWS) * le);
-    const Cplx Wm{e128 * c, e128 * s};
-    const double inji = c3a[idx], injr = inji * cota[idx];
+    const size_t g = (size_t)(obj0 + o) * n_modes + m;
+    const double le = lneps[g], th = theta[g], T = trans[g];
+    const Cplx Wm = pole_pow64(le, th, (double)(TCB_L * TCB_ROWS));
+    const double inji = c3a[g], injr = inji * cota[g];
     Cplx v{0.0, 0.0};
-    int e = ev_off[o];
-    const int e_end = ev_off[o + 1];
+    int e = ev_off[obj0 + o];
+    const int e_end = ev_off[obj0 + o + 1];
     for (int it = 0; it < n_it; ++it) {
-        Vbase[(size_t)it * npm + idx] = make_float2((float)v.x, (float)v.y);
+        V[((size_t)it * n_obj + o) * mp + m] = make_float2((float)(T * v.x), (float)(T * v.y));
         v = cmul(v, Wm);
         const long long row_end = (long long)(it + 1) * TCB_ROWS;
         while (e < e_end) {
-            const long long row = (long long)ev_buf[e] * tiles_per_buf_num / tiles_per_buf_den;
+            const long long row = (long long)ev_buf[e] * tiles_per_buf;
             if (row >= row_end) break;
-            const double k = (double)(row_end - row) * TCB_L;               // samples from the impulse to the next M-tile start
+            const Cplx z = pole_pow64(le, th, (double)(row_end - row) * TCB_L);   // from the impulse to the next M-tile start
             const double sp = ev_space[(size_t)e * n_modes + m];
-            sincos(k * th, &s, &c);
-            const double ek = exp(k * le);
-            v.x += sp * (injr * (ek * c) - inji * (ek * s));
-            v.y += sp * (injr * (ek * s) + inji * (ek * c));
+            v.x += sp * (injr * z.x - inji * z.y);
+            v.y += sp * (injr * z.y + inji * z.x);
             ++e;
         }
     }
 }
-
-// ---- operand generation ------------------------------------------------------------------------------------
-// Complex numbers are (re, im) packed in one 64-bit register; products use mul/fma.rn.f32x2 (SASS FMUL2/FFMA2).
-typedef unsigned long long c32;                                          // packed (re, im)
-__device__ __forceinline__ c32 pk(float re, float im) { c32 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(re), "f"(im)); return r; }
-__device__ __forceinline__ void upk(c32 v, float& re, float& im) { asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(v)); }
-__device__ __forceinline__ c32 pk2(float2 v) { return pk(v.x, v.y); }
-// p * q = pr (qr, qi) + pi (-qi, qr): q is passed with its rotation qrot = i q = (-qi, qr) so that both packed
-// instructions take p's components as broadcast scalars (no register-pair shuffling in the inner loops).
-__device__ __forceinline__ c32 cmulf(c32 p, c32 q, c32 qrot) {
-    float pr, pi; upk(p, pr, pi);
-    const c32 pa = pk(pr, pr), pb = pk(pi, pi);
-    c32 r;
-    asm("{\n\t.reg .b64 t;\n\tmul.rn.f32x2 t, %1, %2;\n\tfma.rn.f32x2 %0, %3, %4, t;\n\t}" : "=l"(r) : "l"(pa), "l"(q), "l"(pb), "l"(qrot));
-    return r;
-}
-__device__ __forceinline__ c32 rot(c32 v) { float a, b; upk(v, a, b); return pk(-b, a); }
-
-template <int SPLIT>
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi_bits, uint32_t& lo_bits) {
-    const uint32_t xb = __float_as_uint(x);
-    if (SPLIT == 2) {                                                  // hi, lo both rounded to nearest
-        const uint32_t h = (xb + 0x1000u) & 0xFFFFE000u;
-        hi_bits = h;
-        lo_bits = __float_as_uint(x - __uint_as_float(h)) + 0x1000u;
-    } else {
-        const uint32_t h = xb & 0xFFFFE000u;                           // what the tensor core reads of x
-        hi_bits = xb;
-        const float l = x - __uint_as_float(h);
-        lo_bits = SPLIT == 1 ? __float_as_uint(l) + 0x1000u : __float_as_uint(l);   // +half ulp: truncation -> RN
-    }
-}
-__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-// row b of the thread's 16-row block, K columns (2 m_l, 2 m_l + 1):
-// byte offset (r/8)*1024 + (r%8)*128 + (((m_l/2) ^ (r%8)) * 16) + (m_l%2)*8 with r = 16 blk + b
-template <int SPLIT>
-__device__ __forceinline__ void store_row(uint32_t tile_hi, uint32_t tile_lo, uint32_t base, int b, c32 v) {
-    float re, im; upk(v, re, im);
-    uint32_t h0, l0, h1, l1;
-    split_tf32<SPLIT>(re, h0, l0);
-    split_tf32<SPLIT>(im, h1, l1);
-    const uint32_t off = (base ^ ((uint32_t)(b & 7) * 16u)) + (uint32_t)(b >> 3) * 1024u + (uint32_t)(b & 7) * 128u;
-    sts_v2(tile_hi + off, h0, h1);
-    sts_v2(tile_lo + off, l0, l1);
+// state injected by impulse e (forces.h:87, sample 0 of its buffer): T * space * c3 (cot theta + i); block vimp0 + e
+__global__ void k_tc_impulse(int n_modes, int mp, int e0, int n_ev, const int* __restrict__ ev_obj,
+                             const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
+                             const double* __restrict__ ev_space, float2* __restrict__ Vimp) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_ev * n_modes) return;
+    const int e = (int)(idx / n_modes), m = (int)(idx % n_modes);
+    const size_t g = (size_t)ev_obj[e0 + e] * n_modes + m;
+    const double sp = ev_space[(size_t)(e0 + e) * n_modes + m] * trans[g], inji = c3a[g];
+    Vimp[(size_t)e * mp + m] = make_float2((float)(sp * inji * cota[g]), (float)(sp * inji));
 }
 
-// Fast path: rows 4t + c = x * Rt[t] * Rc[c]  (Rt[0] = Rc[0] = 1).  t123 / c123 hold entries 8..13 of the table.
-template <int SPLIT>
-__device__ __forceinline__ void gen_block(uint32_t tile_hi, uint32_t tile_lo, int blk, int m_l, c32 x, const c32 (&rt)[3], const c32 (&rc)[3]) {
-    const uint32_t base = (uint32_t)blk * 2048u + (uint32_t)(m_l >> 1) * 16u + (uint32_t)(m_l & 1) * 8u;
-    const c32 rcs[3] = {rot(rc[0]), rot(rc[1]), rot(rc[2])};   // i rc
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const c32 pt = t == 0 ? x : cmulf(x, rt[t - 1], rot(rt[t - 1]));
-        store_row<SPLIT>(tile_hi, tile_lo, base, 4 * t, pt);
-#pragma unroll
-        for (int c = 1; c < 4; ++c) store_row<SPLIT>(tile_hi, tile_lo, base, 4 * t + c, cmulf(pt, rc[c - 1], rcs[c - 1]));
-    }
+// ---- device helpers of the main kernel ----------------------------------------------------------------------
+typedef unsigned long long c32;                                          // packed (re, im) or any f32x2
+__device__ __forceinline__ c32 pk(float a, float b) { c32 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(c32 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ c32 mul2(c32 a, c32 b) { c32 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ c32 fma2(c32 a, c32 b, c32 c) { c32 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ c32 add2(c32 a, c32 b) { c32 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ c32 sub2(c32 a, c32 b) { c32 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// complex product p * q in plain registers (seed warps: a few per chunk)
+__device__ __forceinline__ float2 cmulf(float2 p, float2 q) {
+    return make_float2(fmaf(-p.y, q.y, p.x * q.x), fmaf(p.x, q.y, p.y * q.x));
 }
-
-// A operand from TMEM, B from shared memory:  D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void lds_2x64(uint32_t addr, c32& a, c32& b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
-    float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr)); return v;
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// Shared-memory map of k_batch_tc: B stages (B_hi | B_lo, 16 KB each), seed ring, barriers.
-// TMEM map (512 columns): main[0] 0..127, main[1] 128..255, small 256..383, A stage s at 384 + 64 s (hi 32 | lo 32).
-constexpr int TCB_BSTAGES = 4, TCB_ASTAGES = 2, TCB_SEEDS = 4;
-constexpr int TCB_BSTAGE_BYTES = 2 * TCB_TILE_BYTES;
-constexpr int TCB_RROW = 18 * 8;                                      // R row: 16 powers, a zero entry, pad (16-byte aligned)
-constexpr int TCB_SEED_BYTES = TCB_KMODES * 64 + TCB_KMODES * TCB_RROW;   // X[16 modes][8 blk] then R[16 modes][18], float2
-constexpr int TCB_TABS = 6, TCB_TAB_BYTES = 2 * 2048;                 // table ring: tabA block | tabB block of a chunk
-constexpr int TCB_SMEM_TS = TCB_BSTAGES * TCB_BSTAGE_BYTES + TCB_SEEDS * TCB_SEED_BYTES + TCB_TABS * TCB_TAB_BYTES + 1024 + 512;
-constexpr int TCB_SMALL_CHAIN = 8;                                   // chunks per small-accumulator chain
-
-template <int SPLIT, int CHAIN>
+// =============================================================================================================
 __global__ void __launch_bounds__(TCB_THREADS, 1)
-k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_first, const Unit* __restrict__ units,
-           const float2* __restrict__ tabA, const float2* __restrict__ tabB, const float2* __restrict__ Vbase,
-           const double* __restrict__ c3a, const double* __restrict__ cota, const int* __restrict__ ev_row,
-           const double* __restrict__ ev_space, double* __restrict__ mix, int flush_units, int ablate) {
-    static_assert(TCB_SMALL_CHAIN % CHAIN == 0, "small chains end on main chain ends");
+k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Unit* __restrict__ units,
+           const uint8_t* __restrict__ tab, const float2* __restrict__ V, int obj0,
+           double* __restrict__ mix, double inv_gain, int ablate) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* seeds = smem + TCB_BSTAGES * TCB_BSTAGE_BYTES;
-    uint8_t* tabs = seeds + TCB_SEEDS * TCB_SEED_BYTES;
-    uint64_t* bars = (uint64_t*)(tabs + TCB_TABS * TCB_TAB_BYTES);
-    uint64_t* b_full = bars;                       // [4]  B stage written (4 generator warps)
-    uint64_t* b_empty = b_full + TCB_BSTAGES;      // [4]  MMAs reading it retired
-    uint64_t* a_full = b_empty + TCB_BSTAGES;      // [2]  A stage stored to TMEM (4 generator warps)
-    uint64_t* a_empty = a_full + TCB_ASTAGES;      // [2]
-    uint64_t* seed_full = a_empty + TCB_ASTAGES;   // [4]  seeds of a chunk written (1 seed warp)
-    uint64_t* seed_empty = seed_full + TCB_SEEDS;  // [4]  consumed (4 A-generator warps)
-    uint64_t* acc_full = seed_empty + TCB_SEEDS;   // [2]  main accumulator chain finished
-    uint64_t* acc_empty = acc_full + 2;            // [2]  drained (128 epilogue threads)
-    uint64_t* small_full = acc_empty + 2;          // [1]
-    uint64_t* small_empty = small_full + 1;        // [1]
-    uint64_t* tab_full = small_empty + 1;          // [6]  bulk copies of a chunk's table blocks landed (tx bytes)
-    uint64_t* tab_empty = tab_full + TCB_TABS;     // [6]  consumed (1 seed warp + 4 B-generator warps)
-    uint32_t* tmem_slot = (uint32_t*)(tab_empty + TCB_TABS);
+    uint8_t* tabs = smem + TCB_NB * TCB_BT_BYTES;
+    uint8_t* seeds = tabs + TCB_NT * TCB_TAB_BYTES;
+    uint64_t* bars = (uint64_t*)(seeds + TCB_NS * TCB_SEED_BYTES);
+    uint64_t* b_full = bars;                       // [NB] = [NA] operand stage written: A in TMEM + B in shared memory (4 + 4 generator warps)
+    uint64_t* b_empty = b_full + TCB_NB;           // [NB] MMAs reading the stage retired (A and B generators both wait on it)
+    uint64_t* t_full = b_empty + TCB_NB;           // [NT] table block + states landed (tx bytes)
+    uint64_t* t_empty = t_full + TCB_NT;           // [NT] consumed (seed warp + 4 A-generator + 4 B-generator warps)
+    uint64_t* s_full = t_empty + TCB_NT;           // [NS] seeds written (seed warp)
+    uint64_t* s_empty = s_full + TCB_NS;           // [NS] consumed (4 A-generator warps)
+    uint64_t* a_full = s_empty + TCB_NS;           // [NA] A stage stored to TMEM (4 generator warps)
+    uint64_t* a_empty = a_full + TCB_NA;           // [NA] MMAs reading it retired
+    uint64_t* acc_full = a_empty + TCB_NA;         // [2]  chunk's MMAs finished
+    uint64_t* acc_empty = acc_full + 2;            // [2]  drained (4 epilogue warps)
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // this CTA's contiguous range of units (sorted by M-tile; ranges of equal estimated cost, built on the host)
     const int u0 = cta_first[blockIdx.x], u1 = cta_first[blockIdx.x + 1];
     const int cpu = (n_modes + TCB_KMODES - 1) / TCB_KMODES;          // K chunks per unit
-    const size_t npm = (size_t)n_obj * n_modes;
+    const int mp = cpu * TCB_KMODES;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TCB_BSTAGES; ++s) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < TCB_ASTAGES; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < TCB_SEEDS; ++s) { mbar_init(&seed_full[s], 1); mbar_init(&seed_empty[s], 4); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
-        mbar_init(small_full, 1); mbar_init(small_empty, 128);
-        for (int s = 0; s < TCB_TABS; ++s) { mbar_init(&tab_full[s], 1); mbar_init(&tab_empty[s], 5); }
+        for (int s = 0; s < TCB_NB; ++s) { mbar_init(&b_full[s], 8); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < TCB_NT; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 9); }
+        for (int s = 0; s < TCB_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+        for (int s = 0; s < TCB_NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -289,164 +263,123 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t n_chunks_total = (uint32_t)(u1 - u0) * (uint32_t)cpu;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (warp == 0) {
             // ---------------- MMA issuer ----------------
-            // The whole warp runs the loop so that every operand stays warp-uniform (uniform registers feed
-            // UTCHMMA directly); one elected lane issues.  B descriptors differ only in their 14-bit address field:
-            // stage base + tile offset (16 KB -> +1024) + k step (32 B -> +2); A is a TMEM column address.
+            // The whole warp runs the loop so that every operand stays warp-uniform; one elected lane issues.
+            // Per K chunk: its 8 small products first (hi*lo, lo*hi), then the 4 hi*hi MMAs on top, one accumulator.
             constexpr uint32_t idesc = umma_idesc_tf32(TCB_ROWS, TCB_L);
             const uint64_t desc0 = umma_desc_k_sw128(smem_u32(smem));
-            uint32_t g = 0, gs = 0;                                    // main / small chain counters
-            int ch = 0;
-            for (uint32_t q = 0; q < n_chunks_total; ++q) {
-                const uint32_t sa = q % TCB_ASTAGES, pha = (q / TCB_ASTAGES) & 1;
-                const uint32_t sb = q % TCB_BSTAGES, phb = (q / TCB_BSTAGES) & 1;
-                const uint32_t buf = g & 1;
-                const bool chain_start = (ch % CHAIN) == 0, chain_end = (ch % CHAIN) == CHAIN - 1 || ch == cpu - 1;
-                const bool small_start = (ch % TCB_SMALL_CHAIN) == 0, small_end = (ch % TCB_SMALL_CHAIN) == TCB_SMALL_CHAIN - 1 || ch == cpu - 1;
-                if (chain_start) mbar_wait(&acc_empty[buf], ((g >> 1) & 1) ^ 1);
-                if (small_start) mbar_wait(small_empty, (gs & 1) ^ 1);
-                mbar_wait(&a_full[sa], pha);
-                mbar_wait(&b_full[sb], phb);
+            const uint32_t n_chunks = (uint32_t)(u1 - u0) * (uint32_t)cpu;
+#pragma unroll 1
+            for (uint32_t q = 0; q < n_chunks; ++q) {
+                const uint32_t buf = q & 1, sa = q % TCB_NA, sb = q % TCB_NB;
+                // the two waits of a chunk ride one instruction: even lanes probe the accumulator, odd lanes the operand stage
+                mbar_wait(lane & 1 ? &b_full[sb] : &acc_empty[buf], lane & 1 ? (q / TCB_NB) & 1 : ((q >> 1) & 1) ^ 1);
+                __syncwarp();
                 tcgen05_fence_after();
                 if (elect_one()) {
+                    const uint32_t acc = tmem_base + buf * TCB_L;
                     if (!(ablate & 8)) {
-                    const uint32_t acc_main = tmem_base + buf * TCB_L, acc_small = tmem_base + 256;
-                    const uint32_t a_hi = tmem_base + 384 + sa * 64, a_lo = a_hi + 32;
-                    const uint64_t dB = desc0 + (uint64_t)(sb * (TCB_BSTAGE_BYTES >> 4));
+                        const uint32_t a_hi = tmem_base + 256 + sa * 64, a_lo = a_hi + 32;
+                        const uint64_t dBh = desc0 + (uint64_t)(sb * (TCB_BT_BYTES >> 4)), dBl = dBh + (TCB_TILE_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t dBh = dB + 2 * k, dBl = dBh + (TCB_TILE_BYTES >> 4);
-                        umma_tf32_ts(acc_main, a_hi + 8 * k, dBh, idesc, (chain_start && k == 0) ? 0u : 1u);
-                        umma_tf32_ts(acc_small, a_hi + 8 * k, dBl, idesc, (small_start && k == 0) ? 0u : 1u);
-                        umma_tf32_ts(acc_small, a_lo + 8 * k, dBh, idesc, 1u);
+                        for (int k = 0; k < 4; ++k) {
+                            umma_ts<0, 1>(acc, a_hi + 8 * k, dBl + 2 * k, idesc, k ? 1u : 0u);
+                            umma_ts<0, 1>(acc, a_lo + 8 * k, dBh + 2 * k, idesc, 1u);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_ts<0, 1>(acc, a_hi + 8 * k, dBh + 2 * k, idesc, 1u);
                     }
-                    }
-                    umma_commit(&a_empty[sa]);
                     umma_commit(&b_empty[sb]);
-                    if (chain_end) umma_commit(&acc_full[buf]);
-                    if (small_end) umma_commit(small_full);
+                    umma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
-                if (chain_end) ++g;
-                if (small_end) ++gs;
-                if (++ch == cpu) ch = 0;
             }
-        } else if (warp == 3) {
-            // ---------------- loader: one bulk copy per operand per chunk into the table ring ----------------
+        } else if (warp == 1) {
+            // ---------------- table loader: a chunk's 5 KB table block and its 16 tile-start states, NT chunks ahead ----------------
             if (lane == 0) {
-                for (uint32_t q = 0; q < n_chunks_total; ++q) {
-                    const uint32_t slot = q % TCB_TABS;
-                    mbar_wait(&tab_empty[slot], ((q / TCB_TABS) & 1) ^ 1);
-                    const size_t blk_idx = ((size_t)units[u0 + (int)(q / cpu)].obj * cpu + (q % cpu)) * 256;
-                    const uint32_t dst = smem_u32(tabs) + slot * TCB_TAB_BYTES;
-                    mbar_expect_tx(&tab_full[slot], TCB_TAB_BYTES);
-                    bulk_g2s(dst, tabA + blk_idx, 2048, &tab_full[slot]);
-                    bulk_g2s(dst + 2048, tabB + blk_idx, 2048, &tab_full[slot]);
+                uint32_t q = 0;
+#pragma unroll 1
+                for (int u = u0; u < u1; ++u) {
+                    const Unit un = units[u];
+                    const uint8_t* tsrc = tab + (size_t)(un.obj - obj0) * cpu * TCB_TABG_BYTES;
+                    const float2* vsrc = V + (size_t)un.src * mp;
+#pragma unroll 1
+                    for (int ch = 0; ch < cpu; ++ch, ++q) {
+                        const uint32_t ts = q % TCB_NT;
+                        mbar_wait(&t_empty[ts], ((q / TCB_NT) & 1) ^ 1);
+                        mbar_expect_tx(&t_full[ts], TCB_TAB_BYTES);
+                        const uint32_t tdst = smem_u32(tabs) + ts * TCB_TAB_BYTES;
+                        bulk_g2s(tdst, tsrc + (size_t)ch * TCB_TABG_BYTES, TCB_TABG_BYTES, &t_full[ts]);
+                        bulk_g2s(tdst + TCB_TABG_BYTES, vsrc + ch * TCB_KMODES, 128, &t_full[ts]);
+                    }
                 }
             }
-        } else if (warp <= 2) {
-            // ---------------- seed warps (chunks alternate between warps 1 and 2) ----------------
-            // lanes 0-15: X[m][blk] = v_base * W^(16 blk), the state at the start of each 16-row block;
-            // lanes 16-31: R[m][j] = W^j = W^(4t) W^c for the 16 rows of a block.
+        } else if (warp == 2) {
+            // ---------------- seed warp: X[blk][m] = v W^(16 blk), the state at the start of every 16-row block ----------------
             const int m_l = lane & 15, half = lane >> 4;
-            for (uint32_t q = warp - 1; q < n_chunks_total; q += 2) {
-                const int u = u0 + (int)(q / cpu), ch = (int)(q % cpu);
-                const Unit un = units[u];
-                const int m = ch * TCB_KMODES + m_l;
-                const bool valid = m < n_modes;
-                const size_t idx = (size_t)un.obj * n_modes + (valid ? m : 0);
-                const uint32_t tslot = q % TCB_TABS;
-                mbar_wait(&tab_full[tslot], (q / TCB_TABS) & 1);
-                const uint32_t tA = smem_u32(tabs) + tslot * TCB_TAB_BYTES + m_l * 8;     // entry e at tA + 128 e
-                float2 out[16];
-                if (half == 0) {
-                    c32 ra[8];
+            uint32_t q = 0;
+#pragma unroll 1
+            for (int u = u0; u < u1; ++u) {
+                const int re = units[u].re;
+#pragma unroll 1
+                for (int ch = 0; ch < cpu; ++ch, ++q) {
+                    const uint32_t ts = q % TCB_NT, ss = q % TCB_NS;
+                    mbar_wait(&t_full[ts], (q / TCB_NT) & 1);
+                    const uint32_t tP = smem_u32(tabs) + ts * TCB_TAB_BYTES, tR = tP + TCB_TAB_R, tV = tP + TCB_TABG_BYTES;
+                    const float2 v = lds_f2(tV + m_l * 8);
+                    float2 x[4];
+                    if (re < 0) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) ra[e] = pk2(lds_f2(tA + 128 * e));
-                    if (un.ev < 0) {
-                        const c32 vb = valid ? pk2(__ldg(&Vbase[(size_t)un.it * npm + idx])) : pk(0.f, 0.f);
-#pragma unroll
-                        for (int blk = 0; blk < 8; ++blk) { float a, b; upk(cmulf(vb, ra[blk], rot(ra[blk])), a, b); out[blk] = make_float2(a, b); }
+                        for (int i = 0; i < 4; ++i) x[i] = cmulf(v, lds_f2(tP + (4 * half + i) * 128 + m_l * 8));
                     } else {
-                        // impulse unit: zero before the impulse row `re`; block ae starts AT the impulse (rows are
-                        // shifted by be in the row threads); later blocks start at u W^(16 (blk - ae) - be)
-                        const int re = ev_row[un.ev] - un.it * TCB_ROWS, ae = re >> 4, be = re & 15;
-                        const double inji = c3a[idx], injr = inji * cota[idx];
-                        const double sp = valid ? ev_space[(size_t)un.ev * n_modes + m] : 0.0;
-                        const c32 uimp = pk((float)(sp * injr), (float)(sp * inji));
+                        // impulse unit: zero before the impulse row `re`; block ae starts AT the impulse (its rows are
+                        // shifted by be in the generators); later blocks start at u W^(16 (blk - ae) - be)
+                        const int ae = re >> 4, be = re & 15;
 #pragma unroll
-                        for (int blk = 0; blk < 8; ++blk) {
-                            c32 x = pk(0.f, 0.f);
-                            if (blk == ae) x = uimp;
+                        for (int i = 0; i < 4; ++i) {
+                            const int blk = 4 * half + i;
+                            float2 xx = make_float2(0.f, 0.f);
+                            if (blk == ae) xx = v;
                             else if (blk > ae) {
                                 const int d = 16 * (blk - ae) - be;
-                                x = uimp;
-                                if (d >> 4) { const c32 qq = pk2(lds_f2(tA + 128 * (d >> 4))); x = cmulf(x, qq, rot(qq)); }
-                                if ((d >> 2) & 3) { const c32 qq = pk2(lds_f2(tA + 128 * (7 + ((d >> 2) & 3)))); x = cmulf(x, qq, rot(qq)); }
-                                if (d & 3) { const c32 qq = pk2(lds_f2(tA + 128 * (10 + (d & 3)))); x = cmulf(x, qq, rot(qq)); }
+                                xx = v;
+                                if (d >> 4) xx = cmulf(xx, lds_f2(tP + (d >> 4) * 128 + m_l * 8));
+                                if (d & 15) xx = cmulf(xx, lds_f2(tR + (d & 15) * TCB_RSTRIDE + m_l * 8));
                             }
-                            float a, b; upk(x, a, b); out[blk] = make_float2(a, b);
+                            x[i] = xx;
                         }
                     }
-                } else {
-                    const c32 rt[4] = {pk(1.f, 0.f), pk2(lds_f2(tA + 128 * 8)), pk2(lds_f2(tA + 128 * 9)), pk2(lds_f2(tA + 128 * 10))};
-                    const c32 rc[4] = {pk(1.f, 0.f), pk2(lds_f2(tA + 128 * 11)), pk2(lds_f2(tA + 128 * 12)), pk2(lds_f2(tA + 128 * 13))};
+                    mbar_wait(&s_empty[ss], ((q / TCB_NS) & 1) ^ 1);
+                    const uint32_t sX = smem_u32(seeds) + ss * TCB_SEED_BYTES;
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const c32 v = (t == 0) ? rc[c] : (c == 0 ? rt[t] : cmulf(rt[t], rc[c], rot(rc[c])));
-                            float a, b; upk(v, a, b); out[4 * t + c] = make_float2(a, b);
-                        }
+                    for (int i = 0; i < 4; ++i) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sX + (4 * half + i) * 128 + m_l * 8), "f"(x[i].x), "f"(x[i].y) : "memory");
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&t_empty[ts]); mbar_arrive(&s_full[ss]); }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tab_empty[tslot]);
-                const uint32_t slot = q % TCB_SEEDS;
-                mbar_wait(&seed_empty[slot], ((q / TCB_SEEDS) & 1) ^ 1);
-                const uint32_t sbase = smem_u32(seeds) + slot * TCB_SEED_BYTES;
-                if (half == 0) {
-                    const uint32_t dst = sbase + m_l * 64;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) sts_v4(dst + 16 * i, out[2 * i].x, out[2 * i].y, out[2 * i + 1].x, out[2 * i + 1].y);
-                } else {
-                    const uint32_t dst = sbase + TCB_KMODES * 64 + m_l * TCB_RROW;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) sts_v4(dst + 16 * i, out[2 * i].x, out[2 * i].y, out[2 * i + 1].x, out[2 * i + 1].y);
-                    sts_v4(dst + 128, 0.f, 0.f, 0.f, 0.f);             // R[m][16] = 0: rows before an impulse
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&seed_full[slot]);
             }
         }
     } else if (warp < 8) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        // ---------------- epilogue: promote finished chains into registers, flush to the FP64 mix ----------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        // ---------------- epilogue: promote finished chunks into registers, flush to the FP64 mix ----------------
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         float acc[TCB_L];
 #pragma unroll
         for (int j = 0; j < TCB_L; ++j) acc[j] = 0.f;
-        uint32_t g = 0, gs = 0;
-        int since_flush = 0;
-        // mean of the tensor core's accumulate-with-truncation (2.5e-8 per main MMA of a chain, measured) and, when
-        // lo is not re-centred (SPLIT < 2), of the dropped lo*lo term
-        const double gain = 1.0 + 1.0e-7 * CHAIN + (SPLIT == 2 ? 0.0 : 0.6e-7);
+        uint32_t g = 0;
+#pragma unroll 1
         for (int u = u0; u < u1; ++u) {
-            const int it = units[u].it;
-            for (int ch = 0; ch < cpu; ++ch) {
-                const bool chain_end = (ch % CHAIN) == CHAIN - 1 || ch == cpu - 1;
-                const bool small_end = (ch % TCB_SMALL_CHAIN) == TCB_SMALL_CHAIN - 1 || ch == cpu - 1;
-                if (chain_end) {
-                    const int buf = g & 1;
-                    mbar_wait(&acc_full[buf], (g >> 1) & 1);
-                    tcgen05_fence_after();
-                    if (!(ablate & 4))
+#pragma unroll 1
+            for (int ch = 0; ch < cpu; ++ch, ++g) {
+                const int buf = g & 1;
+                mbar_wait(&acc_full[buf], (g >> 1) & 1);
+                tcgen05_fence_after();
+                if (!(ablate & 4)) {
 #pragma unroll
                     for (int qd = 0; qd < TCB_L / 32; ++qd) {
                         uint32_t vm[32];
@@ -455,103 +388,124 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[qd * 32 + j] += __uint_as_float(vm[j]);
                     }
-                    tcgen05_fence_before();
-                    mbar_arrive(&acc_empty[buf]);
-                    ++g;
                 }
-                if (small_end) {
-                    mbar_wait(small_full, gs & 1);
-                    tcgen05_fence_after();
-                    if (!(ablate & 4))
-#pragma unroll
-                    for (int qd = 0; qd < TCB_L / 32; ++qd) {
-                        uint32_t vs[32];
-                        tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(256 + qd * 32), vs);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[qd * 32 + j] += __uint_as_float(vs[j]);
-                    }
-                    tcgen05_fence_before();
-                    mbar_arrive(small_empty);
-                    ++gs;
-                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }
-            ++since_flush;
-            const bool flush = (u + 1 == u1) || (units[u + 1].it != it) || since_flush >= flush_units;
-            if (flush) {
-                since_flush = 0;
-                const long long tile = (long long)it * TCB_ROWS + row;
+            const Unit un = units[u];
+            if (un.flush) {
+                const long long tile = (long long)un.it * TCB_ROWS + row;
                 if (tile < n_tiles) {
                     double* dst = mix + tile * TCB_L;
 #pragma unroll
-                    for (int j = 0; j < TCB_L; ++j) atomicAdd(dst + j, (double)acc[j] * gain);
+                    for (int j = 0; j < TCB_L; ++j) atomicAdd(dst + j, (double)acc[j] * inv_gain);
                 }
 #pragma unroll
                 for (int j = 0; j < TCB_L; ++j) acc[j] = 0.f;
             }
         }
     } else if (warp < 12) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-        // ---------------- A generators: thread = row (TMEM lane); A[row][2m..2m+1] = X[m][blk] * R[m][j] -----------
-        const int row = (warp - 8) * 32 + lane, blk = row >> 4, j = row & 15;
-        const uint32_t lane_off = (uint32_t)((warp - 8) * 32) << 16;
-        for (uint32_t q = 0; q < n_chunks_total; ++q) {
-            const int u = u0 + (int)(q / cpu);
-            const Unit un = units[u];
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+        // ---------------- A generators: thread = row (TMEM lane); A[row][2m..2m+1] = X[blk][m] * R[j][m] ----------------
+        // two modes per 16-byte load: X from the seed slot (two addresses per warp: broadcast), R straight from the table
+        // slot (16 rows 144 bytes apart: conflict-free); an impulse unit's rows before the impulse read the zero row.
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane, blk = row >> 4, j = row & 15;
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        uint32_t q = 0;
+#pragma unroll 1
+        for (int u = u0; u < u1; ++u) {
+            const int re = units[u].re;
             int jj = j;
-            if (un.ev >= 0) {                                         // impulse unit: rows of block ae are shifted by be
-                const int re = ev_row[un.ev] - un.it * TCB_ROWS;
-                if (blk == (re >> 4)) jj = j - (re & 15);
-            }
-            const uint32_t slot = q % TCB_SEEDS, sa = q % TCB_ASTAGES;
-            mbar_wait(&seed_full[slot], (q / TCB_SEEDS) & 1);
-            const uint32_t sX = smem_u32(seeds) + slot * TCB_SEED_BYTES + blk * 8;
-            const uint32_t sR = smem_u32(seeds) + slot * TCB_SEED_BYTES + TCB_KMODES * 64 + (jj < 0 ? 16 : jj) * 8;
-            uint32_t hi[32], lo[32];
-            if (ablate & 2) {
+            if (re >= 0 && blk == (re >> 4)) { jj = j - (re & 15); if (jj < 0) jj = 16; }   // impulse unit: rows of block ae are shifted by be; row 16 = 0
+#pragma unroll 1
+            for (int ch = 0; ch < cpu; ++ch, ++q) {
+                const uint32_t ss = q % TCB_NS, sa = q % TCB_NA, ts = q % TCB_NT;
+                mbar_wait(&t_full[ts], (q / TCB_NT) & 1);
+                mbar_wait(&s_full[ss], (q / TCB_NS) & 1);
+                const uint32_t sX = smem_u32(seeds) + ss * TCB_SEED_BYTES + blk * 128;
+                const uint32_t sR = smem_u32(tabs) + ts * TCB_TAB_BYTES + TCB_TAB_R + jj * TCB_RSTRIDE;
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int m = 0; m < 32; ++m) hi[m] = lo[m] = 0u;
-            } else
+                for (int m2 = 0; m2 < TCB_KMODES / 2; ++m2) {
+                    float4 x, r;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(sX + m2 * 16));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sR + m2 * 16));
+                    float v[4];
+                    v[0] = fmaf(-x.y, r.y, x.x * r.x); v[1] = fmaf(x.x, r.y, x.y * r.x);
+                    v[2] = fmaf(-x.w, r.w, x.z * r.z); v[3] = fmaf(x.z, r.w, x.w * r.z);
 #pragma unroll
-            for (int m = 0; m < TCB_KMODES; ++m) {
-                const float2 x = lds_f2(sX + m * 64), r = lds_f2(sR + m * TCB_RROW);
-                float vr, vi; upk(cmulf(pk(x.x, x.y), pk(r.x, r.y), pk(-r.y, r.x)), vr, vi);
-                split_tf32<SPLIT>(vr, hi[2 * m], lo[2 * m]);
-                split_tf32<SPLIT>(vi, hi[2 * m + 1], lo[2 * m + 1]);
+                    for (int c = 0; c < 4; ++c) {
+                        // hi = the raw value (the tensor core reads its upper 19 bits); lo = what those bits miss, rounded to nearest
+                        const uint32_t bits = __float_as_uint(v[c]);
+                        const float l = __uint_as_float(bits) - __uint_as_float(bits & 0xFFFFE000u);
+                        hi[4 * m2 + c] = bits; lo[4 * m2 + c] = __float_as_uint(l) + 0x1000u;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&s_empty[ss]); mbar_arrive(&t_empty[ts]); }
+                mbar_wait(&b_empty[sa], ((q / TCB_NA) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t a_col = tmem_base + lane_off + 256 + sa * 64;
+                tmem_st_32x32(a_col, hi);
+                tmem_st_32x32(a_col + 32, lo);
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[sa]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&seed_empty[slot]);
-            mbar_wait(&a_empty[sa], ((q / TCB_ASTAGES) & 1) ^ 1);
-            tcgen05_fence_after();
-            const uint32_t a_col = tmem_base + lane_off + 384 + sa * 64;
-            if (!(ablate & 2)) {
-            tmem_st_32x32(a_col, hi);
-            tmem_st_32x32(a_col + 32, lo);
-            tmem_st_wait();
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[sa]);
         }
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-        // ---------------- B generators: thread = (mode of the chunk, 16-row block), pole powers T w^j -----------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+        // ---------------- B generators: thread = (mode of the chunk, 16-row block); rows 4t + c = x Rt[t] Rc[c] ----------------
+        // straight into the UMMA K-major 128-byte-swizzle layout: row r = 16 blk + b, K columns (2 m, 2 m + 1) at byte
+        // (r / 8) 1024 + (r % 8) 128 + (((m / 2) ^ (r % 8)) 16) + (m % 2) 8; the eight swizzled offsets of a thread never change
         const int m_l = lane & 15, blk = (warp - 12) * 2 + (lane >> 4);
-        for (uint32_t q = 0; q < n_chunks_total; ++q) {
-            const uint32_t sb = q % TCB_BSTAGES, tslot = q % TCB_TABS;
-            mbar_wait(&tab_full[tslot], (q / TCB_TABS) & 1);
-            const uint32_t tB = smem_u32(tabs) + tslot * TCB_TAB_BYTES + 2048 + m_l * 8;   // entry e at tB + 128 e
-            const c32 ra = pk2(lds_f2(tB + 128 * blk));
-            const c32 rt[3] = {pk2(lds_f2(tB + 128 * 8)), pk2(lds_f2(tB + 128 * 9)), pk2(lds_f2(tB + 128 * 10))};
-            const c32 rc[3] = {pk2(lds_f2(tB + 128 * 11)), pk2(lds_f2(tB + 128 * 12)), pk2(lds_f2(tB + 128 * 13))};
-            mbar_wait(&b_empty[sb], ((q / TCB_BSTAGES) & 1) ^ 1);
-            const uint32_t st = smem_u32(smem) + sb * TCB_BSTAGE_BYTES;
-            if (!(ablate & 1)) gen_block<SPLIT>(st, st + TCB_TILE_BYTES, blk, m_l, ra, rt, rc);
+        uint32_t xoff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xoff[i] = sw128_pair(16 * blk + i, m_l);
+        const uint32_t n_chunks = (uint32_t)(u1 - u0) * (uint32_t)cpu;
+#pragma unroll 1
+        for (uint32_t q = 0; q < n_chunks; ++q) {
+            const uint32_t sb = q % TCB_NB, ts = q % TCB_NT;
+            mbar_wait(&t_full[ts], (q / TCB_NT) & 1);
+            const uint32_t tB = smem_u32(tabs) + ts * TCB_TAB_BYTES + TCB_TAB_B + m_l * 8;   // entry e at tB + 128 e
+            const float2 ra = lds_f2(tB + 128 * blk);
+            float2 rt[3], rc[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { rt[t] = lds_f2(tB + 128 * (8 + t)); rc[t] = lds_f2(tB + 128 * (11 + t)); }
+            // broadcast pairs of the step powers: p * q = (pr, pr) * q + (pi, pi) * (i q)
+            c32 rtr[3], rti[3], rcr[3], rci[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { rtr[t] = pk(rt[t].x, rt[t].x); rti[t] = pk(rt[t].y, rt[t].y); rcr[t] = pk(rc[t].x, rc[t].x); rci[t] = pk(rc[t].y, rc[t].y); }
+            const c32 xa = pk(ra.x, ra.y), xar = pk(-ra.y, ra.x);
+            mbar_wait(&b_empty[sb], ((q / TCB_NB) & 1) ^ 1);
+            const uint32_t st = smem_u32(smem) + sb * TCB_BT_BYTES;
+            if (!(ablate & 1)) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const c32 pt = t == 0 ? xa : fma2(rti[t - 1], xar, mul2(rtr[t - 1], xa));
+                    float pr, pi; upk(pt, pr, pi);
+                    const c32 ptr_ = pk(-pi, pr);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const c32 v = c == 0 ? pt : fma2(rci[c - 1], ptr_, mul2(rcr[c - 1], pt));
+                        float vr, vi; upk(v, vr, vi);
+                        const uint32_t br = __float_as_uint(vr), bi = __float_as_uint(vi);
+                        const c32 tt = pk(__uint_as_float(br & 0xFFFFE000u), __uint_as_float(bi & 0xFFFFE000u));
+                        float lr, li; upk(sub2(v, tt), lr, li);
+                        const int b = 4 * t + c;
+                        const uint32_t addr = st + xoff[b & 7] + (uint32_t)(b >> 3) * 1024u;
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(br), "r"(bi) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + TCB_TILE_BYTES), "r"(__float_as_uint(lr) + 0x1000u), "r"(__float_as_uint(li) + 0x1000u) : "memory");
+                    }
+                }
+            }
             fence_proxy_async_smem();
             __syncwarp();
-            // the table slot is released only here: the loads above are certainly complete once their values have
-            // been used (an arrive issued right after the LDS can overtake them in the MIO queue)
-            if (lane == 0) { mbar_arrive(&tab_empty[tslot]); mbar_arrive(&b_full[sb]); }
+            // the table slot is released only here: its loads are certainly complete once their values have been used
+            if (lane == 0) { mbar_arrive(&t_empty[ts]); mbar_arrive(&b_full[sb]); }
         }
     }
     tcgen05_fence_before();
@@ -560,139 +514,219 @@ k_batch_tc(int n_obj, int n_modes, int n_tiles, const int* __restrict__ cta_firs
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCB_TMEM_COLS));
 }
 
-__global__ void k_ev_rows(int n, const int* __restrict__ ev_buf, int num, int den, int* __restrict__ ev_row) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ev_row[i] = (int)((long long)ev_buf[i] * num / den);
-}
-
 }  // namespace
 
 namespace pbso {
 
 struct TcState {
-    float2 *tabA = nullptr, *tabB = nullptr, *Vbase = nullptr;
-    Unit* units = nullptr; int* ev_row = nullptr; int* cta_first = nullptr; int grid = 0;
-    size_t npm = 0, vbase_cap = 0, units_cap = 0, ev_cap = 0;
-    unsigned tables_ver = ~0u, units_ev_ver = ~0u;
-    int units_n_it = -1, units_buf_size = -1, n_units = 0;
-    std::vector<Unit> h_units;
+    uint8_t* tab = nullptr;                         // per-handle operand tables of the resident object batch
+    float2* V = nullptr; size_t v_cap = 0;          // state blocks: carrier | impulses
+    int v_nit = -1, v_no = -1, v_ne = -1;           // layout the pad entries of V were zeroed for
+    Unit* units = nullptr; size_t unit_cap = 0;
+    int* cta_first = nullptr; int* ev_obj = nullptr; size_t ev_cap = 0;
+    int grid = 0;
+    int tab_obj0 = -1, tab_nobj = 0, batch_obj = 0; // objects [tab_obj0, tab_obj0 + tab_nobj) have tables resident
+    size_t npm = 0;
+    // cached unit list
+    unsigned ev_ver = ~0u; int list_tiles = -1, list_buf = -1, list_obj0 = -1, list_nobj = -1, n_units = 0;
+    std::vector<Unit> h_units; std::vector<int> h_first;
+    std::vector<int> h_ev_obj;
 };
 
 void tc_free(TcState* st) {
     if (!st) return;
-    cudaFree(st->tabA); cudaFree(st->tabB); cudaFree(st->Vbase);
-    cudaFree(st->units); cudaFree(st->ev_row); cudaFree(st->cta_first);
+    cudaFree(st->tab); cudaFree(st->V); cudaFree(st->units); cudaFree(st->cta_first); cudaFree(st->ev_obj);
     delete st;
 }
+
+// unit list of the objects [o0, o0 + no): work items = (window of TCB_WINDOW objects, M-tile), dealt round-robin to the
+// CTAs in (window, M-tile) order -- the CTAs rendering the M-tiles of one window run at about the same time, so a
+// window's table blocks are read from HBM once and from L2 by the rest; a CTA keeps one M-tile's partial mix in
+// registers across the units of an item.
+static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tiles, int n_it, int tpb) {
+    const int ncta = st->grid;
+    const unsigned imp_blk0 = (unsigned)((size_t)n_it * no);
+    const int e_base = a.h_ev_off[o0];
+    static const int window = getenv("PBSO_TC_WINDOW") ? std::max(1, atoi(getenv("PBSO_TC_WINDOW"))) : TCB_WINDOW;
+    static const int flush_units = getenv("PBSO_TC_FLUSH") ? std::max(1, atoi(getenv("PBSO_TC_FLUSH"))) : TCB_FLUSH_UNITS;
+    std::vector<std::vector<Unit>> per(ncta);
+    std::vector<int> cur(no);
+    long long item = 0;
+    for (int w0 = 0; w0 < no; w0 += window) {
+        const int w1 = std::min(no, w0 + window);
+        for (int o = w0; o < w1; ++o) cur[o] = a.h_ev_off[o0 + o];
+        for (int it = 0; it < n_it; ++it) {
+            const long long row0 = (long long)it * TCB_ROWS, row1 = row0 + TCB_ROWS;
+            std::vector<Unit> tmp;
+            for (int o = w0; o < w1; ++o) {
+                const int e_begin = a.h_ev_off[o0 + o], e_end = a.h_ev_off[o0 + o + 1];
+                // carry unit (an earlier impulse exists), then the impulses landing inside the M-tile (events are sorted by buffer)
+                if (e_begin < e_end && (long long)a.h_ev_buf[e_begin] * tpb < row0) tmp.push_back(Unit{o0 + o, it, (unsigned)((size_t)it * no + o), (short)-1, 0});
+                int& e = cur[o];
+                while (e < e_end && (long long)a.h_ev_buf[e] * tpb < row1) {
+                    const long long row = (long long)a.h_ev_buf[e] * tpb;
+                    if (row >= row0 && row < n_tiles) tmp.push_back(Unit{o0 + o, it, imp_blk0 + (unsigned)(e - e_base), (short)(row - row0), 0});
+                    ++e;
+                }
+            }
+            if (tmp.empty()) continue;
+            std::vector<Unit>& out = per[item++ % ncta];
+            int since = 0;
+            for (Unit& un : tmp) { un.flush = (short)(++since >= flush_units); if (un.flush) since = 0; out.push_back(un); }
+            out.back().flush = 1;                                    // the M-tile changes with the item
+        }
+    }
+    st->h_units.clear(); st->h_first.assign(ncta + 1, 0);
+    for (int c = 0; c < ncta; ++c) {
+        st->h_first[c] = (int)st->h_units.size();
+        st->h_units.insert(st->h_units.end(), per[c].begin(), per[c].end());
+    }
+    st->h_first[ncta] = (int)st->h_units.size();
+    st->n_units = (int)st->h_units.size();
+}
+
+static double g_inv_gain[64];            // per device; 0 = not calibrated yet
+static bool g_calibrating = false;
+
+static int tc_calibrate(int device, int sm_count);
 
 int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     PBSO_REQUIRE(a.buf_size % TCB_L == 0, PBSO_ERR_UNSUPPORTED, "PBSO_PREC_TC3X needs buf_size to be a multiple of 128");
     if (!*pst) *pst = new TcState();
     TcState* st = *pst;
+    *launches = 0;
+    int dev = 0; PBSO_CUDA(cudaGetDevice(&dev));
+    if (g_inv_gain[dev & 63] == 0.0 && !g_calibrating) { if (int rc = tc_calibrate(dev, a.sm_count)) return rc; }
+    const double inv_gain = g_calibrating ? 1.0 : g_inv_gain[dev & 63];
     const size_t npm = (size_t)a.n_obj * a.n_modes;
-    const int cpu = div_up(a.n_modes, TCB_KMODES);
-    const size_t ntab = (size_t)a.n_obj * cpu * 256;                  // float2 entries per operand table
+    const int cpu = div_up(a.n_modes, TCB_KMODES), mp = cpu * TCB_KMODES;
     const long long n_samples = (long long)a.buf_size * a.n_buffers;
     const int n_tiles = (int)(n_samples / TCB_L);
     const int n_it = div_up(n_tiles, TCB_ROWS);
     const int tpb = a.buf_size / TCB_L;                               // tiles per buffer
-    *launches = 0;
-    // static tables (depend on a, b, the transfer vectors and L)
-    if (st->npm != npm) {
-        cudaFree(st->tabA); cudaFree(st->tabB);
-        st->tabA = st->tabB = nullptr; st->npm = 0;
-        PBSO_CUDA(cudaMalloc(&st->tabA, sizeof(float2) * ntab));
-        PBSO_CUDA(cudaMalloc(&st->tabB, sizeof(float2) * ntab));
-        st->npm = npm; st->tables_ver = ~0u;
+    st->grid = std::max(1, a.sm_count);
+    // ---- objects per batch: the operand tables of a batch stay resident (5 KB per object and 16-mode chunk) ----
+    if (st->npm != npm || st->batch_obj == 0) {
+        cudaFree(st->tab); st->tab = nullptr; st->tab_obj0 = -1; st->npm = 0;
+        size_t free_b = 0, total_b = 0; PBSO_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_obj = (size_t)cpu * TCB_TABG_BYTES;
+        // PBSO_TC_TABLE_BYTES caps the resident tables (tests use it to force the multi-batch path)
+        const double frac = getenv("PBSO_TC_TABLE_FRAC") ? atof(getenv("PBSO_TC_TABLE_FRAC")) : 0.4;
+        size_t budget = (size_t)(frac * (double)free_b);
+        if (getenv("PBSO_TC_TABLE_BYTES")) budget = std::min(budget, (size_t)atoll(getenv("PBSO_TC_TABLE_BYTES")));
+        size_t fit = budget / per_obj;
+        if (fit < 1) return set_error(PBSO_ERR_CUDA, "PBSO_PREC_TC3X: not enough device memory for one object's operand tables (%zu bytes)", per_obj);
+        st->batch_obj = (int)std::min<size_t>(fit, (size_t)a.n_obj);
+        PBSO_CUDA(cudaMalloc(&st->tab, (size_t)st->batch_obj * per_obj));
+        st->npm = npm; st->ev_ver = ~0u;
     }
-    if (st->tables_ver != a.trans_ver) {
-        k_tc_tables<<<(unsigned)(((size_t)a.n_obj * cpu * TCB_KMODES + 255) / 256), 256, 0, a.stream>>>(a.n_obj, a.n_modes, cpu, a.lneps, a.theta, a.trans, st->tabA, st->tabB);
-        PBSO_CUDA(cudaGetLastError());
-        st->tables_ver = a.trans_ver; ++*launches;
+    if ((size_t)std::max(a.n_events, 1) > st->ev_cap) {
+        cudaFree(st->ev_obj); st->ev_obj = nullptr; st->ev_cap = 0;
+        PBSO_CUDA(cudaMalloc(&st->ev_obj, sizeof(int) * std::max(a.n_events, 1))); st->ev_cap = std::max(a.n_events, 1);
     }
-    // unit list (depends on the impulse script and the render length)
-    if (st->units_ev_ver != a.ev_ver || st->units_n_it != n_it || st->units_buf_size != a.buf_size) {
-        std::vector<Unit>& hu = st->h_units;
-        hu.clear();
-        std::vector<int> cursor(a.h_ev_off, a.h_ev_off + a.n_obj);    // first event of each object not yet placed
-        for (int it = 0; it < n_it; ++it) {
-            const long long row0 = (long long)it * TCB_ROWS, row1 = row0 + TCB_ROWS;
-            for (int o = 0; o < a.n_obj; ++o) {
-                const int e_begin = a.h_ev_off[o], e_end = a.h_ev_off[o + 1];
-                if (e_begin < e_end && (long long)a.h_ev_buf[e_begin] * tpb < row0) hu.push_back(Unit{it, o, -1, 0});
-                int& e = cursor[o];
-                while (e < e_end && (long long)a.h_ev_buf[e] * tpb < row1) {
-                    if ((long long)a.h_ev_buf[e] * tpb < n_tiles) hu.push_back(Unit{it, o, e, 0});
-                    ++e;
-                }
-            }
-        }
-        st->n_units = (int)hu.size();
-        if (hu.size() > st->units_cap) {
-            cudaFree(st->units); st->units = nullptr; st->units_cap = 0;
-            PBSO_CUDA(cudaMalloc(&st->units, sizeof(Unit) * hu.size())); st->units_cap = hu.size();
-        }
-        if ((size_t)std::max(a.n_events, 1) > st->ev_cap) {
-            cudaFree(st->ev_row); st->ev_row = nullptr; st->ev_cap = 0;
-            PBSO_CUDA(cudaMalloc(&st->ev_row, sizeof(int) * std::max(a.n_events, 1))); st->ev_cap = std::max(a.n_events, 1);
-        }
-        if (!hu.empty()) PBSO_CUDA(cudaMemcpyAsync(st->units, hu.data(), sizeof(Unit) * hu.size(), cudaMemcpyHostToDevice, a.stream));
-        // contiguous ranges of equal estimated cost, one per CTA: an impulse unit costs more than a carry unit (one
-        // of its 16-row blocks takes the general path), and impulse units cluster in the first M-tiles
-        static const double imp_w = getenv("PBSO_TC_IMPW") ? atof(getenv("PBSO_TC_IMPW")) : 2.0;
-        st->grid = std::max(1, std::min(a.sm_count, st->n_units));
-        std::vector<int> first(st->grid + 1, st->n_units);
-        double total = 0.0;
-        for (const Unit& un : hu) total += un.ev >= 0 ? imp_w : 1.0;
-        double acc_cost = 0.0; int c = 0;
-        first[0] = 0;
-        for (int i = 0; i < st->n_units; ++i) {
-            while (c + 1 < st->grid && acc_cost >= total * (c + 1) / st->grid) first[++c] = i;
-            acc_cost += hu[i].ev >= 0 ? imp_w : 1.0;
-        }
-        while (c + 1 <= st->grid) first[++c] = st->n_units;
-        if (!st->cta_first) PBSO_CUDA(cudaMalloc(&st->cta_first, sizeof(int) * (a.sm_count + 1)));
-        PBSO_CUDA(cudaMemcpyAsync(st->cta_first, first.data(), sizeof(int) * (st->grid + 1), cudaMemcpyHostToDevice, a.stream));
-        if (a.n_events > 0) {
-            k_ev_rows<<<div_up(a.n_events, 256), 256, 0, a.stream>>>(a.n_events, a.d_ev_buf, tpb, 1, st->ev_row);
-            PBSO_CUDA(cudaGetLastError());
-        }
-        PBSO_CUDA(cudaStreamSynchronize(a.stream));                   // h_units may be rebuilt by the next call
-        st->units_ev_ver = a.ev_ver; st->units_n_it = n_it; st->units_buf_size = a.buf_size;
-    }
-    if (st->n_units == 0) return PBSO_OK;                             // silence: the mix is already zeroed
-    const size_t vneed = (size_t)n_it * npm;
-    if (vneed > st->vbase_cap) {
-        cudaFree(st->Vbase); st->Vbase = nullptr; st->vbase_cap = 0;
-        PBSO_CUDA(cudaMalloc(&st->Vbase, sizeof(float2) * vneed)); st->vbase_cap = vneed;
-    }
-    k_tc_carrier<<<(unsigned)((npm + 255) / 256), 256, 0, a.stream>>>(a.n_obj, a.n_modes, n_it, tpb, 1, a.lneps, a.theta, a.c3, a.cot,
-                                                                   a.d_ev_off, a.d_ev_buf, a.d_ev_space, st->Vbase);
-    PBSO_CUDA(cudaGetLastError());
-    ++*launches;
-    static const int split = getenv("PBSO_TC_SPLIT") ? atoi(getenv("PBSO_TC_SPLIT")) : 1;
-    static const int chain = getenv("PBSO_TC_CHAIN") ? atoi(getenv("PBSO_TC_CHAIN")) : 2;
-    static const int flush_units = getenv("PBSO_TC_FLUSH") ? atoi(getenv("PBSO_TC_FLUSH")) : TCB_FLUSH_UNITS;
+    if (!st->cta_first) PBSO_CUDA(cudaMalloc(&st->cta_first, sizeof(int) * (a.sm_count + 2)));
     static const int ablate = getenv("PBSO_TC_ABLATE") ? atoi(getenv("PBSO_TC_ABLATE")) : 0;
-    const int grid = st->grid;
-#define PBSO_TC_LAUNCH(S, C)                                                                                         \
-    do {                                                                                                             \
-        static bool attr[64] = {};      /* per device: function attributes do not carry across devices */          \
-        int dev_ = 0; cudaGetDevice(&dev_);                                                                          \
-        if (!attr[dev_ & 63]) { PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_TS)); attr[dev_ & 63] = true; } \
-        k_batch_tc<S, C><<<grid, TCB_THREADS, TCB_SMEM_TS, a.stream>>>(a.n_obj, a.n_modes, n_tiles, st->cta_first, st->units, st->tabA, \
-            st->tabB, st->Vbase, a.c3, a.cot, st->ev_row, a.d_ev_space, a.d_mix, flush_units, ablate);                     \
-    } while (0)
-    if (split == 0 && chain == 2) PBSO_TC_LAUNCH(0, 2);
-    else if (split == 2 && chain == 2) PBSO_TC_LAUNCH(2, 2);
-    else if (split == 1 && chain == 1) PBSO_TC_LAUNCH(1, 1);
-    else if (split == 1 && chain == 4) PBSO_TC_LAUNCH(1, 4);
-    else if (split == 2 && chain == 4) PBSO_TC_LAUNCH(2, 4);
-    else PBSO_TC_LAUNCH(1, 2);
-#undef PBSO_TC_LAUNCH
-    PBSO_CUDA(cudaGetLastError());
-    ++*launches;
+    static bool attr[64] = {};            // per device: function attributes do not carry across devices
+    if (!attr[dev & 63]) { PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM)); attr[dev & 63] = true; }
+    const int n_batches = div_up(a.n_obj, st->batch_obj);
+    for (int bi = 0; bi < n_batches; ++bi) {
+        const int o0 = bi * st->batch_obj, no = std::min(st->batch_obj, a.n_obj - o0);
+        // operand tables (depend on the poles only: built once when every object fits in one batch)
+        if (st->tab_obj0 != o0 || st->tab_nobj != no) {
+            k_tc_tabs<<<(unsigned)(((size_t)no * mp + 255) / 256), 256, 0, a.stream>>>(no, a.n_modes, cpu, o0, a.lneps, a.theta, st->tab);
+            PBSO_CUDA(cudaGetLastError());
+            st->tab_obj0 = o0; st->tab_nobj = no; ++*launches;
+        }
+        // unit list (depends on the impulse script, the render length and the batch)
+        const bool relist = st->ev_ver != a.ev_ver || st->list_tiles != n_tiles || st->list_buf != a.buf_size || st->list_obj0 != o0 || st->list_nobj != no;
+        if (relist) {
+            build_units(st, a, o0, no, n_tiles, n_it, tpb);
+            if ((size_t)st->n_units > st->unit_cap) {
+                cudaFree(st->units); st->units = nullptr; st->unit_cap = 0;
+                PBSO_CUDA(cudaMalloc(&st->units, sizeof(Unit) * st->n_units)); st->unit_cap = st->n_units;
+            }
+            // pageable sources: cudaMemcpyAsync stages them before it returns, the vectors may be rebuilt right away
+            if (st->n_units) PBSO_CUDA(cudaMemcpyAsync(st->units, st->h_units.data(), sizeof(Unit) * st->n_units, cudaMemcpyHostToDevice, a.stream));
+            PBSO_CUDA(cudaMemcpyAsync(st->cta_first, st->h_first.data(), sizeof(int) * (st->grid + 1), cudaMemcpyHostToDevice, a.stream));
+            if (a.n_events > 0) {
+                st->h_ev_obj.resize(a.n_events);
+                for (int o = 0; o < a.n_obj; ++o) for (int e = a.h_ev_off[o]; e < a.h_ev_off[o + 1]; ++e) st->h_ev_obj[e] = o;
+                PBSO_CUDA(cudaMemcpyAsync(st->ev_obj, st->h_ev_obj.data(), sizeof(int) * a.n_events, cudaMemcpyHostToDevice, a.stream));
+            }
+            st->ev_ver = a.ev_ver; st->list_tiles = n_tiles; st->list_buf = a.buf_size; st->list_obj0 = o0; st->list_nobj = no;
+        }
+        if (st->n_units == 0) continue;                               // silence: the mix is already zeroed
+        // state blocks: carrier [n_it][no] | impulses of the batch
+        const int e0 = a.h_ev_off[o0], ne = a.h_ev_off[o0 + no] - e0;
+        const size_t vneed = ((size_t)n_it * no + ne) * mp;
+        if (vneed > st->v_cap) {
+            cudaFree(st->V); st->V = nullptr; st->v_cap = 0;
+            PBSO_CUDA(cudaMalloc(&st->V, sizeof(float2) * vneed)); st->v_cap = vneed;
+            st->v_nit = -1;
+        }
+        if (mp != a.n_modes && (st->v_nit != n_it || st->v_no != no || st->v_ne != ne)) {                   // pad modes stay zero
+            PBSO_CUDA(cudaMemsetAsync(st->V, 0, sizeof(float2) * vneed, a.stream));
+        }
+        st->v_nit = n_it; st->v_no = no; st->v_ne = ne;
+        k_tc_carrier<<<(unsigned)(((size_t)no * a.n_modes + 255) / 256), 256, 0, a.stream>>>(no, a.n_modes, n_it, tpb, mp, o0, a.lneps, a.theta, a.c3, a.cot,
+                                                                                       a.trans, a.d_ev_off, a.d_ev_buf, a.d_ev_space, st->V);
+        PBSO_CUDA(cudaGetLastError());
+        ++*launches;
+        if (ne > 0) {
+            k_tc_impulse<<<(unsigned)(((size_t)ne * a.n_modes + 255) / 256), 256, 0, a.stream>>>(a.n_modes, mp, e0, ne, st->ev_obj, a.c3, a.cot, a.trans,
+                                                                                              a.d_ev_space, st->V + (size_t)n_it * no * mp);
+            PBSO_CUDA(cudaGetLastError());
+            ++*launches;
+        }
+        k_batch_tc<<<st->grid, TCB_THREADS, TCB_SMEM, a.stream>>>(a.n_modes, n_tiles, st->cta_first, st->units, st->tab, st->V, o0, a.d_mix, inv_gain, ablate);
+        PBSO_CUDA(cudaGetLastError());
+        ++*launches;
+    }
     return PBSO_OK;
 }
+
+// ---- gain calibration -----------------------------------------------------------------------------------------
+// The tensor core adds into its FP32 accumulator with truncation; over a chain of 8 hi*hi MMAs that is a coherent
+// gain error of about -2e-7 which belongs to the hardware, not to the workload.  Measured once per device: a
+// synthetic batch (256 modes spread like SURVEY 8(d)'s, both materials, one impulse per object) rendered by
+// k_batch_tc with gain 1 and by the FP64 direct-form kernel; gain = <y_tc, y_64> / <y_64, y_64>.
+static int tc_calibrate(int device, int sm_count) {
+    const char* fixed = getenv("PBSO_TC_GAIN");
+    if (fixed) { g_inv_gain[device & 63] = 1.0 / atof(fixed); return PBSO_OK; }
+    g_calibrating = true;
+    const int n_obj = std::max(64, sm_count), n_modes = 256, buf = 256, n_buf = 128;     // two M-tiles of 128 tiles
+    const double h = 1.0 / 44100.0;
+    std::vector<double> a((size_t)n_obj * n_modes), b(a.size()), tr(a.size()), sp(a.size());
+    unsigned s = 2463534242u;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return (double)(s >> 8) / 16777216.0; };
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int o = 0; o < n_obj; ++o)
+        for (int m = 0; m < n_modes; ++m) {
+            const double f = 80.0 * std::pow(18000.0 / 80.0, ((double)m + rnd()) / n_modes), om = two_pi * f;
+            const double alpha = (o & 1) ? 30.0 : 1.0, beta = (o & 1) ? 5e-7 : 1e-7;
+            const double xi = 0.5 * (alpha / om + beta * om);
+            a[(size_t)o * n_modes + m] = 2.0 * xi * om; b[(size_t)o * n_modes + m] = om * om;
+            tr[(size_t)o * n_modes + m] = 0.1 + rnd(); sp[(size_t)o * n_modes + m] = 2.0 * rnd() - 1.0;
+        }
+    std::vector<int> obj(n_obj), bufi(n_obj);
+    for (int o = 0; o < n_obj; ++o) { obj[o] = o; bufi[o] = (int)(rnd() * 40.0); }
+    pbso_batch* bt = nullptr;
+    int rc = pbso_batch_create(n_obj, n_modes, h, a.data(), b.data(), &bt);
+    std::vector<double> y64((size_t)buf * n_buf), ytc(y64.size());
+    if (!rc) rc = pbso_batch_set_transfer(bt, tr.data());
+    if (!rc) rc = pbso_batch_set_impulses(bt, n_obj, obj.data(), bufi.data(), sp.data());
+    if (!rc) rc = pbso_batch_render_mix(bt, buf, n_buf, PBSO_PREC_F64, 0, y64.data());
+    if (!rc) rc = pbso_batch_render_mix(bt, buf, n_buf, PBSO_PREC_TC3X, 0, ytc.data());
+    pbso_batch_destroy(bt);
+    g_calibrating = false;
+    if (rc) return rc;
+    double num = 0.0, den = 0.0;
+    for (size_t i = 0; i < y64.size(); ++i) { num += ytc[i] * y64[i]; den += y64[i] * y64[i]; }
+    const double gain = den > 0.0 ? num / den : 1.0;
+    if (!(gain > 0.999 && gain < 1.001)) return set_error(PBSO_ERR_CUDA, "tensor-core gain calibration out of range: %.9f", gain);
+    g_inv_gain[device & 63] = 1.0 / gain;
+    return PBSO_OK;
+}
+double tc_gain(int device) { return g_inv_gain[device & 63] != 0.0 ? 1.0 / g_inv_gain[device & 63] : 0.0; }
 
 }  // namespace pbso

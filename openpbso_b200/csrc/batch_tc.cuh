@@ -19,5 +19,6 @@ struct TcArgs {
 
 int tc_render(TcState** st, const TcArgs& a, int* launches);
 void tc_free(TcState* st);
+double tc_gain(int device);   // calibrated accumulate-truncation gain of the tensor-core path (0 = not calibrated yet)
 
 }  // namespace pbso

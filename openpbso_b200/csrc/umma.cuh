@@ -15,15 +15,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires) instead of
+// polling: a role that runs ahead of the pipeline must not spend issue slots and MIO-queue entries on failed probes
+// (profiles/r2_k_batch_tc.md: 76 probes per chunk and generator warp without it).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(

@@ -531,6 +531,59 @@ def test_batch_tc3x_many_events(pbso):
         br.render_mix(64, n_buf, pbso.PREC_TC3X)              # buf_size must be a multiple of the 128-sample tile
 
 
+@pytest.mark.parametrize("material", ["low_damping", "high_damping"])
+def test_batch_tc3x_and_f64_vs_oracle_full_length(pbso, orc, material):
+    """The headline configuration's shape side by side with the CPU oracle: 512 modes x 1723 buffers (10 s, 441 088
+    samples), 4 objects, both materials.  PREC_F64 must meet the oracle to 1e-9 of full scale, PREC_TC3X the north-star
+    tolerance (rel-L2 <= 1e-5, max-abs <= 1e-6 of full scale) over the whole waveform AND over its last second."""
+    n_obj, n_modes, n_buf = 4, 512, 1723
+    w = synth.batch_workload(n_obj, n_modes, n_buf, 1005, material)
+    ref = np.zeros(n_buf * 256)
+    import threading
+    parts = [np.zeros(n_buf * 256) for _ in range(n_obj)]
+    th = [threading.Thread(target=orc.batch_render, args=(H, w["a"][o:o + 1], w["b"][o:o + 1], w["space"][o:o + 1], w["trans"][o:o + 1],
+                                                         w["imp_buf"][o:o + 1], 256, n_buf, parts[o])) for o in range(n_obj)]
+    for t in th: t.start()
+    for t in th: t.join()
+    for part in parts: ref += part
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"])
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], w["space"])
+    y64 = br.render_mix(256, n_buf, pbso.PREC_F64)
+    assert_waveform_parity(y64, ref, rel=1e-9, mx=1e-9)
+    ytc = br.render_mix(256, n_buf, pbso.PREC_TC3X)
+    rel, mx = assert_waveform_parity(ytc, ref)
+    tail = slice(-44100, None)
+    assert np.linalg.norm(ytc[tail] - ref[tail]) <= 1e-5 * np.linalg.norm(ref[tail])
+    print("full length vs oracle (%s): tc3x rel-L2 %.2e max-abs %.2e" % (material, rel, mx))
+
+
+def test_batch_tc3x_longer_render_after_shorter(pbso):
+    """Regression (round-1 ADVICE): the cached unit list depends on the exact render length, not only on the number of
+    M-tiles -- render 100 buffers, then 120 (same M-tile count), then 40, on one handle with impulses in the added range."""
+    n_obj, n_modes = 6, 48
+    w = synth.batch_workload(n_obj, n_modes, 120, 31, "high_damping")
+    rng = np.random.default_rng(31)
+    obj = np.repeat(np.arange(n_obj), 3)
+    buf = np.concatenate([[3 + o, 104 + o, 117 - o] for o in range(n_obj)])
+    space = rng.standard_normal((len(obj), n_modes))
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"]); br.set_impulses(obj, buf, space)
+    for n_buf in (100, 120, 40, 120):
+        assert_waveform_parity(br.render_mix(256, n_buf, pbso.PREC_TC3X), br.render_mix(256, n_buf, pbso.PREC_F64))
+
+
+def test_batch_tc3x_object_batches(pbso, monkeypatch):
+    """Operand tables larger than the table budget: the renderer walks the objects in batches and rebuilds the tables per
+    batch; same waveform as the FP64 kernel."""
+    n_obj, n_modes, n_buf = 23, 40, 150
+    w = synth.batch_workload(n_obj, n_modes, n_buf, 77, "low_damping", first_second_bufs=100)
+    monkeypatch.setenv("PBSO_TC_TABLE_BYTES", str(5 * 3 * 5376))           # room for 5 objects (3 chunks each)
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"])
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], w["space"])
+    y64 = br.render_mix(256, n_buf, pbso.PREC_F64)
+    for _ in range(2):
+        assert_waveform_parity(br.render_mix(256, n_buf, pbso.PREC_TC3X), y64)
+
+
 def test_batch_tc3x_cfg1_golden(pbso, golden_dir):
     g = np.load(os.path.join(golden_dir, "cfg1_ball.npz"))
     a, b = synth.ab_from_material(synth.mode_frequencies(64, 1001), synth.MATERIALS["low_damping"])
