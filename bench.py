@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_OBJ, N_MODES, BUF, N_BUF = 4096, 512, 256, 1723      # cfg5: 441 088 samples = 10.0 s
-TC3X_DRAM_BYTES_PER_MODE_SAMPLE = 14.688e9 / 9.2504e11   # ncu --set full, cfg5 launch: 14.30 GB read + 0.38 GB written (profiles/r1_k_batch_tc.md)
+TC3X_DRAM_BYTES_PER_MODE_SAMPLE = 1.127e9 / 9.2504e11    # ncu --set full, cfg5 launch: 1.12 GB read + 0.007 GB written (profiles/r2_k_batch_tc.md)
 FLOP_PER_MODE_SAMPLE = 8.0                              # 4 FMA: 3 in Step (modal_integrator.h:109-110) + 1 in the dot (modal_solver.h:267-269)
 
 
@@ -53,12 +53,9 @@ def parse():
     ap.add_argument("--precision", default="tc3x", choices=["tc3x", "f32_tiled", "f64"])
     ap.add_argument("--no-realtime", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the K3/K4/K5/K6 micro-benchmarks folded in under 'kernels'")
+    ap.add_argument("--no-parity", action="store_true", help="skip the FP64 re-render of the job that 'parity' compares with")
     return ap.parse_args()
-
-
-def shard(n_obj, world, rank):
-    from openpbso_b200.shard import shard_range
-    return shard_range(n_obj, world, rank)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -366,11 +363,17 @@ def run_ours(args):
         dist.barrier()
     import openpbso_b200 as pbso
     from openpbso_b200 import synth
-    from openpbso_b200.shard import reduce_mix
     pbso.set_device(local)
     prec = {"f32_tiled": pbso.PREC_F32_TILED, "f64": pbso.PREC_F64, "tc3x": pbso.PREC_TC3X}[args.precision]
 
-    lo, hi = shard(args.objects, world, rank)
+    # the product's own multi-GPU path: pbso_comm_* (NCCL called from the C ABI on the render stream); torch.distributed
+    # only carries the 128-byte id to the ranks and the barriers / max-over-ranks of the measurement
+    comm = None
+    if world > 1:
+        uid = [pbso.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = pbso.Comm(world, rank, uid[0])
+    lo, hi = comm.shard(args.objects) if comm else (0, args.objects)
     n_local = hi - lo
     # synthetic workload: generated per rank for its own shard (seeded by object range)
     w = synth.batch_workload(args.objects, args.modes, args.buffers, 1005)
@@ -394,9 +397,10 @@ def run_ours(args):
     mix = torch.zeros(n_samples, dtype=torch.float64, device="cuda")     # also the NCCL send buffer
     mix_host = torch.empty(n_samples, dtype=torch.float64, pin_memory=True)
 
-    def step_device():
-        br.render_mix_device(BUF, args.buffers, mix.data_ptr(), prec)
-        reduce_mix(mix, 0)
+    def step_device(precision=prec):
+        br.render_mix_device(BUF, args.buffers, mix.data_ptr(), precision)
+        if comm:
+            comm.reduce_audio(mix.data_ptr(), n_samples, 0, stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -420,7 +424,8 @@ def run_ours(args):
         ev[k][0].record(stream)
         step_device()
         ev[k][1].record(stream)
-        kernel_ms.append(br.last_kernel_ms()[0])       # syncs on the render kernel's own event pair
+        km, launches_per_render = br.last_kernel_ms()   # syncs on the render kernels' own event pair
+        kernel_ms.append(km)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.mark_end()
@@ -456,9 +461,24 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(h2d_t, op=dist.ReduceOp.SUM)
 
+    # ---- parity of the timed configuration itself: the same job re-rendered by the FP64 direct-form kernel (the
+    # reference's arithmetic: modal_integrator.h:109-110 + modal_solver.h:267-269), reduced the same way -----------
+    parity = None
+    if not args.no_parity and prec != pbso.PREC_F64:
+        y_fast = mix.clone() if rank == 0 else None              # rank 0 holds the reduced mix of the last step
+        step_device(pbso.PREC_F64)
+        torch.cuda.synchronize()
+        if rank == 0:
+            d = (y_fast - mix)
+            full = mix.abs().max().item()
+            tail = slice(-44100, None)
+            parity = {"vs": "k_batch_f64 (FP64 direct-form kernel, same %d objects, reduced over the same ranks)" % args.objects,
+                      "rel_l2": (d.norm() / mix.norm()).item(), "max_abs": d.abs().max().item() / full,
+                      "rel_l2_last_second": (d[tail].norm() / mix[tail].norm()).item(),
+                      "tolerance": {"rel_l2": 1e-5, "max_abs": 1e-6}, "tc_gain_calibrated": pbso.tc_gain()}
     if rank != 0:
         if world > 1:
-            dist.barrier(); dist.destroy_process_group()
+            dist.barrier(); comm.close(); dist.destroy_process_group()
         return
     # ---- rank 0 only: peaks, roofline, CPU baseline, real-time latency -----------------------
     checksum = float(mix_host.abs().sum().item())
@@ -473,20 +493,23 @@ def run_ours(args):
     ms_local = float(n_local) * args.modes * n_samples
     achieved = ms_local * FLOP_PER_MODE_SAMPLE / (k_ms * 1e-3) / 1e12          # algorithmic: 8 FLOP per mode-sample
     nominal_fp32 = info["sm_count"] * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+    tf32_peak_measured, tf32_cyc, _ = pbso.measure_tc_peak(0, 1, 128)
     if prec == pbso.PREC_TC3X:
         # tensor-pipe roofline: the kernel issues 3 TF32 MMAs (hi*hi, hi*lo, lo*hi) per product and 2 K columns per
-        # mode (Re, Im of the tile-start state), i.e. 12 tensor FLOP per mode-sample.  No TF32 figure exists in
-        # MEASURED_PEAKS.json: kind::tf32 runs at half the kind::f16 rate, so the denominator is half the measured
-        # cuBLAS bf16 burst rate.
+        # mode (Re, Im of the tile-start state), i.e. 12 tensor FLOP per mode-sample.  The denominator is the kind::tf32
+        # rate of a bare tcgen05.mma loop measured in THIS run (pbso_measure_tc_peak: one persistent CTA per SM, A in
+        # TMEM, B in shared memory, nothing else running); half the cuBLAS bf16 burst figure of MEASURED_PEAKS.json is
+        # reported beside it (MEASURED_PEAKS.json has no TF32 number).
         issued = ms_local * 12.0 / (k_ms * 1e-3) / 1e12
-        tf32_peak = 0.5 * float(peaks.get("bf16_tflops", 1590.0))
-        roofline = {"bound": "tensor", "kernel": "k_batch_tc<split=1,chain=2> (tcgen05 kind::tf32, 3xTF32)", "achieved": issued,
-                    "peak": tf32_peak, "unit": "TFLOP/s", "frac": issued / tf32_peak,
+        half_bf16 = 0.5 * float(peaks.get("bf16_tflops", 1590.0))
+        roofline = {"bound": "tensor", "kernel": "k_batch_tc (tcgen05 kind::tf32, 3xTF32, 12 MMAs per 16-mode K chunk)", "achieved": issued,
+                    "peak": tf32_peak_measured, "unit": "TFLOP/s", "frac": issued / tf32_peak_measured,
                     "traffic": TC3X_DRAM_BYTES_PER_MODE_SAMPLE * ms_local if (TC3X_DRAM_BYTES_PER_MODE_SAMPLE and args.modes == N_MODES and args.buffers == N_BUF) else None,
                     "kernel_ms": k_ms,
-                    "peak_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (%s, burst): kind::tf32 issues at half the bf16 rate" % peaks_kind,
+                    "peak_source": "kind::tf32 peak measured in this run by pbso_measure_tc_peak (bare tcgen05.mma loop, %.1f cycles per 128x128x8 MMA)" % tf32_cyc,
+                    "frac_of_half_bf16_cublas": issued / half_bf16, "half_bf16_cublas_tflops": half_bf16, "half_bf16_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (%s, burst)" % peaks_kind,
                     "achieved_counts": "issued tensor FLOP: 3 MMAs x 2 K-columns x 2 FLOP = 12 per mode-sample",
-                    "traffic_source": "dram__bytes_read+write of one ncu --set full capture of this kernel, scaled per mode-sample (profiles/r1_k_batch_tc.md)",
+                    "traffic_source": "dram__bytes_read+write of one ncu --set full capture of this kernel, scaled per mode-sample (profiles/r2_k_batch_tc.md)",
                     "algorithmic_tflops": achieved, "algorithmic": "8 FLOP per mode-sample (reference recurrence + dot, SURVEY 8d)",
                     "fp32_fma_peak": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak, "peak_nominal_fp32": nominal_fp32,
                     "fma_microbench_tflops": fma}
@@ -503,7 +526,7 @@ def run_ours(args):
         "metric": "mode-samples/s (IIR+FFAT)", "value": value, "unit": "mode-samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": {pbso.PREC_TC3X: "tf32x3 (tensor cores, fp32 accumulate) + f64 carrier", pbso.PREC_F32_TILED: "f32 tiles + f64 carrier"}.get(prec, "f64"),
+        "dtype": {pbso.PREC_TC3X: "tf32x3 (tcgen05 kind::tf32 hi/lo split, fp32 accumulate) + f64 carrier", pbso.PREC_F32_TILED: "f32 tiles + f64 carrier"}.get(prec, "f64"),
         "data": "synthetic",
         "config": {"workload": "cfg5 offline batch: %d objects x %d modes x %d samples (%d buffers of %d), one PointForce "
                                "per object, static listeners, mixed down" % (args.objects, args.modes, n_samples, args.buffers, BUF),
@@ -511,11 +534,21 @@ def run_ours(args):
                    "l2": "flushed with a 256 MiB write between timed steps; per-step inputs %.0f MB" % (
                        (7 * a.size * 8 + space_h.nbytes) / 1e6),
                    "mix_abs_sum": checksum},
-        "roofline": roofline, "clocks": clocks, "gpu_launches": args.steps * world * (2 if prec == pbso.PREC_TC3X else 1),
+        "roofline": roofline, "clocks": clocks, "gpu_launches": args.steps * world * int(launches_per_render),
+        "gpu_launches_note": "kernels of libpbso_b200.so inside the timed region: %d per render and rank (tc3x: k_tc_carrier, k_tc_impulse, k_batch_tc)" % int(launches_per_render),
         "e2e": {"value": e2e_value, "unit": "mode-samples/s", "h2d_bytes_per_step": int(h2d_t.item()),
                 "d2h_bytes_per_step": int(mix_host.numel() * 8), "ms_per_step": 1e3 * e2e_t.item() / args.steps},
         "wall_ms_per_step": 1e3 * t_wall / args.steps, "peaks": {"source": peaks_kind, "hbm_gbs": peaks.get("hbm_gbs")},
     }
+    if parity:
+        line["parity"] = parity
+    if comm:
+        line["config"]["parallelism"] = ("objects block-partitioned over %d ranks (pbso_comm_shard); one ncclReduce(sum) of the FP64 mix issued by "
+                                         "pbso_comm_reduce_audio on the render stream (NCCL %d)" % (world, comm.nccl_version()))
+    if not args.no_kernels and world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_kernels
+        line["kernels"] = bench_kernels.run_all(tf32_peak=tf32_peak_measured)
     if not args.no_cpu_baseline:
         model, cores = cpu_info()
         ms, dt = cpu_render_sample(cores, 1, args.modes, args.buffers, 1005)
@@ -530,7 +563,7 @@ def run_ours(args):
         line["moving_listeners"] = moving_listeners_latency(pbso, synth)
     emit(line)
     if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+        dist.barrier(); comm.close(); dist.destroy_process_group()
 
 
 _JSON_FD = None

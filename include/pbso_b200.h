@@ -50,6 +50,7 @@ typedef struct pbso_integrator pbso_integrator;  /* ModalIntegrator<double> + pe
 typedef struct pbso_ffat pbso_ffat;              /* std::map<int, FFAT_Map<double,3>> */
 typedef struct pbso_modes pbso_modes;            /* ModeData<double>::_modes on the device */
 typedef struct pbso_batch pbso_batch;            /* many independent sound objects, offline */
+typedef struct pbso_comm pbso_comm;              /* the ranks of a multi-GPU render (one NCCL communicator) */
 
 /* ---- library / device ----------------------------------------------------------------- */
 int pbso_abi_version(void);
@@ -233,6 +234,23 @@ int pbso_batch_set_stream(pbso_batch* bt, void* cuda_stream);
 int pbso_tc_gain(double* gain);
 /* CUDA-event time of the last render kernel(s) on the handle's stream, and launches issued. */
 int pbso_batch_last_kernel_ms(pbso_batch* bt, float* ms, int* launches);
+
+/* ---- multi-GPU: object / mode-block sharding and the audio reduce -------------
+ * Sound objects are independent, and so are the modes of one object (the reference's hot loop is a sum over modes,
+ * modal_solver.h:261-272): every rank renders a contiguous block of (object, mode block) units into its own FP64 mix,
+ * and one sum-reduce of the audio is the only exchange.  One rank per GPU; NCCL (libnccl.so.2) is loaded on first use.
+ *   pbso_comm_unique_id   rank 0 creates the 128-byte id, the caller hands it to every rank (file, socket, MPI ...)
+ *   pbso_comm_init        collective; binds the communicator to the calling thread's current device
+ *   pbso_comm_shard       this rank's block [lo, hi) of n_units; the blocks tile [0, n_units)
+ *   pbso_comm_reduce_audio  d_audio[n] (double, device) summed over the ranks onto `root` in place (root = -1: onto
+ *                         every rank), enqueued on cuda_stream -- the stream the render was enqueued on, so no host
+ *                         synchronisation sits between render and reduce */
+int pbso_comm_unique_id(unsigned char* id128);
+int pbso_comm_init(int nranks, int rank, const unsigned char* id128, pbso_comm** out);
+int pbso_comm_destroy(pbso_comm* c);
+int pbso_comm_info(const pbso_comm* c, int* nranks, int* rank, int* nccl_version);
+int pbso_comm_shard(const pbso_comm* c, long long n_units, long long* lo, long long* hi);
+int pbso_comm_reduce_audio(pbso_comm* c, double* d_audio, size_t n, int root, void* cuda_stream);
 
 /* ---- measurement helpers (device micro-benchmarks used by bench.py for roofline peaks) -- */
 /* kind 0: FP32 FFMA (uniform operands); 1: packed fma.rn.f32x2 (uniform operands); 2: FP64 DFMA;

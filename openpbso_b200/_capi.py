@@ -100,6 +100,12 @@ def lib():
             "pbso_batch_sync": [vp],
             "pbso_batch_set_stream": [vp, vp],
             "pbso_batch_last_kernel_ms": [vp, c_fp, c_ip],
+            "pbso_comm_unique_id": [C.POINTER(C.c_ubyte)],
+            "pbso_comm_init": [C.c_int, C.c_int, C.POINTER(C.c_ubyte), c_vpp],
+            "pbso_comm_destroy": [vp],
+            "pbso_comm_info": [vp, c_ip, c_ip, c_ip],
+            "pbso_comm_shard": [vp, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
+            "pbso_comm_reduce_audio": [vp, vp, C.c_size_t, C.c_int, vp],
             "pbso_measure_fma_peak": [C.c_int, c_dp, c_dp],
             "pbso_measure_tc_peak": [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp],
             "pbso_tc_selftest": [C.c_int, c_dp],

@@ -56,6 +56,45 @@ def flush_l2(nbytes=256 << 20):
     check(lib().pbso_flush_l2(nbytes))
 
 
+class Comm:
+    """The ranks of a multi-GPU render: pbso_comm_* (NCCL from the C ABI).  `unique_id()` on rank 0, hand the 128
+    bytes to every rank, then Comm(nranks, rank, id) on each (collective)."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        check(lib().pbso_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, nranks, rank, uid=None):
+        self._h = C.c_void_p()
+        buf = (C.c_ubyte * 128).from_buffer_copy(uid) if uid is not None else None
+        check(lib().pbso_comm_init(nranks, rank, buf, C.byref(self._h)))
+        self.nranks, self.rank = nranks, rank
+
+    def shard(self, n_units):
+        lo = C.c_longlong(); hi = C.c_longlong()
+        check(lib().pbso_comm_shard(self._h, n_units, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def nccl_version(self):
+        n = C.c_int(); r = C.c_int(); v = C.c_int()
+        check(lib().pbso_comm_info(self._h, C.byref(n), C.byref(r), C.byref(v)))
+        return v.value
+
+    def reduce_audio(self, d_ptr, n, root=0, stream=None):
+        """Sum of the ranks' double[n] at device pointer d_ptr onto `root` (-1: every rank), enqueued on `stream`."""
+        check(lib().pbso_comm_reduce_audio(self._h, C.c_void_p(d_ptr), n, root, C.c_void_p(stream) if stream else None))
+
+    def close(self):
+        if self._h:
+            lib().pbso_comm_destroy(self._h); self._h = C.c_void_p()
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+
 class ModalIntegrator:
     """ModalIntegrator<double> (modal_integrator.h:19-45) + the ModalSolver::step hot loop."""
 

@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s" % src)
         if verbose:
             sys.stdout.write(out)
-    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     return OUT
 
 

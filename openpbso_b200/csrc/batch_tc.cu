@@ -276,9 +276,8 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
 #pragma unroll 1
             for (uint32_t q = 0; q < n_chunks; ++q) {
                 const uint32_t buf = q & 1, sa = q % TCB_NA, sb = q % TCB_NB;
-                // the two waits of a chunk ride one instruction: even lanes probe the accumulator, odd lanes the operand stage
-                mbar_wait(lane & 1 ? &b_full[sb] : &acc_empty[buf], lane & 1 ? (q / TCB_NB) & 1 : ((q >> 1) & 1) ^ 1);
-                __syncwarp();
+                mbar_wait(&acc_empty[buf], ((q >> 1) & 1) ^ 1);
+                mbar_wait(&b_full[sb], (q / TCB_NB) & 1);
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint32_t acc = tmem_base + buf * TCB_L;
@@ -443,6 +442,12 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                         hi[4 * m2 + c] = bits; lo[4 * m2 + c] = __float_as_uint(l) + 0x1000u;
                     }
                 }
+                // the slots are released only once every loaded value has been USED: a release issued right behind the loads
+                // can overtake them in the MIO queue, and the seed warp refills its slot within tens of cycles
+#pragma unroll
+                for (int m = 0; m < 32; m += 8)
+                    asm volatile("" ::"r"(hi[m]), "r"(hi[m + 1]), "r"(hi[m + 2]), "r"(hi[m + 3]), "r"(hi[m + 4]), "r"(hi[m + 5]), "r"(hi[m + 6]), "r"(hi[m + 7]),
+                                 "r"(lo[m]), "r"(lo[m + 1]), "r"(lo[m + 2]), "r"(lo[m + 3]), "r"(lo[m + 4]), "r"(lo[m + 5]), "r"(lo[m + 6]), "r"(lo[m + 7]) : "memory");
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&s_empty[ss]); mbar_arrive(&t_empty[ts]); }
                 mbar_wait(&b_empty[sa], ((q / TCB_NA) & 1) ^ 1);

@@ -535,7 +535,8 @@ def test_batch_tc3x_many_events(pbso):
 def test_batch_tc3x_and_f64_vs_oracle_full_length(pbso, orc, material):
     """The headline configuration's shape side by side with the CPU oracle: 512 modes x 1723 buffers (10 s, 441 088
     samples), 4 objects, both materials.  PREC_F64 must meet the oracle to 1e-9 of full scale, PREC_TC3X the north-star
-    tolerance (rel-L2 <= 1e-5, max-abs <= 1e-6 of full scale) over the whole waveform AND over its last second."""
+    tolerance (rel-L2 <= 1e-5, max-abs <= 1e-6 of full scale) over the whole waveform AND, where the signal is still
+    inside FP32's range, over its last second alone."""
     n_obj, n_modes, n_buf = 4, 512, 1723
     w = synth.batch_workload(n_obj, n_modes, n_buf, 1005, material)
     ref = np.zeros(n_buf * 256)
@@ -553,7 +554,8 @@ def test_batch_tc3x_and_f64_vs_oracle_full_length(pbso, orc, material):
     ytc = br.render_mix(256, n_buf, pbso.PREC_TC3X)
     rel, mx = assert_waveform_parity(ytc, ref)
     tail = slice(-44100, None)
-    assert np.linalg.norm(ytc[tail] - ref[tail]) <= 1e-5 * np.linalg.norm(ref[tail])
+    if np.linalg.norm(ref[tail]) > 1e-30 * np.linalg.norm(ref):      # high damping: the last second is below FP32's range (e^-135)
+        assert np.linalg.norm(ytc[tail] - ref[tail]) <= 1e-5 * np.linalg.norm(ref[tail])
     print("full length vs oracle (%s): tc3x rel-L2 %.2e max-abs %.2e" % (material, rel, mx))
 
 
