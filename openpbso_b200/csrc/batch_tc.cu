@@ -36,8 +36,10 @@
 //    error of ~2e-7) is measured once per device by tc_calibrate() -- the same kernel on a synthetic batch against
 //    the FP64 direct-form kernel -- and divided out at the flush.
 //
-// CTA = 16 warps: warp 0 issues the MMAs, warp 1 lane 0 is the loader, warps 2-3 compute seeds (alternating
-// chunks), warps 4-7 drain TMEM (epilogue), warps 8-11 / 12-15 generate A for even / odd chunks.
+// CTA = 24 warps, ordered by how much the pipeline waits for them (the scheduler prefers the higher warp id of a
+// sub-partition): warps 0-7 generate A and warps 8-15 generate B (two groups of four each, alternate K chunks; they run
+// ahead of the MMAs), warps 16-19 drain TMEM (epilogue), warps 20-21 issue the MMAs (even / odd K chunks), warp 22 computes
+// the seeds, warp 23 lane 0 is the table loader.  setmaxnreg: 64 / 64 / 64 / 64 / 168 / 56 registers per thread of the six warp groups.
 // TMEM (512 columns): accumulators 0..127 | 128..255, four A stages of 64 columns (hi 32 | lo 32) at 256.
 // =============================================================================
 #include "common.cuh"
@@ -59,11 +61,11 @@ constexpr int TCB_ROWS = 128;              // tiles per M-tile = M of the MMA
 constexpr int TCB_KMODES = 16;             // modes per K chunk (K = 32 fp32 = one 128-byte swizzle row)
 constexpr int TCB_TILE_BYTES = 128 * 32 * 4;
 constexpr int TCB_BT_BYTES = 2 * TCB_TILE_BYTES;        // one chunk of operand B in shared memory: hi tile | lo tile
-constexpr int TCB_THREADS = 512;
+constexpr int TCB_THREADS = 768;              // 24 warps, see the role table at k_batch_tc
 constexpr int TCB_TMEM_COLS = 512;
 constexpr int TCB_NB = 4;                  // B stages
 constexpr int TCB_NA = 4;                  // A stages in TMEM
-constexpr int TCB_NT = 6;                  // table slots (requested well ahead: the copy latency is what the ring hides)
+constexpr int TCB_NT = 8;                  // table slots (requested well ahead: the copy latency is what the ring hides)
 constexpr int TCB_NS = 4;                  // seed slots
 constexpr int TCB_RSTRIDE = 144;                        // bytes between the R rows of a table block (128 + 16: 16 rows spread over all banks)
 constexpr int TCB_TABG_BYTES = 1024 + 17 * TCB_RSTRIDE + 2048;   // per chunk in HBM: P[8 blk][16 m] | R[16 j + a zero row][16 m (+pad)] | tabB[16 entries][16 m], float2
@@ -220,11 +222,35 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// acc[0..15] (packed column pairs) += 32 consecutive TMEM columns of this thread's lane, round-to-nearest FP32 adds.
+// One asm block: the 32 loaded registers are consumed pairwise by add.rn.f32x2 without leaving the register pairs the
+// load wrote (no packing moves).
+__device__ __forceinline__ void tmem_ld_add_32x32(uint32_t taddr, c32* acc) {
+    asm volatile(
+        "{\n\t.reg .b32 t<32>;\n\t.reg .b64 p<16>;\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, "
+        "t16, t17, t18, t19, t20, t21, t22, t23, t24, t25, t26, t27, t28, t29, t30, t31}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n\t"
+        "mov.b64 p0, {t0, t1};\n\tmov.b64 p1, {t2, t3};\n\tmov.b64 p2, {t4, t5};\n\tmov.b64 p3, {t6, t7};\n\t"
+        "mov.b64 p4, {t8, t9};\n\tmov.b64 p5, {t10, t11};\n\tmov.b64 p6, {t12, t13};\n\tmov.b64 p7, {t14, t15};\n\t"
+        "mov.b64 p8, {t16, t17};\n\tmov.b64 p9, {t18, t19};\n\tmov.b64 p10, {t20, t21};\n\tmov.b64 p11, {t22, t23};\n\t"
+        "mov.b64 p12, {t24, t25};\n\tmov.b64 p13, {t26, t27};\n\tmov.b64 p14, {t28, t29};\n\tmov.b64 p15, {t30, t31};\n\t"
+        "add.rn.f32x2 %0, %0, p0;\n\tadd.rn.f32x2 %1, %1, p1;\n\tadd.rn.f32x2 %2, %2, p2;\n\tadd.rn.f32x2 %3, %3, p3;\n\t"
+        "add.rn.f32x2 %4, %4, p4;\n\tadd.rn.f32x2 %5, %5, p5;\n\tadd.rn.f32x2 %6, %6, p6;\n\tadd.rn.f32x2 %7, %7, p7;\n\t"
+        "add.rn.f32x2 %8, %8, p8;\n\tadd.rn.f32x2 %9, %9, p9;\n\tadd.rn.f32x2 %10, %10, p10;\n\tadd.rn.f32x2 %11, %11, p11;\n\t"
+        "add.rn.f32x2 %12, %12, p12;\n\tadd.rn.f32x2 %13, %13, p13;\n\tadd.rn.f32x2 %14, %14, p14;\n\tadd.rn.f32x2 %15, %15, p15;\n\t}"
+        : "+l"(acc[0]), "+l"(acc[1]), "+l"(acc[2]), "+l"(acc[3]), "+l"(acc[4]), "+l"(acc[5]), "+l"(acc[6]), "+l"(acc[7]),
+          "+l"(acc[8]), "+l"(acc[9]), "+l"(acc[10]), "+l"(acc[11]), "+l"(acc[12]), "+l"(acc[13]), "+l"(acc[14]), "+l"(acc[15])
+        : "r"(taddr) : "memory");
+}
+
 // =============================================================================================================
+template <int EPI>
 __global__ void __launch_bounds__(TCB_THREADS, 1)
 k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Unit* __restrict__ units,
            const uint8_t* __restrict__ tab, const float2* __restrict__ V, int obj0,
-           double* __restrict__ mix, double inv_gain, int ablate) {
+           double* __restrict__ mix, double inv_gain, int ablate, unsigned long long* __restrict__ prof) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* tabs = smem + TCB_NB * TCB_BT_BYTES;
@@ -238,12 +264,17 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
     uint64_t* s_empty = s_full + TCB_NS;           // [NS] consumed (4 A-generator warps)
     uint64_t* a_full = s_empty + TCB_NS;           // [NA] A stage stored to TMEM (4 generator warps)
     uint64_t* a_empty = a_full + TCB_NA;           // [NA] MMAs reading it retired
-    uint64_t* acc_full = a_empty + TCB_NA;         // [2]  chunk's MMAs finished
+    uint64_t* acc_full = a_empty + TCB_NA;         // [2]  chain's MMAs finished
     uint64_t* acc_empty = acc_full + 2;            // [2]  drained (4 epilogue warps)
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u0 = cta_first[blockIdx.x], u1 = cta_first[blockIdx.x + 1];
+    // optional in-kernel timing (PBSO_TC_PROF=1): cycles every role of CTA 0 spends in each of its barrier waits
+    unsigned long long pw[4] = {0ull, 0ull, 0ull, 0ull};
+    const bool profiling = prof != nullptr && blockIdx.x == 0;
+    const long long t_role0 = clock64();
+#define PBSO_TW(slot, stmt) do { if (profiling) { const long long t_ = clock64(); stmt; pw[slot] += (unsigned long long)(clock64() - t_); } else { stmt; } } while (0)
     const int cpu = (n_modes + TCB_KMODES - 1) / TCB_KMODES;          // K chunks per unit
     const int mp = cpu * TCB_KMODES;
 
@@ -255,7 +286,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == 20) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCB_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -264,40 +295,231 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (warp == 0) {
-            // ---------------- MMA issuer ----------------
-            // The whole warp runs the loop so that every operand stays warp-uniform; one elected lane issues.
-            // Per K chunk: its 8 small products first (hi*lo, lo*hi), then the 4 hi*hi MMAs on top, one accumulator.
+        // ---------------- A generators: thread = row (TMEM lane); A[row][2m..2m+1] = X[blk][m] * R[j][m] ----------------
+        // Two groups of four warps (0-3, 4-7) take alternate K chunks: a generator warp is a long dependent chain per
+        // chunk (loads, packed complex products, splits, TMEM stores, three barrier round trips), and one group alone
+        // cannot turn a chunk around in the 768 cycles its MMAs take.  Per mode two 16-byte loads -- X4 = (xr, xr, xi, xi)
+        // from the seed slot (two addresses per warp: broadcast), R4 = (rr, ri, -ri, rr) straight from the table slot -- feed
+        // ONE mul.f32x2 + fma.f32x2; an impulse unit's rows before the impulse read the zero row.  A chunk is generated in
+        // two halves of 8 modes (32 registers each).
+        const int grp = warp >> 2, wq = warp & 3;
+        const int row = wq * 32 + lane, blk = row >> 4, j = row & 15;
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        uint32_t q = 0;
+#pragma unroll 1
+        for (int u = u0; u < u1; ++u) {
+            const int re = units[u].re;
+            int jj = j;
+            if (re >= 0 && blk == (re >> 4)) { jj = j - (re & 15); if (jj < 0) jj = 16; }   // impulse unit: rows of block ae are shifted by be; row 16 = 0
+#pragma unroll 1
+            for (int ch = 0; ch < cpu; ++ch, ++q) {
+                if ((int)(q & 1) != grp) continue;
+                const uint32_t ss = q % TCB_NS, sa = q % TCB_NA, ts = q % TCB_NT;
+                PBSO_TW(0, mbar_wait(&t_full[ts], (q / TCB_NT) & 1));
+                PBSO_TW(1, mbar_wait(&s_full[ss], (q / TCB_NS) & 1));
+                const uint32_t sX = smem_u32(seeds) + ss * TCB_SEED_BYTES + blk * 128;
+                const uint32_t sR = smem_u32(tabs) + ts * TCB_TAB_BYTES + TCB_TAB_R + jj * TCB_RSTRIDE;
+                const uint32_t a_col = tmem_base + lane_off + 256 + sa * 64;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int m2 = 0; m2 < 4; ++m2) {
+                        float4 x, r;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(sX + (4 * hf + m2) * 16));
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sR + (4 * hf + m2) * 16));
+                        float v[4];
+                        v[0] = fmaf(-x.y, r.y, x.x * r.x); v[1] = fmaf(x.x, r.y, x.y * r.x);
+                        v[2] = fmaf(-x.w, r.w, x.z * r.z); v[3] = fmaf(x.z, r.w, x.w * r.z);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            // hi = the raw value (the tensor core reads its upper 19 bits); lo = what those bits miss (the tensor
+                            // core truncates it to TF32: a mean shift of the gain that tc_calibrate() measures with everything else)
+                            const uint32_t bits = __float_as_uint(v[c]);
+                            hi[4 * m2 + c] = bits;
+                            lo[4 * m2 + c] = __float_as_uint(v[c] - __uint_as_float(bits & 0xFFFFE000u));
+                        }
+                    }
+                    if (hf == 0) {
+                        PBSO_TW(2, mbar_wait_relaxed(&b_empty[sa], ((q / TCB_NA) & 1) ^ 1));
+                        tcgen05_fence_after();
+                    } else {
+                        // the slots are released only once every loaded value has been USED: a release issued right behind the
+                        // loads can overtake them in the MIO queue, and the seed warp refills its slot within tens of cycles
+                        asm volatile("" ::"r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]),
+                                     "r"(hi[8]), "r"(hi[9]), "r"(hi[10]), "r"(hi[11]), "r"(hi[12]), "r"(hi[13]), "r"(hi[14]), "r"(hi[15]) : "memory");
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive(&s_empty[ss]); mbar_arrive(&t_empty[ts]); }
+                    }
+                    tmem_st_32x16(a_col + 16 * hf, hi);
+                    tmem_st_32x16(a_col + 32 + 16 * hf, lo);
+                }
+                PBSO_TW(3, tmem_st_wait());
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[sa]);
+            }
+        }
+    } else if (warp < 16) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // ---------------- B generators: thread = (mode of the chunk, 16-row block); rows 4t + c = x Rt[t] Rc[c] ----------------
+        // two groups of four warps (8-11, 12-15) take alternate K chunks, like the A generators
+        // straight into the UMMA K-major 128-byte-swizzle layout: row r = 16 blk + b, K columns (2 m, 2 m + 1) at byte
+        // (r / 8) 1024 + (r % 8) 128 + (((m / 2) ^ (r % 8)) 16) + (m % 2) 8; the eight swizzled offsets of a thread never change
+        const int m_l = lane & 15, bgrp = (warp - 8) >> 2, blk = ((warp - 8) & 3) * 2 + (lane >> 4);
+        uint32_t xoff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xoff[i] = sw128_pair(16 * blk + i, m_l);
+        const uint32_t n_chunks = (uint32_t)(u1 - u0) * (uint32_t)cpu;
+#pragma unroll 1
+        for (uint32_t q = (uint32_t)bgrp; q < n_chunks; q += 2) {
+            const uint32_t sb = q % TCB_NB, ts = q % TCB_NT;
+            PBSO_TW(0, mbar_wait(&t_full[ts], (q / TCB_NT) & 1));
+            const uint32_t tB = smem_u32(tabs) + ts * TCB_TAB_BYTES + TCB_TAB_B + m_l * 8;   // entry e at tB + 128 e
+            const float2 ra = lds_f2(tB + 128 * blk);
+            float2 rt[3], rc[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { rt[t] = lds_f2(tB + 128 * (8 + t)); rc[t] = lds_f2(tB + 128 * (11 + t)); }
+            // broadcast pairs of the step powers: p * q = (pr, pr) * q + (pi, pi) * (i q)
+            c32 rtr[3], rti[3], rcr[3], rci[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { rtr[t] = pk(rt[t].x, rt[t].x); rti[t] = pk(rt[t].y, rt[t].y); rcr[t] = pk(rc[t].x, rc[t].x); rci[t] = pk(rc[t].y, rc[t].y); }
+            const c32 xa = pk(ra.x, ra.y), xar = pk(-ra.y, ra.x);
+            PBSO_TW(1, mbar_wait_relaxed(&b_empty[sb], ((q / TCB_NB) & 1) ^ 1));
+            const uint32_t st = smem_u32(smem) + sb * TCB_BT_BYTES;
+            if (!(ablate & 1)) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const c32 pt = t == 0 ? xa : fma2(rti[t - 1], xar, mul2(rtr[t - 1], xa));
+                    float pr, pi; upk(pt, pr, pi);
+                    const c32 ptr_ = pk(-pi, pr);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const c32 v = c == 0 ? pt : fma2(rci[c - 1], ptr_, mul2(rcr[c - 1], pt));
+                        float vr, vi; upk(v, vr, vi);
+                        const uint32_t br = __float_as_uint(vr), bi = __float_as_uint(vi);
+                        const c32 tt = pk(__uint_as_float(br & 0xFFFFE000u), __uint_as_float(bi & 0xFFFFE000u));
+                        float lr, li; upk(sub2(v, tt), lr, li);
+                        const int b = 4 * t + c;
+                        const uint32_t addr = st + xoff[b & 7] + (uint32_t)(b >> 3) * 1024u;
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(br), "r"(bi) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + TCB_TILE_BYTES), "f"(lr), "f"(li) : "memory");
+                    }
+                }
+            }
+            PBSO_TW(2, fence_proxy_async_smem());
+            __syncwarp();
+            // the table slot is released only here: its loads are certainly complete once their values have been used
+            if (lane == 0) { mbar_arrive(&t_empty[ts]); mbar_arrive(&b_full[sb]); }
+        }
+    } else if (warp < 20) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        // ---------------- epilogue: promote finished chains into registers, flush to the FP64 mix ----------------
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        c32 acc[TCB_L / 2];                                                  // packed pairs of columns
+#pragma unroll
+        for (int j = 0; j < TCB_L / 2; ++j) acc[j] = 0ull;
+        uint32_t g = 0;
+#pragma unroll 1
+        for (int u = u0; u < u1; ++u) {
+#pragma unroll 1
+            for (int ch = 0; ch < cpu; ch += 2, ++g) {
+                const int buf = g & 1;
+                PBSO_TW(0, mbar_wait(&acc_full[buf], (g >> 1) & 1));
+                tcgen05_fence_after();
+                if (!(ablate & 4)) {
+                    if (EPI == 1) {
+#pragma unroll
+                        for (int qd = 0; qd < TCB_L / 32; ++qd) tmem_ld_add_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), &acc[qd * 16]);
+                    } else {
+#pragma unroll
+                        for (int qd = 0; qd < TCB_L / 32; ++qd) {
+                            uint32_t vm[32];
+                            tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), vm);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float a, b; upk(acc[qd * 16 + j], a, b);
+                                acc[qd * 16 + j] = pk(a + __uint_as_float(vm[2 * j]), b + __uint_as_float(vm[2 * j + 1]));
+                            }
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+            const Unit un = units[u];
+            if (un.flush) {
+                const long long tile = (long long)un.it * TCB_ROWS + row;
+                if (tile < n_tiles) {
+                    double* dst = mix + tile * TCB_L;
+#pragma unroll
+                    for (int j = 0; j < TCB_L / 2; ++j) {
+                        float a, b; upk(acc[j], a, b);
+                        atomicAdd(dst + 2 * j, (double)a * inv_gain);
+                        atomicAdd(dst + 2 * j + 1, (double)b * inv_gain);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < TCB_L / 2; ++j) acc[j] = 0ull;
+            }
+        }
+    } else {
+        // warps 20-23: the scheduler prefers the highest warp id of a sub-partition, and the MMA issuers are the warps the
+        // whole pipeline waits for
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp < 22) {
+            // ---------------- MMA issuers: warp 20 takes the even chains (accumulator 0), warp 21 the odd ones ----------------
+            // A chain = two K chunks of a unit (one at an odd tail): the 16 small products of both chunks first (hi*lo, lo*hi
+            // -- their accumulate-truncation is relative to a 2^-11 smaller sum), then the 8 hi*hi MMAs on top, ONE accumulator,
+            // drained once: reading TMEM back costs ~1000 cycles per 128 x 128 accumulator (64 B/clk), more than one chunk's
+            // 768 cycles of MMAs, so per-chunk draining would bound the kernel.  Issuing is serial work of one thread; two
+            // issuers keep the tensor pipe's queue fed while one of them is between chains.  The whole warp runs the loop
+            // so that every operand stays warp-uniform.
             constexpr uint32_t idesc = umma_idesc_tf32(TCB_ROWS, TCB_L);
             const uint64_t desc0 = umma_desc_k_sw128(smem_u32(smem));
-            const uint32_t n_chunks = (uint32_t)(u1 - u0) * (uint32_t)cpu;
+            const uint32_t cpp = (uint32_t)(cpu + 1) >> 1;                              // chains per unit
+            const uint32_t n_chains = (uint32_t)(u1 - u0) * cpp;
+            const uint32_t par = (uint32_t)(warp - 20);
+            const uint32_t acc = tmem_base + par * TCB_L;
 #pragma unroll 1
-            for (uint32_t q = 0; q < n_chunks; ++q) {
-                const uint32_t buf = q & 1, sa = q % TCB_NA, sb = q % TCB_NB;
-                mbar_wait(&acc_empty[buf], ((q >> 1) & 1) ^ 1);
-                mbar_wait(&b_full[sb], (q / TCB_NB) & 1);
+            for (uint32_t g = par; g < n_chains; g += 2) {
+                const uint32_t ui = g / cpp, ci = g - ui * cpp;
+                const uint32_t q0 = ui * (uint32_t)cpu + 2 * ci;
+                const uint32_t nc = (2 * ci + 1 < (uint32_t)cpu) ? 2u : 1u;
+                PBSO_TW(0, mbar_wait(&acc_empty[par], ((g >> 1) & 1) ^ 1));
+                PBSO_TW(1, mbar_wait(&b_full[q0 & 3], (q0 >> 2) & 1));
+                if (nc == 2) PBSO_TW(1, mbar_wait(&b_full[(q0 + 1) & 3], ((q0 + 1) >> 2) & 1));
                 tcgen05_fence_after();
                 if (elect_one()) {
-                    const uint32_t acc = tmem_base + buf * TCB_L;
-                    if (!(ablate & 8)) {
-                        const uint32_t a_hi = tmem_base + 256 + sa * 64, a_lo = a_hi + 32;
-                        const uint64_t dBh = desc0 + (uint64_t)(sb * (TCB_BT_BYTES >> 4)), dBl = dBh + (TCB_TILE_BYTES >> 4);
+                    for (uint32_t i = 0; i < nc; ++i) {
+                        const uint32_t st = (q0 + i) & 3;
+                        const uint32_t a_hi = tmem_base + 256 + st * 64, a_lo = a_hi + 32;
+                        const uint64_t dBh = desc0 + (uint64_t)(st * (TCB_BT_BYTES >> 4)), dBl = dBh + (TCB_TILE_BYTES >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_ts<0, 1>(acc, a_hi + 8 * k, dBl + 2 * k, idesc, k ? 1u : 0u);
+                            umma_ts<0, 1>(acc, a_hi + 8 * k, dBl + 2 * k, idesc, (i | (uint32_t)k) ? 1u : 0u);
                             umma_ts<0, 1>(acc, a_lo + 8 * k, dBh + 2 * k, idesc, 1u);
                         }
+                    }
+                    for (uint32_t i = 0; i < nc; ++i) {
+                        const uint32_t st = (q0 + i) & 3;
+                        const uint32_t a_hi = tmem_base + 256 + st * 64;
+                        const uint64_t dBh = desc0 + (uint64_t)(st * (TCB_BT_BYTES >> 4));
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_ts<0, 1>(acc, a_hi + 8 * k, dBh + 2 * k, idesc, 1u);
                     }
-                    umma_commit(&b_empty[sb]);
-                    umma_commit(&acc_full[buf]);
+                    for (uint32_t i = 0; i < nc; ++i) umma_commit(&b_empty[(q0 + i) & 3]);
+                    umma_commit(&acc_full[par]);
                 }
                 __syncwarp();
             }
-        } else if (warp == 1) {
+        } else if (warp == 23) {
             // ---------------- table loader: a chunk's 5 KB table block and its 16 tile-start states, NT chunks ahead ----------------
             if (lane == 0) {
                 uint32_t q = 0;
@@ -309,7 +531,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
 #pragma unroll 1
                     for (int ch = 0; ch < cpu; ++ch, ++q) {
                         const uint32_t ts = q % TCB_NT;
-                        mbar_wait(&t_empty[ts], ((q / TCB_NT) & 1) ^ 1);
+                        PBSO_TW(0, mbar_wait_relaxed(&t_empty[ts], ((q / TCB_NT) & 1) ^ 1));
                         mbar_expect_tx(&t_full[ts], TCB_TAB_BYTES);
                         const uint32_t tdst = smem_u32(tabs) + ts * TCB_TAB_BYTES;
                         bulk_g2s(tdst, tsrc + (size_t)ch * TCB_TABG_BYTES, TCB_TABG_BYTES, &t_full[ts]);
@@ -317,8 +539,8 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                     }
                 }
             }
-        } else if (warp == 2) {
-            // ---------------- seed warp: X[blk][m] = v W^(16 blk), the state at the start of every 16-row block ----------------
+        } else if (warp == 22) {
+            // ---------------- seed warp: X4[blk][m] = v W^(16 blk), the state at the start of every 16-row block ----------------
             const int m_l = lane & 15, half = lane >> 4;
             uint32_t q = 0;
 #pragma unroll 1
@@ -327,7 +549,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
 #pragma unroll 1
                 for (int ch = 0; ch < cpu; ++ch, ++q) {
                     const uint32_t ts = q % TCB_NT, ss = q % TCB_NS;
-                    mbar_wait(&t_full[ts], (q / TCB_NT) & 1);
+                    PBSO_TW(0, mbar_wait(&t_full[ts], (q / TCB_NT) & 1));
                     const uint32_t tP = smem_u32(tabs) + ts * TCB_TAB_BYTES, tR = tP + TCB_TAB_R, tV = tP + TCB_TABG_BYTES;
                     const float2 v = lds_f2(tV + m_l * 8);
                     float2 x[4];
@@ -352,7 +574,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                             x[i] = xx;
                         }
                     }
-                    mbar_wait(&s_empty[ss], ((q / TCB_NS) & 1) ^ 1);
+                    PBSO_TW(1, mbar_wait_relaxed(&s_empty[ss], ((q / TCB_NS) & 1) ^ 1));
                     const uint32_t sX = smem_u32(seeds) + ss * TCB_SEED_BYTES;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sX + (4 * half + i) * 128 + m_l * 8), "f"(x[i].x), "f"(x[i].y) : "memory");
@@ -361,161 +583,15 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                 }
             }
         }
-    } else if (warp < 8) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-        // ---------------- epilogue: promote finished chunks into registers, flush to the FP64 mix ----------------
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        float acc[TCB_L];
-#pragma unroll
-        for (int j = 0; j < TCB_L; ++j) acc[j] = 0.f;
-        uint32_t g = 0;
-#pragma unroll 1
-        for (int u = u0; u < u1; ++u) {
-#pragma unroll 1
-            for (int ch = 0; ch < cpu; ++ch, ++g) {
-                const int buf = g & 1;
-                mbar_wait(&acc_full[buf], (g >> 1) & 1);
-                tcgen05_fence_after();
-                if (!(ablate & 4)) {
-#pragma unroll
-                    for (int qd = 0; qd < TCB_L / 32; ++qd) {
-                        uint32_t vm[32];
-                        tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), vm);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[qd * 32 + j] += __uint_as_float(vm[j]);
-                    }
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            }
-            const Unit un = units[u];
-            if (un.flush) {
-                const long long tile = (long long)un.it * TCB_ROWS + row;
-                if (tile < n_tiles) {
-                    double* dst = mix + tile * TCB_L;
-#pragma unroll
-                    for (int j = 0; j < TCB_L; ++j) atomicAdd(dst + j, (double)acc[j] * inv_gain);
-                }
-#pragma unroll
-                for (int j = 0; j < TCB_L; ++j) acc[j] = 0.f;
-            }
-        }
-    } else if (warp < 12) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
-        // ---------------- A generators: thread = row (TMEM lane); A[row][2m..2m+1] = X[blk][m] * R[j][m] ----------------
-        // two modes per 16-byte load: X from the seed slot (two addresses per warp: broadcast), R straight from the table
-        // slot (16 rows 144 bytes apart: conflict-free); an impulse unit's rows before the impulse read the zero row.
-        const int wq = warp & 3;
-        const int row = wq * 32 + lane, blk = row >> 4, j = row & 15;
-        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-        uint32_t q = 0;
-#pragma unroll 1
-        for (int u = u0; u < u1; ++u) {
-            const int re = units[u].re;
-            int jj = j;
-            if (re >= 0 && blk == (re >> 4)) { jj = j - (re & 15); if (jj < 0) jj = 16; }   // impulse unit: rows of block ae are shifted by be; row 16 = 0
-#pragma unroll 1
-            for (int ch = 0; ch < cpu; ++ch, ++q) {
-                const uint32_t ss = q % TCB_NS, sa = q % TCB_NA, ts = q % TCB_NT;
-                mbar_wait(&t_full[ts], (q / TCB_NT) & 1);
-                mbar_wait(&s_full[ss], (q / TCB_NS) & 1);
-                const uint32_t sX = smem_u32(seeds) + ss * TCB_SEED_BYTES + blk * 128;
-                const uint32_t sR = smem_u32(tabs) + ts * TCB_TAB_BYTES + TCB_TAB_R + jj * TCB_RSTRIDE;
-                uint32_t hi[32], lo[32];
-#pragma unroll
-                for (int m2 = 0; m2 < TCB_KMODES / 2; ++m2) {
-                    float4 x, r;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(sX + m2 * 16));
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sR + m2 * 16));
-                    float v[4];
-                    v[0] = fmaf(-x.y, r.y, x.x * r.x); v[1] = fmaf(x.x, r.y, x.y * r.x);
-                    v[2] = fmaf(-x.w, r.w, x.z * r.z); v[3] = fmaf(x.z, r.w, x.w * r.z);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        // hi = the raw value (the tensor core reads its upper 19 bits); lo = what those bits miss, rounded to nearest
-                        const uint32_t bits = __float_as_uint(v[c]);
-                        const float l = __uint_as_float(bits) - __uint_as_float(bits & 0xFFFFE000u);
-                        hi[4 * m2 + c] = bits; lo[4 * m2 + c] = __float_as_uint(l) + 0x1000u;
-                    }
-                }
-                // the slots are released only once every loaded value has been USED: a release issued right behind the loads
-                // can overtake them in the MIO queue, and the seed warp refills its slot within tens of cycles
-#pragma unroll
-                for (int m = 0; m < 32; m += 8)
-                    asm volatile("" ::"r"(hi[m]), "r"(hi[m + 1]), "r"(hi[m + 2]), "r"(hi[m + 3]), "r"(hi[m + 4]), "r"(hi[m + 5]), "r"(hi[m + 6]), "r"(hi[m + 7]),
-                                 "r"(lo[m]), "r"(lo[m + 1]), "r"(lo[m + 2]), "r"(lo[m + 3]), "r"(lo[m + 4]), "r"(lo[m + 5]), "r"(lo[m + 6]), "r"(lo[m + 7]) : "memory");
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&s_empty[ss]); mbar_arrive(&t_empty[ts]); }
-                mbar_wait(&b_empty[sa], ((q / TCB_NA) & 1) ^ 1);
-                tcgen05_fence_after();
-                const uint32_t a_col = tmem_base + lane_off + 256 + sa * 64;
-                tmem_st_32x32(a_col, hi);
-                tmem_st_32x32(a_col + 32, lo);
-                tmem_st_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&b_full[sa]);
-            }
-        }
-    } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
-        // ---------------- B generators: thread = (mode of the chunk, 16-row block); rows 4t + c = x Rt[t] Rc[c] ----------------
-        // straight into the UMMA K-major 128-byte-swizzle layout: row r = 16 blk + b, K columns (2 m, 2 m + 1) at byte
-        // (r / 8) 1024 + (r % 8) 128 + (((m / 2) ^ (r % 8)) 16) + (m % 2) 8; the eight swizzled offsets of a thread never change
-        const int m_l = lane & 15, blk = (warp - 12) * 2 + (lane >> 4);
-        uint32_t xoff[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xoff[i] = sw128_pair(16 * blk + i, m_l);
-        const uint32_t n_chunks = (uint32_t)(u1 - u0) * (uint32_t)cpu;
-#pragma unroll 1
-        for (uint32_t q = 0; q < n_chunks; ++q) {
-            const uint32_t sb = q % TCB_NB, ts = q % TCB_NT;
-            mbar_wait(&t_full[ts], (q / TCB_NT) & 1);
-            const uint32_t tB = smem_u32(tabs) + ts * TCB_TAB_BYTES + TCB_TAB_B + m_l * 8;   // entry e at tB + 128 e
-            const float2 ra = lds_f2(tB + 128 * blk);
-            float2 rt[3], rc[3];
-#pragma unroll
-            for (int t = 0; t < 3; ++t) { rt[t] = lds_f2(tB + 128 * (8 + t)); rc[t] = lds_f2(tB + 128 * (11 + t)); }
-            // broadcast pairs of the step powers: p * q = (pr, pr) * q + (pi, pi) * (i q)
-            c32 rtr[3], rti[3], rcr[3], rci[3];
-#pragma unroll
-            for (int t = 0; t < 3; ++t) { rtr[t] = pk(rt[t].x, rt[t].x); rti[t] = pk(rt[t].y, rt[t].y); rcr[t] = pk(rc[t].x, rc[t].x); rci[t] = pk(rc[t].y, rc[t].y); }
-            const c32 xa = pk(ra.x, ra.y), xar = pk(-ra.y, ra.x);
-            mbar_wait(&b_empty[sb], ((q / TCB_NB) & 1) ^ 1);
-            const uint32_t st = smem_u32(smem) + sb * TCB_BT_BYTES;
-            if (!(ablate & 1)) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const c32 pt = t == 0 ? xa : fma2(rti[t - 1], xar, mul2(rtr[t - 1], xa));
-                    float pr, pi; upk(pt, pr, pi);
-                    const c32 ptr_ = pk(-pi, pr);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const c32 v = c == 0 ? pt : fma2(rci[c - 1], ptr_, mul2(rcr[c - 1], pt));
-                        float vr, vi; upk(v, vr, vi);
-                        const uint32_t br = __float_as_uint(vr), bi = __float_as_uint(vi);
-                        const c32 tt = pk(__uint_as_float(br & 0xFFFFE000u), __uint_as_float(bi & 0xFFFFE000u));
-                        float lr, li; upk(sub2(v, tt), lr, li);
-                        const int b = 4 * t + c;
-                        const uint32_t addr = st + xoff[b & 7] + (uint32_t)(b >> 3) * 1024u;
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(br), "r"(bi) : "memory");
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + TCB_TILE_BYTES), "r"(__float_as_uint(lr) + 0x1000u), "r"(__float_as_uint(li) + 0x1000u) : "memory");
-                    }
-                }
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            // the table slot is released only here: its loads are certainly complete once their values have been used
-            if (lane == 0) { mbar_arrive(&t_empty[ts]); mbar_arrive(&b_full[sb]); }
-        }
     }
+    if (profiling && lane == 0) {
+        unsigned long long* o = prof + warp * 8;
+        o[0] = (unsigned long long)(clock64() - t_role0); o[1] = pw[0]; o[2] = pw[1]; o[3] = pw[2]; o[4] = pw[3];
+    }
+#undef PBSO_TW
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0)
+    if (warp == 20)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCB_TMEM_COLS));
 }
 
@@ -632,7 +708,12 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     if (!st->cta_first) PBSO_CUDA(cudaMalloc(&st->cta_first, sizeof(int) * (a.sm_count + 2)));
     static const int ablate = getenv("PBSO_TC_ABLATE") ? atoi(getenv("PBSO_TC_ABLATE")) : 0;
     static bool attr[64] = {};            // per device: function attributes do not carry across devices
-    if (!attr[dev & 63]) { PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM)); attr[dev & 63] = true; }
+    if (!attr[dev & 63]) {
+        PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
+        PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
+        attr[dev & 63] = true;
+    }
+    static const int epi = getenv("PBSO_TC_EPI") ? atoi(getenv("PBSO_TC_EPI")) : 1;
     const int n_batches = div_up(a.n_obj, st->batch_obj);
     for (int bi = 0; bi < n_batches; ++bi) {
         const int o0 = bi * st->batch_obj, no = std::min(st->batch_obj, a.n_obj - o0);
@@ -683,7 +764,24 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             PBSO_CUDA(cudaGetLastError());
             ++*launches;
         }
-        k_batch_tc<<<st->grid, TCB_THREADS, TCB_SMEM, a.stream>>>(a.n_modes, n_tiles, st->cta_first, st->units, st->tab, st->V, o0, a.d_mix, inv_gain, ablate);
+        static const bool want_prof = getenv("PBSO_TC_PROF") != nullptr;
+        unsigned long long* d_prof = nullptr;
+        if (want_prof && !g_calibrating) { PBSO_CUDA(cudaMalloc(&d_prof, sizeof(unsigned long long) * 24 * 8)); PBSO_CUDA(cudaMemsetAsync(d_prof, 0, sizeof(unsigned long long) * 24 * 8, a.stream)); }
+        if (epi == 1) k_batch_tc<1><<<st->grid, TCB_THREADS, TCB_SMEM, a.stream>>>(a.n_modes, n_tiles, st->cta_first, st->units, st->tab, st->V, o0, a.d_mix, inv_gain, ablate, d_prof);
+        else k_batch_tc<0><<<st->grid, TCB_THREADS, TCB_SMEM, a.stream>>>(a.n_modes, n_tiles, st->cta_first, st->units, st->tab, st->V, o0, a.d_mix, inv_gain, ablate, d_prof);
+        if (d_prof) {
+            unsigned long long h[24 * 8];
+            PBSO_CUDA(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, a.stream));
+            PBSO_CUDA(cudaStreamSynchronize(a.stream));
+            cudaFree(d_prof);
+            const long long chunks = (long long)(st->h_first[1] - st->h_first[0]) * cpu;
+            static const char* role[24] = {"A0.0", "A0.1", "A0.2", "A0.3", "A1.0", "A1.1", "A1.2", "A1.3", "B0.0", "B0.1", "B0.2", "B0.3",
+                                           "B1.0", "B1.1", "B1.2", "B1.3", "epi0", "epi1", "epi2", "epi3", "MMA0", "MMA1", "seed", "load"};
+            fprintf(stderr, "[tc prof] CTA 0: %lld chunks; cycles per chunk: total | wait0 wait1 wait2 wait3\n", chunks);
+            for (int w = 0; w < 24; ++w)
+                fprintf(stderr, "[tc prof] %-5s %8.1f | %8.1f %8.1f %8.1f %8.1f\n", role[w], (double)h[w * 8] / chunks, (double)h[w * 8 + 1] / chunks,
+                        (double)h[w * 8 + 2] / chunks, (double)h[w * 8 + 3] / chunks, (double)h[w * 8 + 4] / chunks);
+        }
         PBSO_CUDA(cudaGetLastError());
         ++*launches;
     }

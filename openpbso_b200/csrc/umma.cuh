@@ -18,6 +18,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // The suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires) instead of
 // polling: a role that runs ahead of the pipeline must not spend issue slots and MIO-queue entries on failed probes
 // (profiles/r2_k_batch_tc.md: 76 probes per chunk and generator warp without it).
+#ifndef PBSO_MBAR_HINT_NS
+#define PBSO_MBAR_HINT_NS 0x989680u
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -26,7 +29,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+        ::"r"(smem_u32(bar)), "r"(parity), "r"(PBSO_MBAR_HINT_NS) : "memory");
+}
+// roles that run AHEAD of the pipeline (operand generators waiting for a free stage): probe, then sleep ~0.1 us between
+// probes -- a failed probe costs an issue slot and an MIO-queue entry that the critical warps need
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONER_%=;\n\t"
+        "WAITR_%=:\n\t"
+        "nanosleep.u32 128;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAITR_%=;\n\t"
+        "DONER_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// latency-critical waiters (MMA issuers): plain probe loop, no suspend
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITS_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONES_%=;\n\t"
+        "bra WAITS_%=;\n\t"
+        "DONES_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(

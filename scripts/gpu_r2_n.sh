@@ -1,0 +1,4 @@
+#!/bin/bash
+timeout 60 python scripts/tc_debug.py 2>&1 | tail -3
+run() { timeout 120 python bench.py --steps 5 --warmup 3 --no-realtime --no-cpu-baseline --no-kernels --no-parity 2>/dev/null | python -c "import sys,json; l=json.loads(sys.stdin.read()); print(l['roofline']['kernel_ms'], l['ms_per_step'], l['clocks']['sm_mhz'], l['clocks']['power_w_max'], l['config']['mix_abs_sum'])"; }
+echo "full"; run; run
