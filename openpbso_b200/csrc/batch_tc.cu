@@ -78,12 +78,14 @@ constexpr int TCB_FLUSH_UNITS = 8;         // units between FP64 flushes of the 
 static_assert(TCB_SMEM <= 232448, "shared memory budget");
 static_assert(TCB_NA == TCB_NB, "A and B stages share their full / empty barriers");
 
-// One unit of work of a CTA: object `obj` over M-tile `it` (128 time tiles), from the state block `src` (tile-start
-// states of a carry unit, or the injected state of an impulse unit landing on row `re` of the M-tile).
+// One unit of work: object `obj` over M-tile `it` (128 time tiles) from the state block `src` -- tile-start states of a
+// carry unit, or the injected state of an impulse unit landing on row `re` of the M-tile.  CTA pairs (cta_group::2)
+// render TWO M-tiles of the object per unit, 2 it + rank, each CTA from its own src[rank] / re[rank] (or the zero block).
 struct Unit {
     int obj, it;
-    unsigned src;          // block index into the state buffer (blocks of mp float2)
-    short re, flush;       // re: impulse row inside the M-tile, -1 for a carry unit; flush: add the register accumulators to the mix after it
+    unsigned src[2];       // block index into the state buffer (blocks of mp float2)
+    short re[2];           // impulse row inside the M-tile, -1 for a carry (or idle) unit
+    short flush, pad;      // add the register accumulators to the mix after this unit
 };
 
 struct Cplx { double x, y; };
@@ -246,7 +248,9 @@ __device__ __forceinline__ void tmem_ld_add_32x32(uint32_t taddr, c32* acc) {
 }
 
 // =============================================================================================================
-template <int EPI>
+// PAIR = 2: clusters of two CTAs, tcgen05.mma cta_group::2 (M = 256): the pair renders two M-tiles of one object and each
+// CTA generates only HALF of operand B (64 of its 128 rows) -- the tensor cores fetch the other half from the peer.
+template <int PAIR>
 __global__ void __launch_bounds__(TCB_THREADS, 1)
 k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Unit* __restrict__ units,
            const uint8_t* __restrict__ tab, const float2* __restrict__ V, int obj0,
@@ -269,29 +273,39 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int u0 = cta_first[blockIdx.x], u1 = cta_first[blockIdx.x + 1];
+    const uint32_t rank = PAIR == 2 ? cluster_ctarank() : 0;
+    const int u0 = cta_first[blockIdx.x / PAIR], u1 = cta_first[blockIdx.x / PAIR + 1];
     // optional in-kernel timing (PBSO_TC_PROF=1): cycles every role of CTA 0 spends in each of its barrier waits
     unsigned long long pw[4] = {0ull, 0ull, 0ull, 0ull};
     const bool profiling = prof != nullptr && blockIdx.x == 0;
+    // barriers the MMA issuers (rank 0) wait on collect arrivals from both CTAs of a pair
+    const uint32_t lead_bfull = PAIR == 2 ? mapa_u32(smem_u32(b_full), 0) : smem_u32(b_full);
+    const uint32_t lead_accempty = PAIR == 2 ? mapa_u32(smem_u32(acc_empty), 0) : smem_u32(acc_empty);
+#define PBSO_ARRIVE_LEAD(base, idx) do { if (PAIR == 2) mbar_arrive_cluster((base) + 8u * (uint32_t)(idx)); else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((base) + 8u * (uint32_t)(idx)) : "memory"); } while (0)
     const long long t_role0 = clock64();
 #define PBSO_TW(slot, stmt) do { if (profiling) { const long long t_ = clock64(); stmt; pw[slot] += (unsigned long long)(clock64() - t_); } else { stmt; } } while (0)
     const int cpu = (n_modes + TCB_KMODES - 1) / TCB_KMODES;          // K chunks per unit
     const int mp = cpu * TCB_KMODES;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TCB_NB; ++s) { mbar_init(&b_full[s], 8); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < TCB_NB; ++s) { mbar_init(&b_full[s], 8 * PAIR); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < TCB_NT; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 9); }
         for (int s = 0; s < TCB_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
         for (int s = 0; s < TCB_NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4 * PAIR); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 20) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCB_TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCB_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCB_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR == 2) cluster_sync_all(); else __syncthreads();          // the peer's barriers exist before anything arrives on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -310,7 +324,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
         uint32_t q = 0;
 #pragma unroll 1
         for (int u = u0; u < u1; ++u) {
-            const int re = units[u].re;
+            const int re = units[u].re[rank];
             int jj = j;
             if (re >= 0 && blk == (re >> 4)) { jj = j - (re & 15); if (jj < 0) jj = 16; }   // impulse unit: rows of block ae are shifted by be; row 16 = 0
 #pragma unroll 1
@@ -359,7 +373,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                 PBSO_TW(3, tmem_st_wait());
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&b_full[sa]);
+                if (lane == 0) PBSO_ARRIVE_LEAD(lead_bfull, sa);
             }
         }
     } else if (warp < 16) {
@@ -368,10 +382,14 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
         // two groups of four warps (8-11, 12-15) take alternate K chunks, like the A generators
         // straight into the UMMA K-major 128-byte-swizzle layout: row r = 16 blk + b, K columns (2 m, 2 m + 1) at byte
         // (r / 8) 1024 + (r % 8) 128 + (((m / 2) ^ (r % 8)) 16) + (m % 2) 8; the eight swizzled offsets of a thread never change
-        const int m_l = lane & 15, bgrp = (warp - 8) >> 2, blk = ((warp - 8) & 3) * 2 + (lane >> 4);
+        // PAIR = 2: this CTA holds rows [64 rank, 64 rank + 64) of the tile: thread = (mode, 8-row half block), local row 8 hb + i
+        const int m_l = lane & 15, bgrp = (warp - 8) >> 2, hb = ((warp - 8) & 3) * 2 + (lane >> 4);
+        const int blk = PAIR == 2 ? 4 * (int)rank + (hb >> 1) : hb;               // 16-row block of the tile the thread starts in
+        const int t0 = PAIR == 2 ? 2 * (hb & 1) : 0;                               // first 4-row step inside the block
+        constexpr int NT4 = PAIR == 2 ? 2 : 4;                                     // 4-row steps per thread
         uint32_t xoff[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xoff[i] = sw128_pair(16 * blk + i, m_l);
+        for (int i = 0; i < 8; ++i) xoff[i] = PAIR == 2 ? sw128_pair(8 * hb + i, m_l) : sw128_pair(16 * hb + i, m_l);
         const uint32_t n_chunks = (uint32_t)(u1 - u0) * (uint32_t)cpu;
 #pragma unroll 1
         for (uint32_t q = (uint32_t)bgrp; q < n_chunks; q += 2) {
@@ -387,12 +405,18 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
 #pragma unroll
             for (int t = 0; t < 3; ++t) { rtr[t] = pk(rt[t].x, rt[t].x); rti[t] = pk(rt[t].y, rt[t].y); rcr[t] = pk(rc[t].x, rc[t].x); rci[t] = pk(rc[t].y, rc[t].y); }
             const c32 xa = pk(ra.x, ra.y), xar = pk(-ra.y, ra.x);
+            // PAIR = 2: the thread's two 4-row steps are t = t0, t0 + 1 with t0 = 0 or 2: multipliers 1, W^4 or W^8, W^12
+            const float2 m0 = t0 ? rt[1] : make_float2(1.f, 0.f), m1 = t0 ? rt[2] : rt[0];
+            const c32 m0r = pk(m0.x, m0.x), m0i = pk(m0.y, m0.y), m1r = pk(m1.x, m1.x), m1i = pk(m1.y, m1.y);
             PBSO_TW(1, mbar_wait_relaxed(&b_empty[sb], ((q / TCB_NB) & 1) ^ 1));
             const uint32_t st = smem_u32(smem) + sb * TCB_BT_BYTES;
             if (!(ablate & 1)) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const c32 pt = t == 0 ? xa : fma2(rti[t - 1], xar, mul2(rtr[t - 1], xa));
+                for (int tt = 0; tt < NT4; ++tt) {
+                    // step t = t0 + tt of the block: x W^(4 t)
+                    c32 pt;
+                    if (PAIR == 2) pt = fma2(tt == 0 ? m0i : m1i, xar, mul2(tt == 0 ? m0r : m1r, xa));
+                    else pt = tt == 0 ? xa : fma2(rti[tt - 1], xar, mul2(rtr[tt - 1], xa));
                     float pr, pi; upk(pt, pr, pi);
                     const c32 ptr_ = pk(-pi, pr);
 #pragma unroll
@@ -400,9 +424,9 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                         const c32 v = c == 0 ? pt : fma2(rci[c - 1], ptr_, mul2(rcr[c - 1], pt));
                         float vr, vi; upk(v, vr, vi);
                         const uint32_t br = __float_as_uint(vr), bi = __float_as_uint(vi);
-                        const c32 tt = pk(__uint_as_float(br & 0xFFFFE000u), __uint_as_float(bi & 0xFFFFE000u));
-                        float lr, li; upk(sub2(v, tt), lr, li);
-                        const int b = 4 * t + c;
+                        const c32 tr = pk(__uint_as_float(br & 0xFFFFE000u), __uint_as_float(bi & 0xFFFFE000u));
+                        float lr, li; upk(sub2(v, tr), lr, li);
+                        const int b = 4 * tt + c;                                  // row of the thread's 8- or 16-row run
                         const uint32_t addr = st + xoff[b & 7] + (uint32_t)(b >> 3) * 1024u;
                         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(br), "r"(bi) : "memory");
                         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + TCB_TILE_BYTES), "f"(lr), "f"(li) : "memory");
@@ -412,7 +436,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
             PBSO_TW(2, fence_proxy_async_smem());
             __syncwarp();
             // the table slot is released only here: its loads are certainly complete once their values have been used
-            if (lane == 0) { mbar_arrive(&t_empty[ts]); mbar_arrive(&b_full[sb]); }
+            if (lane == 0) { mbar_arrive(&t_empty[ts]); PBSO_ARRIVE_LEAD(lead_bfull, sb); }
         }
     } else if (warp < 20) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
@@ -432,7 +456,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                 PBSO_TW(0, mbar_wait(&acc_full[buf], (g >> 1) & 1));
                 tcgen05_fence_after();
                 if (!(ablate & 4)) {
-                    if (EPI == 1) {
+                    if (true) {
 #pragma unroll
                         for (int qd = 0; qd < TCB_L / 32; ++qd) tmem_ld_add_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), &acc[qd * 16]);
                     } else {
@@ -451,11 +475,11 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                if (lane == 0) PBSO_ARRIVE_LEAD(lead_accempty, buf);
             }
             const Unit un = units[u];
             if (un.flush) {
-                const long long tile = (long long)un.it * TCB_ROWS + row;
+                const long long tile = ((long long)un.it * PAIR + rank) * TCB_ROWS + row;
                 if (tile < n_tiles) {
                     double* dst = mix + tile * TCB_L;
 #pragma unroll
@@ -474,6 +498,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
         // whole pipeline waits for
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp < 22) {
+          if (rank == 0) {
             // ---------------- MMA issuers: warp 20 takes the even chains (accumulator 0), warp 21 the odd ones ----------------
             // A chain = two K chunks of a unit (one at an odd tail): the 16 small products of both chunks first (hi*lo, lo*hi
             // -- their accumulate-truncation is relative to a 2^-11 smaller sum), then the 8 hi*hi MMAs on top, ONE accumulator,
@@ -481,7 +506,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
             // 768 cycles of MMAs, so per-chunk draining would bound the kernel.  Issuing is serial work of one thread; two
             // issuers keep the tensor pipe's queue fed while one of them is between chains.  The whole warp runs the loop
             // so that every operand stays warp-uniform.
-            constexpr uint32_t idesc = umma_idesc_tf32(TCB_ROWS, TCB_L);
+            constexpr uint32_t idesc = umma_idesc_tf32(TCB_ROWS * PAIR, TCB_L);
             const uint64_t desc0 = umma_desc_k_sw128(smem_u32(smem));
             const uint32_t cpp = (uint32_t)(cpu + 1) >> 1;                              // chains per unit
             const uint32_t n_chains = (uint32_t)(u1 - u0) * cpp;
@@ -503,8 +528,8 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                         const uint64_t dBh = desc0 + (uint64_t)(st * (TCB_BT_BYTES >> 4)), dBl = dBh + (TCB_TILE_BYTES >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_ts<0, 1>(acc, a_hi + 8 * k, dBl + 2 * k, idesc, (i | (uint32_t)k) ? 1u : 0u);
-                            umma_ts<0, 1>(acc, a_lo + 8 * k, dBh + 2 * k, idesc, 1u);
+                            umma_ts<0, PAIR>(acc, a_hi + 8 * k, dBl + 2 * k, idesc, (i | (uint32_t)k) ? 1u : 0u);
+                            umma_ts<0, PAIR>(acc, a_lo + 8 * k, dBh + 2 * k, idesc, 1u);
                         }
                     }
                     for (uint32_t i = 0; i < nc; ++i) {
@@ -512,13 +537,19 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                         const uint32_t a_hi = tmem_base + 256 + st * 64;
                         const uint64_t dBh = desc0 + (uint64_t)(st * (TCB_BT_BYTES >> 4));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_ts<0, 1>(acc, a_hi + 8 * k, dBh + 2 * k, idesc, 1u);
+                        for (int k = 0; k < 4; ++k) umma_ts<0, PAIR>(acc, a_hi + 8 * k, dBh + 2 * k, idesc, 1u);
                     }
-                    for (uint32_t i = 0; i < nc; ++i) umma_commit(&b_empty[(q0 + i) & 3]);
-                    umma_commit(&acc_full[par]);
+                    if (PAIR == 2) {
+                        for (uint32_t i = 0; i < nc; ++i) umma_commit_2cta(&b_empty[(q0 + i) & 3], 3);
+                        umma_commit_2cta(&acc_full[par], 3);
+                    } else {
+                        for (uint32_t i = 0; i < nc; ++i) umma_commit(&b_empty[(q0 + i) & 3]);
+                        umma_commit(&acc_full[par]);
+                    }
                 }
                 __syncwarp();
             }
+          }
         } else if (warp == 23) {
             // ---------------- table loader: a chunk's 5 KB table block and its 16 tile-start states, NT chunks ahead ----------------
             if (lane == 0) {
@@ -527,7 +558,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                 for (int u = u0; u < u1; ++u) {
                     const Unit un = units[u];
                     const uint8_t* tsrc = tab + (size_t)(un.obj - obj0) * cpu * TCB_TABG_BYTES;
-                    const float2* vsrc = V + (size_t)un.src * mp;
+                    const float2* vsrc = V + (size_t)un.src[rank] * mp;
 #pragma unroll 1
                     for (int ch = 0; ch < cpu; ++ch, ++q) {
                         const uint32_t ts = q % TCB_NT;
@@ -545,7 +576,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
             uint32_t q = 0;
 #pragma unroll 1
             for (int u = u0; u < u1; ++u) {
-                const int re = units[u].re;
+                const int re = units[u].re[rank];
 #pragma unroll 1
                 for (int ch = 0; ch < cpu; ++ch, ++q) {
                     const uint32_t ts = q % TCB_NT, ss = q % TCB_NS;
@@ -589,10 +620,13 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
         o[0] = (unsigned long long)(clock64() - t_role0); o[1] = pw[0]; o[2] = pw[1]; o[3] = pw[2]; o[4] = pw[3];
     }
 #undef PBSO_TW
+#undef PBSO_ARRIVE_LEAD
     tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 20)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCB_TMEM_COLS));
+    if (PAIR == 2) cluster_sync_all(); else __syncthreads();          // the peer's tensor core may still read this CTA's operands
+    if (warp == 20) {
+        if (PAIR == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCB_TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCB_TMEM_COLS));
+    }
 }
 
 }  // namespace
@@ -605,7 +639,7 @@ struct TcState {
     int v_nit = -1, v_no = -1, v_ne = -1;           // layout the pad entries of V were zeroed for
     Unit* units = nullptr; size_t unit_cap = 0;
     int* cta_first = nullptr; int* ev_obj = nullptr; size_t ev_cap = 0;
-    int grid = 0;
+    int grid = 0, pair = 1;                         // CTAs per cluster: 2 = tcgen05 cta_group::2 pairs
     int tab_obj0 = -1, tab_nobj = 0, batch_obj = 0; // objects [tab_obj0, tab_obj0 + tab_nobj) have tables resident
     size_t npm = 0;
     // cached unit list
@@ -620,49 +654,66 @@ void tc_free(TcState* st) {
     delete st;
 }
 
-// unit list of the objects [o0, o0 + no): work items = (window of TCB_WINDOW objects, M-tile), dealt round-robin to the
-// CTAs in (window, M-tile) order -- the CTAs rendering the M-tiles of one window run at about the same time, so a
+// unit list of the objects [o0, o0 + no): work items = (window of TCB_WINDOW objects, M-tile or pair of M-tiles), dealt
+// round-robin to the CTAs (clusters) in (window, M-tile) order -- the CTAs rendering the M-tiles of one window run at about the same time, so a
 // window's table blocks are read from HBM once and from L2 by the rest; a CTA keeps one M-tile's partial mix in
 // registers across the units of an item.
 static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tiles, int n_it, int tpb) {
-    const int ncta = st->grid;
+    const int PAIR = st->pair, ncl = st->grid / PAIR, n_grp = div_up(n_it, PAIR);
     const unsigned imp_blk0 = (unsigned)((size_t)n_it * no);
     const int e_base = a.h_ev_off[o0];
+    const unsigned zero_blk = imp_blk0 + (unsigned)(a.h_ev_off[o0 + no] - e_base);          // idle half of a pair
     static const int window = getenv("PBSO_TC_WINDOW") ? std::max(1, atoi(getenv("PBSO_TC_WINDOW"))) : TCB_WINDOW;
     static const int flush_units = getenv("PBSO_TC_FLUSH") ? std::max(1, atoi(getenv("PBSO_TC_FLUSH"))) : TCB_FLUSH_UNITS;
-    std::vector<std::vector<Unit>> per(ncta);
+    std::vector<std::vector<Unit>> per(ncl);
     std::vector<int> cur(no);
     long long item = 0;
     for (int w0 = 0; w0 < no; w0 += window) {
         const int w1 = std::min(no, w0 + window);
         for (int o = w0; o < w1; ++o) cur[o] = a.h_ev_off[o0 + o];
-        for (int it = 0; it < n_it; ++it) {
-            const long long row0 = (long long)it * TCB_ROWS, row1 = row0 + TCB_ROWS;
+        for (int t = 0; t < n_grp; ++t) {
             std::vector<Unit> tmp;
             for (int o = w0; o < w1; ++o) {
                 const int e_begin = a.h_ev_off[o0 + o], e_end = a.h_ev_off[o0 + o + 1];
-                // carry unit (an earlier impulse exists), then the impulses landing inside the M-tile (events are sorted by buffer)
-                if (e_begin < e_end && (long long)a.h_ev_buf[e_begin] * tpb < row0) tmp.push_back(Unit{o0 + o, it, (unsigned)((size_t)it * no + o), (short)-1, 0});
-                int& e = cur[o];
-                while (e < e_end && (long long)a.h_ev_buf[e] * tpb < row1) {
-                    const long long row = (long long)a.h_ev_buf[e] * tpb;
-                    if (row >= row0 && row < n_tiles) tmp.push_back(Unit{o0 + o, it, imp_blk0 + (unsigned)(e - e_base), (short)(row - row0), 0});
-                    ++e;
+                // per M-tile of the group: carry unit (an earlier impulse exists), then the impulses landing inside it
+                // (events are sorted by buffer; cur[o] walks them once across the M-tiles)
+                std::vector<std::pair<unsigned, int>> u[2];
+                for (int r = 0; r < PAIR; ++r) {
+                    const int it = t * PAIR + r;
+                    if (it >= n_it) continue;
+                    const long long row0 = (long long)it * TCB_ROWS, row1 = row0 + TCB_ROWS;
+                    if (e_begin < e_end && (long long)a.h_ev_buf[e_begin] * tpb < row0) u[r].push_back({(unsigned)((size_t)it * no + o), -1});
+                    int& e = cur[o];
+                    while (e < e_end && (long long)a.h_ev_buf[e] * tpb < row1) {
+                        const long long row = (long long)a.h_ev_buf[e] * tpb;
+                        if (row >= row0 && row < n_tiles) u[r].push_back({imp_blk0 + (unsigned)(e - e_base), (int)(row - row0)});
+                        ++e;
+                    }
+                }
+                const size_t np = std::max(u[0].size(), u[1].size());
+                for (size_t i = 0; i < np; ++i) {
+                    Unit un{};
+                    un.obj = o0 + o; un.it = t;
+                    for (int r = 0; r < 2; ++r) {
+                        if (i < u[r].size()) { un.src[r] = u[r][i].first; un.re[r] = (short)u[r][i].second; }
+                        else { un.src[r] = zero_blk; un.re[r] = -1; }
+                    }
+                    tmp.push_back(un);
                 }
             }
             if (tmp.empty()) continue;
-            std::vector<Unit>& out = per[item++ % ncta];
+            std::vector<Unit>& out = per[item++ % ncl];
             int since = 0;
             for (Unit& un : tmp) { un.flush = (short)(++since >= flush_units); if (un.flush) since = 0; out.push_back(un); }
-            out.back().flush = 1;                                    // the M-tile changes with the item
+            out.back().flush = 1;                                    // the M-tiles change with the item
         }
     }
-    st->h_units.clear(); st->h_first.assign(ncta + 1, 0);
-    for (int c = 0; c < ncta; ++c) {
+    st->h_units.clear(); st->h_first.assign(ncl + 1, 0);
+    for (int c = 0; c < ncl; ++c) {
         st->h_first[c] = (int)st->h_units.size();
         st->h_units.insert(st->h_units.end(), per[c].begin(), per[c].end());
     }
-    st->h_first[ncta] = (int)st->h_units.size();
+    st->h_first[ncl] = (int)st->h_units.size();
     st->n_units = (int)st->h_units.size();
 }
 
@@ -685,7 +736,9 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     const int n_tiles = (int)(n_samples / TCB_L);
     const int n_it = div_up(n_tiles, TCB_ROWS);
     const int tpb = a.buf_size / TCB_L;                               // tiles per buffer
-    st->grid = std::max(1, a.sm_count);
+    static const int force_pair = getenv("PBSO_TC_PAIR") ? atoi(getenv("PBSO_TC_PAIR")) : 0;
+    st->pair = (force_pair == 1 || a.sm_count < 2) ? 1 : 2;
+    st->grid = std::max(st->pair, a.sm_count / st->pair * st->pair);
     // ---- objects per batch: the operand tables of a batch stay resident (5 KB per object and 16-mode chunk) ----
     if (st->npm != npm || st->batch_obj == 0) {
         cudaFree(st->tab); st->tab = nullptr; st->tab_obj0 = -1; st->npm = 0;
@@ -709,11 +762,10 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     static const int ablate = getenv("PBSO_TC_ABLATE") ? atoi(getenv("PBSO_TC_ABLATE")) : 0;
     static bool attr[64] = {};            // per device: function attributes do not carry across devices
     if (!attr[dev & 63]) {
-        PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
         PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
+        PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
         attr[dev & 63] = true;
     }
-    static const int epi = getenv("PBSO_TC_EPI") ? atoi(getenv("PBSO_TC_EPI")) : 1;
     const int n_batches = div_up(a.n_obj, st->batch_obj);
     for (int bi = 0; bi < n_batches; ++bi) {
         const int o0 = bi * st->batch_obj, no = std::min(st->batch_obj, a.n_obj - o0);
@@ -733,7 +785,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             }
             // pageable sources: cudaMemcpyAsync stages them before it returns, the vectors may be rebuilt right away
             if (st->n_units) PBSO_CUDA(cudaMemcpyAsync(st->units, st->h_units.data(), sizeof(Unit) * st->n_units, cudaMemcpyHostToDevice, a.stream));
-            PBSO_CUDA(cudaMemcpyAsync(st->cta_first, st->h_first.data(), sizeof(int) * (st->grid + 1), cudaMemcpyHostToDevice, a.stream));
+            PBSO_CUDA(cudaMemcpyAsync(st->cta_first, st->h_first.data(), sizeof(int) * (st->grid / st->pair + 1), cudaMemcpyHostToDevice, a.stream));
             if (a.n_events > 0) {
                 st->h_ev_obj.resize(a.n_events);
                 for (int o = 0; o < a.n_obj; ++o) for (int e = a.h_ev_off[o]; e < a.h_ev_off[o + 1]; ++e) st->h_ev_obj[e] = o;
@@ -744,14 +796,15 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
         if (st->n_units == 0) continue;                               // silence: the mix is already zeroed
         // state blocks: carrier [n_it][no] | impulses of the batch
         const int e0 = a.h_ev_off[o0], ne = a.h_ev_off[o0 + no] - e0;
-        const size_t vneed = ((size_t)n_it * no + ne) * mp;
+        const size_t vneed = ((size_t)n_it * no + ne + 1) * mp;           // + one zero block: the idle half of a pair
         if (vneed > st->v_cap) {
             cudaFree(st->V); st->V = nullptr; st->v_cap = 0;
             PBSO_CUDA(cudaMalloc(&st->V, sizeof(float2) * vneed)); st->v_cap = vneed;
             st->v_nit = -1;
         }
-        if (mp != a.n_modes && (st->v_nit != n_it || st->v_no != no || st->v_ne != ne)) {                   // pad modes stay zero
-            PBSO_CUDA(cudaMemsetAsync(st->V, 0, sizeof(float2) * vneed, a.stream));
+        if (st->v_nit != n_it || st->v_no != no || st->v_ne != ne) {
+            if (mp != a.n_modes) PBSO_CUDA(cudaMemsetAsync(st->V, 0, sizeof(float2) * vneed, a.stream));     // pad modes stay zero
+            else PBSO_CUDA(cudaMemsetAsync(st->V + (vneed - mp), 0, sizeof(float2) * mp, a.stream));          // the zero block
         }
         st->v_nit = n_it; st->v_no = no; st->v_ne = ne;
         k_tc_carrier<<<(unsigned)(((size_t)no * a.n_modes + 255) / 256), 256, 0, a.stream>>>(no, a.n_modes, n_it, tpb, mp, o0, a.lneps, a.theta, a.c3, a.cot,
@@ -767,14 +820,25 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
         static const bool want_prof = getenv("PBSO_TC_PROF") != nullptr;
         unsigned long long* d_prof = nullptr;
         if (want_prof && !g_calibrating) { PBSO_CUDA(cudaMalloc(&d_prof, sizeof(unsigned long long) * 24 * 8)); PBSO_CUDA(cudaMemsetAsync(d_prof, 0, sizeof(unsigned long long) * 24 * 8, a.stream)); }
-        if (epi == 1) k_batch_tc<1><<<st->grid, TCB_THREADS, TCB_SMEM, a.stream>>>(a.n_modes, n_tiles, st->cta_first, st->units, st->tab, st->V, o0, a.d_mix, inv_gain, ablate, d_prof);
-        else k_batch_tc<0><<<st->grid, TCB_THREADS, TCB_SMEM, a.stream>>>(a.n_modes, n_tiles, st->cta_first, st->units, st->tab, st->V, o0, a.d_mix, inv_gain, ablate, d_prof);
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(st->grid); cfg.blockDim = dim3(TCB_THREADS); cfg.dynamicSmemBytes = TCB_SMEM; cfg.stream = a.stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = st->pair; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            if (st->pair == 2)
+                PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<2>, a.n_modes, n_tiles, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
+                                             (const float2*)st->V, o0, a.d_mix, inv_gain, ablate, d_prof));
+            else
+                PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<1>, a.n_modes, n_tiles, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
+                                             (const float2*)st->V, o0, a.d_mix, inv_gain, ablate, d_prof));
+        }
         if (d_prof) {
             unsigned long long h[24 * 8];
             PBSO_CUDA(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, a.stream));
             PBSO_CUDA(cudaStreamSynchronize(a.stream));
             cudaFree(d_prof);
-            const long long chunks = (long long)(st->h_first[1] - st->h_first[0]) * cpu;
+            const long long chunks = std::max(1LL, (long long)(st->h_first[1] - st->h_first[0]) * cpu);
             static const char* role[24] = {"A0.0", "A0.1", "A0.2", "A0.3", "A1.0", "A1.1", "A1.2", "A1.3", "B0.0", "B0.1", "B0.2", "B0.3",
                                            "B1.0", "B1.1", "B1.2", "B1.3", "epi0", "epi1", "epi2", "epi3", "MMA0", "MMA1", "seed", "load"};
             fprintf(stderr, "[tc prof] CTA 0: %lld chunks; cycles per chunk: total | wait0 wait1 wait2 wait3\n", chunks);

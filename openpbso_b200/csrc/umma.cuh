@@ -130,8 +130,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
 }
+// Remote arrive on a peer CTA's barrier.  No `.release.cluster`: ptxas turns that into MEMBAR.ALL.GPU + CGAERRBAR in front
+// of every arrive (and the matching `.acquire.cluster` wait into an L1 invalidate), thousands of cycles per K chunk.  What
+// this arrive publishes is already PERFORMED when it is issued -- shared-memory stores followed by fence.proxy.async,
+// TMEM stores followed by tcgen05.wait::st, TMEM loads followed by tcgen05.wait::ld -- and is only ever read by the
+// producing CTA's own tensor core (cta_group::2 MMAs read each operand half from the CTA that holds it), so the default
+// release at CTA scope is what the hardware needs (the CUTLASS ClusterBarrier::arrive(cta_id) form).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // acquire at cluster scope: pairs with mbar_arrive_cluster from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
