@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_OBJ, N_MODES, BUF, N_BUF = 4096, 512, 256, 1723      # cfg5: 441 088 samples = 10.0 s
-TC3X_DRAM_BYTES_PER_MODE_SAMPLE = 1.127e9 / 9.2504e11    # ncu --set full, cfg5 launch: 1.12 GB read + 0.007 GB written (profiles/r2_k_batch_tc.md)
+TC3X_DRAM_BYTES_PER_MODE_SAMPLE = 1.222e9 / 9.2504e11    # ncu --set full, cfg5 launch: 1.18 GB read + 0.04 GB written (profiles/r2_k_batch_tc_metrics.txt)
 FLOP_PER_MODE_SAMPLE = 8.0                              # 4 FMA: 3 in Step (modal_integrator.h:109-110) + 1 in the dot (modal_solver.h:267-269)
 
 
@@ -441,8 +441,9 @@ def run_ours(args):
 
     # ---- e2e: same job through the host-pointer C ABI, copies inside the timed region --------
     def step_e2e():
-        br.set_transfer(trans_h)                       # H2D
-        br.set_impulses(obj_h, buf_h, space_h)         # H2D (+ host-side CSR build)
+        # pinned inputs, copies enqueued on the render stream: one host synchronisation per step, after the mix is back
+        br.set_transfer(trans_h, wait=False)               # H2D
+        br.set_impulses(obj_h, buf_h, space_h, wait=False)  # H2D (+ host-side CSR build)
         step_device()
         if rank == 0:
             mix_host.copy_(mix, non_blocking=True)     # D2H of the result
@@ -493,7 +494,8 @@ def run_ours(args):
     ms_local = float(n_local) * args.modes * n_samples
     achieved = ms_local * FLOP_PER_MODE_SAMPLE / (k_ms * 1e-3) / 1e12          # algorithmic: 8 FLOP per mode-sample
     nominal_fp32 = info["sm_count"] * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
-    tf32_peak_measured, tf32_cyc, _ = pbso.measure_tc_peak(0, 1, 128)
+    tf32_peak_measured, tf32_cyc, _ = pbso.measure_tc_peak(0, 2, 128)
+    tf32_peak_sustained = pbso.measure_tc_peak_sustained(0, 2, 128, 300.0)
     if prec == pbso.PREC_TC3X:
         # tensor-pipe roofline: the kernel issues 3 TF32 MMAs (hi*hi, hi*lo, lo*hi) per product and 2 K columns per
         # mode (Re, Im of the tile-start state), i.e. 12 tensor FLOP per mode-sample.  The denominator is the kind::tf32
@@ -502,11 +504,13 @@ def run_ours(args):
         # reported beside it (MEASURED_PEAKS.json has no TF32 number).
         issued = ms_local * 12.0 / (k_ms * 1e-3) / 1e12
         half_bf16 = 0.5 * float(peaks.get("bf16_tflops", 1590.0))
-        roofline = {"bound": "tensor", "kernel": "k_batch_tc (tcgen05 kind::tf32, 3xTF32, 12 MMAs per 16-mode K chunk)", "achieved": issued,
-                    "peak": tf32_peak_measured, "unit": "TFLOP/s", "frac": issued / tf32_peak_measured,
+        roofline = {"bound": "tensor", "kernel": "k_batch_tc<2> (tcgen05.mma cta_group::2 kind::tf32, 3xTF32, 12 MMAs per 16-mode K chunk and CTA pair)", "achieved": issued,
+                    "peak": tf32_peak_sustained, "unit": "TFLOP/s", "frac": issued / tf32_peak_sustained,
+                    "peak_burst": tf32_peak_measured, "frac_of_burst_peak": issued / tf32_peak_measured,
                     "traffic": TC3X_DRAM_BYTES_PER_MODE_SAMPLE * ms_local if (TC3X_DRAM_BYTES_PER_MODE_SAMPLE and args.modes == N_MODES and args.buffers == N_BUF) else None,
                     "kernel_ms": k_ms,
-                    "peak_source": "kind::tf32 peak measured in this run by pbso_measure_tc_peak (bare tcgen05.mma loop, %.1f cycles per 128x128x8 MMA)" % tf32_cyc,
+                    "peak_source": "kind::tf32 rate of a bare tcgen05.mma cta_group::2 loop measured in this run (pbso_measure_tc_peak_sustained: launched back to "
+                                   "back for 300 ms, i.e. under the same power cap as the timed steps); peak_burst is one 2.6 ms launch of the same loop (%.1f cycles per 256x128x8 MMA)" % tf32_cyc,
                     "frac_of_half_bf16_cublas": issued / half_bf16, "half_bf16_cublas_tflops": half_bf16, "half_bf16_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (%s, burst)" % peaks_kind,
                     "achieved_counts": "issued tensor FLOP: 3 MMAs x 2 K-columns x 2 FLOP = 12 per mode-sample",
                     "traffic_source": "dram__bytes_read+write of one ncu --set full capture of this kernel, scaled per mode-sample (profiles/r2_k_batch_tc.md)",

@@ -212,6 +212,13 @@ int pbso_batch_set_transfer(pbso_batch* bt, const double* trans);
  * in the same buffer are rejected with PBSO_ERR_INVALID. */
 int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const int* buf,
                             const double* space);
+/* The same two calls without the final host synchronisation: the copies are only ENQUEUED on the handle's stream, so
+ * `trans` / `space` must stay valid and unchanged until the stream has passed them (pbso_batch_sync, or a later call
+ * that synchronises such as pbso_batch_render_mix).  With pinned buffers a whole step -- inputs in, render, audio
+ * reduce, mix out -- then costs ONE host synchronisation. */
+int pbso_batch_set_transfer_async(pbso_batch* bt, const double* trans);
+int pbso_batch_set_impulses_async(pbso_batch* bt, int n_events, const int* obj, const int* buf,
+                                  const double* space);
 /* Render n_buffers x buf_size samples of every object from zero state and mix them down:
  * mix[i] = sum_obj y_obj[i]  (double, n_buffers*buf_size).  With PBSO_PREC_F32_TILED and buf_size 256 the
  * render is also parallel over n_chunks independent time chunks (0 = choose from the SM count) whose start
@@ -264,6 +271,9 @@ int pbso_measure_fma_peak(int kind, double* tflops, double* sm_mhz_est);
  * wavefronts per cycle per SM they sustained.  Outputs: TFLOP/s of the whole device, median cycles per MMA. */
 int pbso_measure_tc_peak(int kind, int cta_group, int n, int stress, double* tflops,
                          double* cycles_per_mma, double* stress_wavefronts_per_cycle);
+/* The same loop launched back to back for at least min_ms of device time: the SUSTAINED tensor rate under the board's
+ * power cap -- the roofline denominator of a kernel timed inside a long step (the burst figure is for a kernel timed alone). */
+int pbso_measure_tc_peak_sustained(int kind, int cta_group, int n, double min_ms, double* tflops);
 /* One [256 x 128] x K product on a CTA pair (tcgen05.mma cta_group::2, A from TMEM) with integer-valued operands:
  * max |D - A B^T| (0 when the operand placement assumed by the pair kernels is right). */
 int pbso_tc_selftest(int kind, double* max_err);

@@ -94,6 +94,8 @@ def lib():
             "pbso_batch_destroy": [vp],
             "pbso_batch_set_transfer": [vp, c_dp],
             "pbso_batch_set_impulses": [vp, C.c_int, c_ip, c_ip, c_dp],
+            "pbso_batch_set_transfer_async": [vp, c_dp],
+            "pbso_batch_set_impulses_async": [vp, C.c_int, c_ip, c_ip, c_dp],
             "pbso_batch_render_mix": [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp],
             "pbso_batch_render_mix_device": [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
             "pbso_batch_render_stems": [vp, C.c_int, C.c_int, C.c_int, c_fp],
@@ -108,6 +110,7 @@ def lib():
             "pbso_comm_reduce_audio": [vp, vp, C.c_size_t, C.c_int, vp],
             "pbso_measure_fma_peak": [C.c_int, c_dp, c_dp],
             "pbso_measure_tc_peak": [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp],
+            "pbso_measure_tc_peak_sustained": [C.c_int, C.c_int, C.c_int, C.c_double, c_dp],
             "pbso_tc_selftest": [C.c_int, c_dp],
             "pbso_tc_gain": [c_dp],
             "pbso_measure_copy_bw": [C.c_size_t, c_dp],

@@ -34,6 +34,12 @@ def measure_tc_peak(kind, cta_group=1, n=128, stress=0):
     return t.value, cyc.value, wf.value
 
 
+def measure_tc_peak_sustained(kind, cta_group=1, n=128, min_ms=200.0):
+    t = C.c_double()
+    check(lib().pbso_measure_tc_peak_sustained(kind, cta_group, n, min_ms, C.byref(t)))
+    return t.value
+
+
 def tc_gain():
     g = C.c_double()
     check(lib().pbso_tc_gain(C.byref(g)))
@@ -387,14 +393,24 @@ class BatchRenderer:
         self._h = C.c_void_p()
         check(lib().pbso_batch_create(self.n_obj, self.n_modes, h, dp(a), dp(b), C.byref(self._h)))
 
-    def set_transfer(self, trans):
+    def set_transfer(self, trans, wait=True):
+        """wait=False: the copy is only enqueued (pbso_batch_set_transfer_async); `trans` must then be a contiguous float64
+        array that stays alive and unchanged until the stream has passed it (ideally pinned)."""
         t = f64(trans); assert t.shape == (self.n_obj, self.n_modes)
-        check(lib().pbso_batch_set_transfer(self._h, dp(t)))
+        if wait:
+            check(lib().pbso_batch_set_transfer(self._h, dp(t)))
+        else:
+            assert t is trans or np.shares_memory(t, trans), "async copies need the caller's own contiguous float64 buffer"
+            check(lib().pbso_batch_set_transfer_async(self._h, dp(t)))
 
-    def set_impulses(self, obj, buf, space):
+    def set_impulses(self, obj, buf, space, wait=True):
         obj = np.ascontiguousarray(obj, dtype=np.int32); buf = np.ascontiguousarray(buf, dtype=np.int32)
-        space = f64(space).reshape(len(obj), self.n_modes)
-        check(lib().pbso_batch_set_impulses(self._h, len(obj), ip(obj), ip(buf), dp(space)))
+        sp = f64(space).reshape(len(obj), self.n_modes)
+        if wait:
+            check(lib().pbso_batch_set_impulses(self._h, len(obj), ip(obj), ip(buf), dp(sp)))
+        else:
+            assert np.shares_memory(sp, space), "async copies need the caller's own contiguous float64 buffer"
+            check(lib().pbso_batch_set_impulses_async(self._h, len(obj), ip(obj), ip(buf), dp(sp)))
 
     def render_mix(self, buf_size, n_buffers, precision=capi.PREC_F32_TILED, n_chunks=0):
         mix = np.empty(buf_size * n_buffers)

@@ -569,16 +569,26 @@ int pbso_batch_destroy(pbso_batch* bt) {
     return PBSO_OK;
 }
 
-int pbso_batch_set_transfer(pbso_batch* bt, const double* trans) {
+static int set_transfer_impl(pbso_batch* bt, const double* trans, bool wait) {
     PBSO_REQUIRE(bt && trans, PBSO_ERR_INVALID, "null argument");
     DeviceGuard g(bt->device);
     PBSO_CUDA(cudaMemcpyAsync(bt->trans(), trans, sizeof(double) * bt->npm(), cudaMemcpyHostToDevice, bt->stream));
-    PBSO_CUDA(cudaStreamSynchronize(bt->stream));
+    if (wait) PBSO_CUDA(cudaStreamSynchronize(bt->stream));          // the caller may reuse its buffer on return
     ++bt->trans_ver;
     return PBSO_OK;
 }
+int pbso_batch_set_transfer(pbso_batch* bt, const double* trans) { return set_transfer_impl(bt, trans, true); }
+int pbso_batch_set_transfer_async(pbso_batch* bt, const double* trans) { return set_transfer_impl(bt, trans, false); }
 
+static int set_impulses_impl(pbso_batch* bt, int n_events, const int* obj, const int* buf, const double* space, bool wait);
 int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const int* buf, const double* space) {
+    return set_impulses_impl(bt, n_events, obj, buf, space, true);
+}
+int pbso_batch_set_impulses_async(pbso_batch* bt, int n_events, const int* obj, const int* buf, const double* space) {
+    return set_impulses_impl(bt, n_events, obj, buf, space, false);
+}
+
+static int set_impulses_impl(pbso_batch* bt, int n_events, const int* obj, const int* buf, const double* space, bool wait) {
     PBSO_REQUIRE(bt && n_events >= 0 && (n_events == 0 || (obj && buf && space)), PBSO_ERR_INVALID, "bad argument");
     DeviceGuard g(bt->device);
     // sort events by (object, buffer) into CSR; a ModalSolver dequeues at most one ForceMessage per
@@ -608,9 +618,9 @@ int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const 
     // caller's (ideally pinned) memory to the device -- when the events arrive unsorted they are
     // permuted there, never through a pageable host copy.
     const size_t rows = (size_t)std::max(n_events, 1);
-    PBSO_CUDA(cudaStreamSynchronize(bt->stream));
     if (!bt->d_ev_off) PBSO_CUDA(cudaMalloc(&bt->d_ev_off, sizeof(int) * off.size()));
     if (rows > bt->ev_cap) {
+        PBSO_CUDA(cudaStreamSynchronize(bt->stream));                // renders in flight still read the old buffers
         cudaFree(bt->d_ev_buf); cudaFree(bt->d_ev_space); cudaFree(bt->d_ev_src);
         bt->d_ev_buf = nullptr; bt->d_ev_space = nullptr; bt->d_ev_src = nullptr; bt->ev_cap = 0;
         PBSO_CUDA(cudaMalloc(&bt->d_ev_buf, sizeof(int) * rows));
@@ -635,7 +645,8 @@ int pbso_batch_set_impulses(pbso_batch* bt, int n_events, const int* obj, const 
             PBSO_CUDA(cudaGetLastError());
         }
     }
-    PBSO_CUDA(cudaStreamSynchronize(bt->stream));      // the caller may reuse its buffers on return
+    // off / sbuf / src are pageable: cudaMemcpyAsync has staged them when it returns; `space` may be pinned
+    if (wait) PBSO_CUDA(cudaStreamSynchronize(bt->stream));          // the caller may reuse its buffers on return
     bt->h_ev_off = off; bt->h_ev_buf.assign(sbuf.begin(), sbuf.begin() + n_events); ++bt->ev_ver;
     bt->n_events = n_events;
     return PBSO_OK;

@@ -260,6 +260,44 @@ int pbso_measure_tc_peak(int kind, int cta_group, int n, int stress, double* tfl
     return PBSO_ERR_INVALID;
 }
 
+// The same loop launched back to back for at least min_ms of device time: the tensor pipe's SUSTAINED rate under the
+// board's power cap, the denominator for a kernel that is timed inside a long step (the burst figure above is for a
+// kernel timed alone).
+int pbso_measure_tc_peak_sustained(int kind, int cta_group, int n, double min_ms, double* tflops) {
+    if (int rc = check_device()) return rc;
+    PBSO_REQUIRE(tflops && min_ms > 0, PBSO_ERR_INVALID, "bad argument");
+    double burst = 0.0, cyc = 0.0;
+    if (int rc = pbso_measure_tc_peak(kind, cta_group, n, 0, &burst, &cyc, nullptr)) return rc;     // also validates the arguments
+    int dev; PBSO_CUDA(cudaGetDevice(&dev));
+    int sms; PBSO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int iters = 20000, grid = (sms / cta_group) * cta_group;
+    const double flop_per_launch = 2.0 * 128.0 * n * (kind == 0 ? 8.0 : 16.0) * 4.0 * iters * grid;
+    const int launches = std::max(4, (int)(min_ms / (flop_per_launch / (burst * 1e12) * 1e3)) + 1);
+    cudaEvent_t e0, e1; PBSO_CUDA(cudaEventCreate(&e0)); PBSO_CUDA(cudaEventCreate(&e1));
+    unsigned long long *d_cyc, *d_ops;
+    PBSO_CUDA(cudaMalloc(&d_cyc, sizeof(unsigned long long) * grid));
+    PBSO_CUDA(cudaMalloc(&d_ops, sizeof(unsigned long long)));
+    const int smem = (n / cta_group) * 128 + 16384 + 64 + 1024;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cta_group; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    PBSO_CUDA(cudaEventRecord(e0));
+    for (int l = 0; l < launches; ++l) {
+#define PBSO_SUS(K_, C_, N_) if (kind == K_ && cta_group == C_ && n == N_) PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_tc_peak<K_, C_, N_>, iters, 0, d_cyc, d_ops))
+        PBSO_SUS(0, 1, 128); PBSO_SUS(0, 1, 256); PBSO_SUS(0, 2, 128); PBSO_SUS(0, 2, 256);
+        PBSO_SUS(1, 1, 128); PBSO_SUS(1, 1, 256); PBSO_SUS(1, 2, 128); PBSO_SUS(1, 2, 256);
+#undef PBSO_SUS
+    }
+    PBSO_CUDA(cudaEventRecord(e1));
+    PBSO_CUDA(cudaEventSynchronize(e1));
+    float ms; PBSO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *tflops = flop_per_launch * launches / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_cyc); cudaFree(d_ops);
+    return PBSO_OK;
+}
+
 int pbso_tc_selftest(int kind, double* max_err) {
     if (int rc = check_device()) return rc;
     PBSO_REQUIRE(max_err && (kind == 0 || kind == 1), PBSO_ERR_INVALID, "bad argument");
