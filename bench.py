@@ -86,8 +86,9 @@ def cpu_render_sample(n_threads, obj_per_thread, n_modes, n_buf, seed):
 def cpu_render_sample_ref(n_threads, n_modes, n_buf, seed):
     """The same loop run by the reference's OWN headers (oracle/_ref: ModalSolver<double,256>::step compiled in place
     against the Eigen shim), one object per host thread.  Returns (mode_samples, seconds) or None when _ref is absent.
-    Reported beside the port: the shim's eager temporaries make it ~4-5x slower than the port, so the port (the
-    faster, i.e. conservative, CPU number) stays the headline baseline."""
+    Reported beside the port on the same sample (same objects, same length); the faster of the two loops on a given host is
+    the conservative CPU number -- in this container the shim's eager temporaries make the headers build 4-5x slower than
+    the port, on the round-1 GPU box the two were equal."""
     from oracle import oracle as orc
     from openpbso_b200 import synth
     if orc.ref() is None:
@@ -104,9 +105,9 @@ def cpu_render_sample_ref(n_threads, n_modes, n_buf, seed):
     return float(n_threads) * n_modes * n_buf * BUF, time.perf_counter() - t0
 
 
-def reference_headers_entry(cores, n_modes):
-    n_buf = 173                                   # 1 s of audio per object (cfg1's length), impulse in buffer 0..171
-    r = cpu_render_sample_ref(cores, n_modes, n_buf, 1007)
+def reference_headers_entry(cores, n_modes, n_buf):
+    """The same sample as the port's (one object per host thread, full length), run by the reference's own headers."""
+    r = cpu_render_sample_ref(cores, n_modes, n_buf, 1005)
     if r is None:
         return None
     return {"value": r[0] / r[1], "unit": "mode-samples/s", "cores": cores, "kind": "reference",
@@ -149,7 +150,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "mode-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    rh = reference_headers_entry(cores, args.modes)
+    rh = reference_headers_entry(cores, args.modes, args.buffers)
     if rh:
         line["cpu_baseline"]["reference_headers"] = rh
     emit(line)
@@ -343,6 +344,52 @@ def moving_listeners_latency(pbso, synth, n_buffers=2000):
             "max_us": float(us.max()), "mode_samples_per_s": float(N * BUF / np.mean(lat)),
             "listener_mode_samples_per_s": float(N * BUF * L / np.mean(lat)), "dtype": "f64",
             "budget_us": 1e6 * BUF / synth.SAMPLE_RATE}
+
+
+def contact_storm(pbso, synth, tf32_peak, n_buffers=300):
+    """cfg3: 100 k impulses/s on 2048 modes x 20 000 vertices = 580 vertex impulses per 256-sample buffer, projected by the
+    tensor-core GEMM (K5) and rendered (K1) without leaving the device: pbso_modes_storm_buffer with host pointers in and out.
+    Parity: the same buffers through the FP64 sparse-gather path (the reference's arithmetic; tests/ pins it to the oracle)."""
+    M, V, B, T = 2048, 20000, 580, BUF
+    K = 3 * V
+    mat = synth.MATERIALS["low_damping"]
+    f = synth.mode_frequencies(M, 1003)
+    a, b = synth.ab_from_material(f, mat)
+    U = synth.mode_shapes(M, K, 1003)
+    md = pbso.ModeShapes(U)
+    rng = np.random.default_rng(1003)
+    tr = np.abs(rng.standard_normal(M)) + 0.1
+    vids = rng.integers(0, V, (16, B)).astype(np.int32)
+    vns = np.stack([synth.unit_vectors(B, 3000 + i) for i in range(16)])
+    res = {}
+    ys = {}
+    for name, prec in (("f64_sparse", pbso.PREC_F64), ("tf32x3_dense", pbso.PREC_TF32X3)):
+        it = pbso.ModalIntegrator(M, synth.H, a, b); it.set_transfer(tr)
+        for i in range(5):
+            md.storm_buffer(it, vids[i % 16], vns[i % 16], T, prec)
+        it2 = pbso.ModalIntegrator(M, synth.H, a, b); it2.set_transfer(tr)
+        out = []
+        lat = np.empty(n_buffers); kms = []
+        for i in range(n_buffers):
+            t0 = time.perf_counter()
+            y, _ = md.storm_buffer(it2, vids[i % 16], vns[i % 16], T, prec)
+            lat[i] = time.perf_counter() - t0
+            if i < 32: out.append(y[0].copy())
+            if i % 16 == 0: kms.append(md.last_kernel_ms())
+        ys[name] = np.concatenate(out)
+        us = lat * 1e6
+        res[name] = {"p50_us": float(np.percentile(us, 50)), "p99_us": float(np.percentile(us, 99)), "impulses_per_s": float(B / np.mean(lat)),
+                     "projection_kernels_ms": float(np.median(kms)), "x_realtime": float((T / synth.SAMPLE_RATE) / np.mean(lat))}
+        it.close(); it2.close()
+    k5 = res["tf32x3_dense"]["projection_kernels_ms"]
+    res["tf32x3_dense"]["issued_tflops"] = 3 * 2.0 * M * K * B / (k5 * 1e-3) / 1e12
+    res["tf32x3_dense"]["frac_of_tf32_peak"] = res["tf32x3_dense"]["issued_tflops"] / tf32_peak
+    d = ys["tf32x3_dense"] - ys["f64_sparse"]
+    return {"workload": "cfg3: %d modes x %d vertices, %d vertex impulses per %d-sample buffer (100 k impulses/s), host pointers in and out of pbso_modes_storm_buffer" % (M, V, B, T),
+            "buffers": n_buffers, "budget_us": 1e6 * T / synth.SAMPLE_RATE, "paths": res,
+            "parity_tf32x3_vs_f64_sparse": {"rel_l2": float(np.linalg.norm(d) / np.linalg.norm(ys["f64_sparse"])),
+                                            "max_abs": float(np.max(np.abs(d)) / np.max(np.abs(ys["f64_sparse"]))), "buffers": 32},
+            "note": "projection_kernels_ms covers the zero-fill of the dense load vectors, the scatter, the TF32 split of F, the tensor-core GEMM and the load sum"}
 
 
 def run_ours(args):
@@ -559,12 +606,13 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": ms / dt, "unit": "mode-samples/s", "cores": cores, "kind": "port",
                                 "sample": "%d objects x %d modes x %d samples (1 object per host thread, %s), %.1f s" % (
                                     cores, args.modes, n_samples, model, dt)}
-        rh = reference_headers_entry(cores, args.modes)
+        rh = reference_headers_entry(cores, args.modes, args.buffers)
         if rh:
             line["cpu_baseline"]["reference_headers"] = rh
     if not args.no_realtime:
         line["realtime"] = realtime_latency(pbso, synth)
         line["moving_listeners"] = moving_listeners_latency(pbso, synth)
+        line["contact_storm"] = contact_storm(pbso, synth, tf32_peak_measured)
     emit(line)
     if world > 1:
         dist.barrier(); comm.close(); dist.destroy_process_group()

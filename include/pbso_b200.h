@@ -69,6 +69,10 @@ int pbso_integrator_create(int N, double h, const double* a, const double* b,
                            pbso_integrator** out);
 int pbso_integrator_destroy(pbso_integrator* it);
 int pbso_integrator_size(const pbso_integrator* it, int* N);
+/* Listeners of the resident transfer table (the L of the last set_transfer call), and the handle's CUDA stream
+ * (cudaStream_t as void*): device-resident callers order their own work with the renders through it. */
+int pbso_integrator_listeners(const pbso_integrator* it, int* L);
+int pbso_integrator_stream(const pbso_integrator* it, void** cuda_stream);
 /* _c1/_c2/_c3 (modal_integrator.h:32-34, 95-99); any pointer may be NULL. */
 int pbso_integrator_get_coeffs(const pbso_integrator* it, double* c1, double* c2, double* c3);
 /* Step(Q) / Step() (modal_integrator.h:43-44, 103-123); Q == NULL selects Step().
@@ -196,6 +200,18 @@ int pbso_modes_last_kernel_ms(const pbso_modes* md, float* ms);
 /* K5 with device-resident FP32 inputs/outputs (d_F[B][K], d_Y[B][force_dim]); enqueue only. */
 int pbso_modes_project_dense_device(const pbso_modes* md, int force_dim, const float* d_F, int B,
                                     float* d_Y, void* cuda_stream);
+
+/* Contact storm, one audio buffer, projection -> load -> integrator without leaving the device:
+ * B vertex impulses land on sample 0 of the buffer; their modal loads add up (superposition; the caller of the reference
+ * sums them into the ONE ForceMessage a buffer can take, modal_solver.h:184, 206-221):
+ *     space[m] = sum_b vn_b . U_m[3 vid_b .. 3 vid_b + 2]     (GetModalForceVertex, tools/real_time_modal_sound.cpp:268-280)
+ *     y        = pbso_render_buffer(it, space, PointForce profile, T)
+ * PBSO_PREC_TF32X3: the impulses are expanded to dense load vectors F[B][K] on the device and contracted with U by the
+ * tensor-core GEMM (kernel K5) -- the batched projection of the north star; PBSO_PREC_F64: sparse gather (K4s), the
+ * reference's arithmetic.  Everything runs on the integrator's stream; host pointers in and out (pinned staging inside);
+ * y_out[L*T] listener-major, qnorm_out[N] or NULL.  force_dim must equal the integrator's N. */
+int pbso_modes_storm_buffer(pbso_modes* md, pbso_integrator* it, int force_dim, int B, const int* vids,
+                            const double* vn, int T, double* y_out, double* qnorm_out, int precision);
 
 /* ---- offline batch renderer (many objects x long audio) ------------- */
 /* n_obj independent sound objects with n_modes each; (a,b) are n_obj x n_modes as accepted by

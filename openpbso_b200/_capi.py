@@ -54,6 +54,9 @@ def lib():
             "pbso_integrator_create": [C.c_int, C.c_double, c_dp, c_dp, c_vpp],
             "pbso_integrator_destroy": [vp],
             "pbso_integrator_size": [vp, c_ip],
+            "pbso_integrator_listeners": [vp, c_ip],
+            "pbso_integrator_stream": [vp, c_vpp],
+            "pbso_modes_storm_buffer": [vp, vp, C.c_int, C.c_int, c_ip, c_dp, C.c_int, c_dp, c_dp, C.c_int],
             "pbso_integrator_get_coeffs": [vp, c_dp, c_dp, c_dp],
             "pbso_integrator_step": [vp, c_dp, c_dp],
             "pbso_integrator_get_state": [vp, c_dp, c_dp],

@@ -368,6 +368,15 @@ class ModeShapes:
     def last_kernel_ms(self):
         ms = C.c_float(); check(lib().pbso_modes_last_kernel_ms(self._h, C.byref(ms))); return ms.value
 
+    def storm_buffer(self, integrator, vids, vn, T, precision=capi.PREC_TF32X3, want_qnorm=False):
+        """cfg3 contact storm, one buffer on the device: B vertex impulses -> projection -> summed load -> K1.
+        Returns (y[L][T], qnorm or None)."""
+        vids = np.ascontiguousarray(vids, dtype=np.int32); vn = f64(vn).reshape(len(vids), 3)
+        L = max(getattr(integrator, "L", 1), 1)
+        y = np.empty((L, T)); qn = np.empty(integrator.N) if want_qnorm else None
+        check(lib().pbso_modes_storm_buffer(self._h, integrator._h, integrator.N, len(vids), ip(vids), dp(vn), T, dp(y), dp(qn), precision))
+        return y, qn
+
     def project_dense_device(self, d_F_ptr, B, d_Y_ptr, forceDim=None, stream_ptr=0):
         n = self.M if forceDim is None else forceDim
         check(lib().pbso_modes_project_dense_device(self._h, n, C.c_void_p(d_F_ptr), B, C.c_void_p(d_Y_ptr),

@@ -477,8 +477,8 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
 #define PBSO_LAUNCH_POW(TT)                                                                              \
         k_batch_pow<TT><<<grid, FB_WARPS * 32, 0, bt->stream>>>(bt->n_modes, slabs, n_buffers, bt->lneps(), \
             bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, d_mix, d_stems)
-        // default: 16 warps x 16 modes, 64-sample tiles, packed FFMA2 (best of the measured variants, see profiles/)
-        static const int variant = getenv("PBSO_POW_VARIANT") ? atoi(getenv("PBSO_POW_VARIANT")) : 1;
+        // 16 warps x 16 modes, 64-sample tiles, packed FFMA2: the best of the variants measured in round 1
+        // (profiles/r1_k_batch_pow.md); the others are gone
 #define PBSO_LAUNCH_G(W, MB, JJ, ...)                                                                      \
         do { const int sl = div_up(bt->n_modes, (W) * (MB));                                               \
              /* time chunks: enough CTAs for ~4 waves of SMs when there are few objects; >= 8 buffers each */ \
@@ -488,18 +488,9 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
              k_batch_pow_g<W, MB, JJ, __VA_ARGS__><<<bt->n_obj * sl * nc, (W) * 32, 0, bt->stream>>>(bt->n_modes, sl, n_buffers, nc, bpc, \
                  bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf,  \
                  bt->d_ev_space, d_mix, d_stems); } while (0)
-        if (buf_size == 256 && variant == 1) PBSO_LAUNCH_G(16, 16, 2, true);
-        else if (buf_size == 256 && variant == 2) PBSO_LAUNCH_G(8, 16, 4, false);
-        else if (buf_size == 256 && variant == 3) PBSO_LAUNCH_G(8, 16, 4, true);
-        else if (buf_size == 256 && variant == 4) PBSO_LAUNCH_G(16, 8, 4, true);
-        else if (buf_size == 256 && variant == 5) PBSO_LAUNCH_G(8, 8, 8, true);
-        else if (buf_size == 256 && variant == 6) PBSO_LAUNCH_G(8, 16, 2, true, 2);
-        else if (buf_size == 256 && variant == 7) PBSO_LAUNCH_G(4, 16, 2, true, 4);
-        else if (buf_size == 256 && variant == 8) PBSO_LAUNCH_G(12, 16, 4, true);
-        else if (buf_size == 256 && variant == 9) PBSO_LAUNCH_G(11, 16, 4, true);
+        if (buf_size == 256) PBSO_LAUNCH_G(16, 16, 2, true);
         else if (buf_size == 64) PBSO_LAUNCH_POW(1);
         else if (buf_size == 128) PBSO_LAUNCH_POW(2);
-        else if (buf_size == 256) PBSO_LAUNCH_POW(4);
         else return set_error(PBSO_ERR_UNSUPPORTED, "PBSO_PREC_F32_TILED needs buf_size in {64,128,256}; got %d (use PBSO_PREC_F64)", buf_size);
 #undef PBSO_LAUNCH_POW
     } else if (precision == PBSO_PREC_TC3X) {

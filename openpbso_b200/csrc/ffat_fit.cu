@@ -44,13 +44,6 @@ constexpr int FIT_MAX_SHELLS = 8;
 #ifndef FIT_MIN_BLOCKS
 #define FIT_MIN_BLOCKS 4
 #endif
-// TMA-staged variant (three shells): per (block, mode) the quads a block's 128 directions touch form one contiguous
-// range per shell; boxes of FIT_BOX quads are pulled into a ring of FIT_STAGES stages through a tensor map whose rows
-// are 32 bytes apart but only 16 bytes wide -- the copy engine drops the unused odd entries on the way in.
-constexpr int FIT_BOX = 64;              // quads per box (1 KB in shared memory)
-constexpr int FIT_STAGE_BOXES = 8;       // 8 KB per stage
-constexpr int FIT_STAGES = 4;
-
 struct FitGeo {                      // per shell, host + device copy
     double geom[32];
     int igeom[18];
@@ -208,118 +201,6 @@ k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, co
     }
 }
 
-// Same fit, pressure staged through shared memory by the TMA engine.  Thread = direction; thread 0 also drives the copies.
-__global__ void __launch_bounds__(FIT_THREADS)
-k_fit_solve_tma(const __grid_constant__ CUtensorMap tm, int n_dir, int n_total, int n_maps, int maps_per_block,
-                const int* __restrict__ st_idx, const double* __restrict__ st_w, const double* __restrict__ st_c,
-                const double* __restrict__ st_inv_r0, const double* __restrict__ kvec,
-                const double2* __restrict__ pressure, double* __restrict__ psi_out, int power_scaling,
-                double2* __restrict__ partial) {
-    __shared__ __align__(128) double2 s_stage[FIT_STAGES][FIT_STAGE_BOXES * FIT_BOX];
-    __shared__ __align__(8) uint64_t s_full[FIT_STAGES];
-    __shared__ int s_lo[3], s_hi[3];
-    __shared__ double2 s_red[FIT_THREADS / 32];
-    const int d = blockIdx.x * FIT_THREADS + threadIdx.x;
-    const bool live = d < n_dir;
-    const int dc = live ? d : n_dir - 1;
-    int q[3][4]; double w[3][4], c[3];
-    if (threadIdx.x < 3) { s_lo[threadIdx.x] = 0x7fffffff; s_hi[threadIdx.x] = -1; }
-    __syncthreads();
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-        c[s] = st_c[(size_t)s * n_dir + dc];
-        int lo = 0x7fffffff, hi = -1;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            q[s][kk] = st_idx[((size_t)s * 4 + kk) * n_dir + dc] >> 1;              // quad index within one mode's vector
-            w[s][kk] = st_w[((size_t)s * 4 + kk) * n_dir + dc];
-            lo = min(lo, q[s][kk]); hi = max(hi, q[s][kk]);
-        }
-        lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-        if ((threadIdx.x & 31) == 0) { atomicMin(&s_lo[s], lo); atomicMax(&s_hi[s], hi); }
-    }
-    const double inv_r0 = st_inv_r0[dc];
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < FIT_STAGES; ++i) umma::mbar_init(&s_full[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    int lo[3], nbox[3], boff[3], boxes = 0;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) { lo[s] = s_lo[s]; nbox[s] = (s_hi[s] - lo[s]) / FIT_BOX + 1; boff[s] = boxes; boxes += nbox[s]; }
-    const bool staged = boxes <= FIT_STAGE_BOXES;                                   // block-uniform
-    if (staged) {
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) q[s][kk] += boff[s] * FIT_BOX - lo[s];    // -> entry index inside a stage
-    }
-    const int m0 = blockIdx.y * maps_per_block, n_local = min(n_maps, m0 + maps_per_block) - m0;
-    auto issue = [&](int i) {                                                       // thread 0 only
-        const int st = i % FIT_STAGES;
-        umma::mbar_expect_tx(&s_full[st], (uint32_t)(boxes * FIT_BOX * sizeof(double2)));
-        const int row0 = (m0 + i) * n_total;
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-            for (int b = 0; b < nbox[s]; ++b)
-                umma::tma_load_2d(&s_stage[st][(boff[s] + b) * FIT_BOX], &tm, 0, row0 + lo[s] + b * FIT_BOX, &s_full[st]);
-    };
-    if (staged && threadIdx.x == 0)
-        for (int i = 0; i < min(FIT_STAGES, n_local); ++i) issue(i);
-    for (int i = 0; i < n_local; ++i) {
-        const int m = m0 + i;
-        const double k = kvec[m];
-        double acc = 0.0, pa0 = 0.0;
-        double2 v[3][4];
-        if (staged) {
-            const int st = i % FIT_STAGES;
-            umma::mbar_wait(&s_full[st], (uint32_t)((i / FIT_STAGES) & 1));
-#pragma unroll
-            for (int s = 0; s < 3; ++s)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) v[s][kk] = s_stage[st][q[s][kk]];
-        } else {
-            const double2* P = pressure + (size_t)m * 2 * n_total;
-#pragma unroll
-            for (int s = 0; s < 3; ++s)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) v[s][kk] = __ldg(P + 2 * q[s][kk]);
-        }
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            double pre = 0.0, pim = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) { pre += w[s][kk] * v[s][kk].x; pim += w[s][kk] * v[s][kk].y; }   // ffat_solver.h:1052-1057
-            const double p2 = cabs_fast(pre, pim);                                 // :885
-            acc += c[s] * p2;
-            if (s == 0) pa0 = p2;
-        }
-        if (live) psi_out[(size_t)m * n_dir + d] = k * acc;                          // :888-895, folded
-        if (power_scaling) {                                                         // :918-923, shell 0
-            const double qq = acc * inv_r0;
-            double2 t2 = live ? make_double2(pa0 * pa0, qq * qq) : make_double2(0.0, 0.0);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                t2.x += __shfl_down_sync(0xffffffffu, t2.x, o);
-                t2.y += __shfl_down_sync(0xffffffffu, t2.y, o);
-            }
-            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t2;
-        }
-        __syncthreads();                                                             // stage consumed; s_red complete
-        if (threadIdx.x == 0) {
-            if (power_scaling) {
-                double2 t = s_red[0];
-#pragma unroll
-                for (int j = 1; j < FIT_THREADS / 32; ++j) { t.x += s_red[j].x; t.y += s_red[j].y; }
-                partial[(size_t)m * gridDim.x + blockIdx.x] = t;
-            }
-            if (staged && i + FIT_STAGES < n_local) issue(i + FIT_STAGES);
-        }
-        if (power_scaling) __syncthreads();                                          // s_red free for the next mode
-    }
-}
-
 // One block per mode: finish the two sums in block order, scale = sqrt(numer/denom) (:924), Psi *= scale (:925-927).
 __global__ void __launch_bounds__(256)
 k_fit_scale(int n_dir, int n_blocks, const double2* __restrict__ partial, double* __restrict__ psi,
@@ -356,31 +237,6 @@ __global__ void k_fit_fill(int n, double v, double* __restrict__ out) {
     if (i < n) out[i] = v;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// The pressure of all modes as a 2-D tensor of doubles: row = one quad's FIRST complex entry (2 doubles, 16 bytes),
-// rows 32 bytes apart (the second-triangle entry in between is never fetched into shared memory).
-static int encode_pressure_map(CUtensorMap* map, const double* d_p, size_t n_rows) {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        cudaDriverEntryPointQueryResult q;
-        void* p = nullptr;
-        PBSO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (!p || q != cudaDriverEntryPointSuccess) return set_error(PBSO_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-        fn = (EncodeTiledFn)p;
-    }
-    const cuuint64_t dims[2] = {2, (cuuint64_t)n_rows};                              // innermost first
-    const cuuint64_t strides[1] = {32};
-    const cuuint32_t box[2] = {2, (cuuint32_t)FIT_BOX};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)d_p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(PBSO_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-    return PBSO_OK;
-}
-
 static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, const double* d_p, int power_scaling,
                         double* d_psi, double* d_scale, cudaStream_t s) {
     const int gx = div_up(f->n_dir, FIT_THREADS);
@@ -397,21 +253,9 @@ static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, cons
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, f->device);
     const double2* P = reinterpret_cast<const double2*>(d_p);
     double2* part = reinterpret_cast<double2*>(f->d_partial);
-    // Measured on B200 (profiles/r1_ffat_fit.md): the TMA-staged kernel (16-byte rows at a 32-byte pitch) runs at the
-    // same ~110 us as the direct gathers for 1024 modes -- the copy engine is slow on 16-byte rows -- so the simpler
-    // direct kernel is the default and staging is opt-in.
-    const char* env = getenv("PBSO_FIT_TMA");
-    const bool tma = env && env[0] == '1';
-    if (f->S == 3 && tma && (long long)n_maps * f->n_total < (1ll << 31)) {
-        // TMA-staged: fold up to 32 modes into a block (the ring needs a run of modes to stream) while keeping
-        // >= 4 blocks per SM
-        int mpb = 1;
-        while (mpb < 32 && (long long)gx * div_up(n_maps, mpb * 2) >= (long long)sm * 4) mpb *= 2;
-        CUtensorMap tm;
-        if (int rc = encode_pressure_map(&tm, d_p, (size_t)n_maps * f->n_total)) return rc;
-        k_fit_solve_tma<<<dim3(gx, div_up(n_maps, mpb)), FIT_THREADS, 0, s>>>(tm, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w,
-                                                                              f->d_c, f->d_inv_r0, d_k, P, d_psi, power_scaling, part);
-    } else {
+    // (a TMA-staged variant -- 16-byte rows at a 32-byte pitch through a shared-memory ring -- was measured in round 1 and was
+    // no faster, profiles/r1_ffat_fit.md: removed)
+    {
         // direct gathers: enough blocks for ~16 resident CTAs on every SM before modes are folded into a block
         int mpb = 1;
         while (mpb < 8 && (long long)gx * div_up(n_maps, mpb * 2) >= (long long)sm * 16) mpb *= 2;

@@ -324,6 +324,18 @@ int pbso_integrator_destroy(pbso_integrator* it) {
     return PBSO_OK;
 }
 
+int pbso_integrator_stream(const pbso_integrator* it, void** cuda_stream) {
+    PBSO_REQUIRE(it && cuda_stream, PBSO_ERR_INVALID, "null argument");
+    *cuda_stream = (void*)it->stream;
+    return PBSO_OK;
+}
+
+int pbso_integrator_listeners(const pbso_integrator* it, int* L) {
+    PBSO_REQUIRE(it && L, PBSO_ERR_INVALID, "null argument");
+    *L = it->L;
+    return PBSO_OK;
+}
+
 int pbso_integrator_size(const pbso_integrator* it, int* N) {
     PBSO_REQUIRE(it && N, PBSO_ERR_INVALID, "null argument");
     *N = it->N;

@@ -31,6 +31,9 @@ struct pbso_modes {
     float* d_Fsplit = nullptr; size_t fsplit_cap = 0;      // F_hi | F_lo planes
     int sm_count = 148;
     cudaEvent_t e0 = nullptr, e1 = nullptr;                // bracket the last projection kernel(s)
+    // contact-storm pipeline (pbso_modes_storm_buffer): dense load vectors, projected loads, summed load, delta profile, output
+    void* d_storm = nullptr; size_t storm_cap = 0;
+    double* h_storm = nullptr; size_t h_storm_cap = 0;     // pinned staging
 };
 
 namespace pbso {
@@ -225,7 +228,8 @@ int pbso_modes_destroy(pbso_modes* md) {
     if (!md) return PBSO_OK;
     DeviceGuard g(md->device);
     if (md->stream) cudaStreamSynchronize(md->stream);
-    cudaFree(md->d_U); cudaFree(md->d_scratch); cudaFree(md->d_Uhi); cudaFree(md->d_Ulo); cudaFree(md->d_Fsplit);
+    cudaFree(md->d_U); cudaFree(md->d_scratch); cudaFree(md->d_Uhi); cudaFree(md->d_Ulo); cudaFree(md->d_Fsplit); cudaFree(md->d_storm);
+    if (md->h_storm) cudaFreeHost(md->h_storm);
     if (md->e0) cudaEventDestroy(md->e0);
     if (md->e1) cudaEventDestroy(md->e1);
     if (md->stream) cudaStreamDestroy(md->stream);
@@ -324,6 +328,96 @@ int pbso_modes_project_dense_device(const pbso_modes* mdc, int force_dim, const 
     const size_t plane = (size_t)B * tc_pitch(md->K);
     if (int rc = tc_split_f32(d_F, B, md->K, md->d_Fsplit, md->d_Fsplit + plane, st)) return rc;
     return tc_project(md->d_Uhi, md->d_Ulo, force_dim, md->d_Fsplit, md->d_Fsplit + plane, B, md->K, d_Y, md->sm_count, st);
+}
+
+// ---- cfg3: contact storm -> projection -> rank-1 load -> integrator, one buffer, all on the integrator's stream ----------
+// F[b][3 vid_b + d] = vn_b[d]: the dense load vector of a vertex impulse (what GetModalForceVertex contracts with U)
+}  // extern "C" (kernels below)
+__global__ void k_storm_scatter(int B, int K, const int* __restrict__ vids, const double* __restrict__ vn, float* __restrict__ F) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float* row = F + (size_t)b * K + 3 * (size_t)vids[b];
+    row[0] = (float)vn[3 * b]; row[1] = (float)vn[3 * b + 1]; row[2] = (float)vn[3 * b + 2];
+}
+// space[m] = sum_b Y[b][m]  (ModalSolver::step sums the spatial loads of the active forces, modal_solver.h:206-221)
+template <typename T>
+__global__ void k_storm_sum(int B, int M, const T* __restrict__ Y, double* __restrict__ space) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int b = 0;
+    for (; b + 3 < B; b += 4) {
+        a0 += (double)Y[(size_t)b * M + m]; a1 += (double)Y[(size_t)(b + 1) * M + m];
+        a2 += (double)Y[(size_t)(b + 2) * M + m]; a3 += (double)Y[(size_t)(b + 3) * M + m];
+    }
+    for (; b < B; ++b) a0 += (double)Y[(size_t)b * M + m];
+    space[m] = (a0 + a1) + (a2 + a3);
+}
+extern "C" {
+
+int pbso_modes_storm_buffer(pbso_modes* md, pbso_integrator* it, int force_dim, int B, const int* vids, const double* vn,
+                            int T, double* y_out, double* qnorm_out, int precision) {
+    PBSO_REQUIRE(md && it && vids && vn && y_out && B > 0 && T > 0, PBSO_ERR_INVALID, "bad argument");
+    PBSO_REQUIRE(precision == PBSO_PREC_F64 || precision == PBSO_PREC_TF32X3, PBSO_ERR_INVALID, "precision must be PBSO_PREC_F64 or PBSO_PREC_TF32X3");
+    int N = 0; if (int rc = pbso_integrator_size(it, &N)) return rc;
+    PBSO_REQUIRE(force_dim == N && force_dim <= md->M, PBSO_ERR_RANGE, "forceDim must equal the integrator's mode count and not exceed the mode shapes");
+    for (int i = 0; i < B; ++i)
+        if (vids[i] < 0 || (long long)vids[i] * 3 + 2 >= md->K)
+            return set_error(PBSO_ERR_RANGE, "vertex id %d outside the %d DOFs (std::vector::at)", vids[i], md->K);
+    DeviceGuard g(md->device);
+    void* sv = nullptr; if (int rc = pbso_integrator_stream(it, &sv)) return rc;
+    cudaStream_t st = (cudaStream_t)sv;
+    const int K = md->K, M = force_dim;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const bool dense = precision == PBSO_PREC_TF32X3;
+    const size_t o_vid = 0, o_vn = al(sizeof(int) * B), o_F = o_vn + al(sizeof(double) * 3 * B);
+    const size_t o_Y = o_F + (dense ? al(sizeof(float) * (size_t)B * K) : 0);
+    const size_t o_sp = o_Y + al((dense ? sizeof(float) : sizeof(double)) * (size_t)B * M);
+    const size_t o_tm = o_sp + al(sizeof(double) * M), o_y = o_tm + al(sizeof(double) * T);
+    const size_t o_q = o_y + al(sizeof(double) * 64 * (size_t)T), total = o_q + al(sizeof(double) * M);
+    if (total > md->storm_cap) {
+        PBSO_CUDA(cudaStreamSynchronize(st));
+        cudaFree(md->d_storm); md->d_storm = nullptr; md->storm_cap = 0;
+        PBSO_CUDA(cudaMalloc(&md->d_storm, total)); md->storm_cap = total;
+    }
+    const size_t h_need = (size_t)4 * B + 64 * (size_t)T + M + T;
+    if (h_need > md->h_storm_cap) {
+        if (md->h_storm) cudaFreeHost(md->h_storm);
+        md->h_storm = nullptr; md->h_storm_cap = 0;
+        PBSO_CUDA(cudaMallocHost(&md->h_storm, sizeof(double) * h_need)); md->h_storm_cap = h_need;
+    }
+    char* d = (char*)md->d_storm;
+    // pinned staging: vids | vn | delta profile in, y | qnorm out
+    int* h_vid = (int*)md->h_storm; double* h_vn = md->h_storm + (B + 1) / 2; double* h_tm = h_vn + 3 * B; double* h_y = h_tm + T; double* h_q = h_y + 64 * (size_t)T;
+    std::memcpy(h_vid, vids, sizeof(int) * B); std::memcpy(h_vn, vn, sizeof(double) * 3 * B);
+    std::memset(h_tm, 0, sizeof(double) * T); h_tm[0] = 1.0;                     // PointForce::Add (forces.h:87)
+    PBSO_CUDA(cudaMemcpyAsync(d + o_vid, h_vid, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    PBSO_CUDA(cudaMemcpyAsync(d + o_vn, h_vn, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, st));
+    PBSO_CUDA(cudaMemcpyAsync(d + o_tm, h_tm, sizeof(double) * T, cudaMemcpyHostToDevice, st));
+    PBSO_CUDA(cudaEventRecord(md->e0, st));
+    if (dense) {
+        PBSO_CUDA(cudaMemsetAsync(d + o_F, 0, sizeof(float) * (size_t)B * K, st));
+        k_storm_scatter<<<div_up(B, 128), 128, 0, st>>>(B, K, (const int*)(d + o_vid), (const double*)(d + o_vn), (float*)(d + o_F));
+        PBSO_CUDA(cudaGetLastError());
+        if (int rc = pbso_modes_project_dense_device(md, M, (const float*)(d + o_F), B, (float*)(d + o_Y), (void*)st)) return rc;
+        k_storm_sum<float><<<div_up(M, 128), 128, 0, st>>>(B, M, (const float*)(d + o_Y), (double*)(d + o_sp));
+    } else {
+        k_project_sparse<<<dim3(div_up(M, 128), std::min(B, 65535)), 128, 0, st>>>(M, K, B, 1, md->d_U, (const int*)(d + o_vid), nullptr,
+                                                                               (const double*)(d + o_vn), (double*)(d + o_Y));
+        PBSO_CUDA(cudaGetLastError());
+        k_storm_sum<double><<<div_up(M, 128), 128, 0, st>>>(B, M, (const double*)(d + o_Y), (double*)(d + o_sp));
+    }
+    PBSO_CUDA(cudaGetLastError());
+    PBSO_CUDA(cudaEventRecord(md->e1, st));
+    if (int rc = pbso_render_buffer_device(it, (const double*)(d + o_sp), (const double*)(d + o_tm), T, (double*)(d + o_y), qnorm_out ? (double*)(d + o_q) : nullptr)) return rc;
+    int L = 1; pbso_integrator_listeners(it, &L);
+    PBSO_REQUIRE(L >= 0 && L <= 64, PBSO_ERR_UNSUPPORTED, "the storm entry stages at most 64 listeners");
+    if (L > 0) PBSO_CUDA(cudaMemcpyAsync(h_y, d + o_y, sizeof(double) * (size_t)L * T, cudaMemcpyDeviceToHost, st));
+    if (qnorm_out) PBSO_CUDA(cudaMemcpyAsync(h_q, d + o_q, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    PBSO_CUDA(cudaStreamSynchronize(st));
+    if (L > 0) std::memcpy(y_out, h_y, sizeof(double) * (size_t)L * T);
+    if (qnorm_out) std::memcpy(qnorm_out, h_q, sizeof(double) * M);
+    return PBSO_OK;
 }
 
 }  // extern "C"

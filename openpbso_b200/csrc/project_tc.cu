@@ -34,13 +34,15 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB per operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;               // A_hi A_lo B_hi B_lo
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TC_TMEM_COLS = 256;                               // two 128-column accumulators
+constexpr int TC_TMEM_COLS = 512;                               // hi*hi accumulators 0 | 128, small-product accumulators 256 | 384
 
 // Two-level accumulation.  The tensor core adds into its FP32 TMEM accumulator with truncation, so the error of a
-// chain grows linearly with its length (measured ~3e-8 per accumulating MMA).  The K loop is therefore cut into
-// chunks of TC_CHUNK K blocks (256 K elements = 96 MMAs): each chunk accumulates into one of two TMEM buffers
-// from zero, and the four epilogue warps promote finished chunks into FP32 registers (round-to-nearest adds)
-// while the MMA warp already works on the other buffer.
+// chain grows linearly with its length (~2.5e-8 per accumulating MMA, a coherent gain error).  The K loop is therefore
+// cut into chunks of TC_CHUNK K blocks (256 K elements): each chunk accumulates from zero -- the 32 hi*hi MMAs into one
+// TMEM buffer, the 64 small products (hi*lo, lo*hi: 2^-11 of the sum, their truncation does not matter) into another
+// -- and the four epilogue warps promote finished chunks into FP32 registers (round-to-nearest adds) while the MMA
+// warp already works on the other pair of buffers.  What is left of the hi*hi chains' truncation, a gain of
+// 1 + gm1 * (mean chain length / TC_CHUNK), is measured once per device (tc_project_calibrate) and divided out.
 constexpr int TC_CHUNK = 8;
 constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA (+ TMEM alloc), warps 2-5 epilogue
 
@@ -48,7 +50,7 @@ constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA (+ TMEM alloc
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_project_tc(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
              const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
-             float* __restrict__ Y, int M, int B, int kb_total, int kb_per_split, int use_atomics) {
+             float* __restrict__ Y, int M, int B, int kb_total, int kb_per_split, int use_atomics, float gm1) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B needs 1024 B alignment
     uint64_t* full = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -118,8 +120,8 @@ k_project_tc(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ 
                     const uint64_t dAh = umma_desc_k_sw128(a_hi + off), dAl = umma_desc_k_sw128(a_lo + off);
                     const uint64_t dBh = umma_desc_k_sw128(b_hi + off), dBl = umma_desc_k_sw128(b_lo + off);
                     umma_tf32(acc, dAh, dBh, idesc, (chunk_start && k == 0) ? 0u : 1u);
-                    umma_tf32(acc, dAh, dBl, idesc, 1u);
-                    umma_tf32(acc, dAl, dBh, idesc, 1u);
+                    umma_tf32(acc + 256, dAh, dBl, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                    umma_tf32(acc + 256, dAl, dBh, idesc, 1u);
                 }
                 umma_commit(&empty[s]);                               // frees the stage when these MMAs retire
                 if ((i % TC_CHUNK) == TC_CHUNK - 1 || i == nkb - 1) umma_commit(&acc_full[buf]);
@@ -137,32 +139,29 @@ k_project_tc(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ 
             mbar_wait(&acc_full[buf], ((uint32_t)c >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int q = 0; q < TC_BN / 32; ++q) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + q * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int part = 0; part < 2; ++part) {                   // hi*hi buffer, then the small-product buffer
 #pragma unroll
-                for (int j = 0; j < 32; ++j) accr[q * 32 + j] += __uint_as_float(v[j]);
+                for (int q = 0; q < TC_BN / 32; ++q) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(part * 256 + buf * TC_BN + q * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) accr[q * 32 + j] += __uint_as_float(v[j]);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[buf]);
         }
         if (m < M && nkb > 0) {
+            // mean truncation of this CTA's hi*hi chains: nkb / TC_CHUNK full ones and a tail, each weighted by its share of K
+            const int n_full = nkb / TC_CHUNK, tail = nkb % TC_CHUNK;
+            const float inv_gain = 1.f / (1.f + gm1 * (float)(n_full * TC_CHUNK * TC_CHUNK + tail * tail) / (float)(TC_CHUNK * nkb));
 #pragma unroll
             for (int j = 0; j < TC_BN; ++j) {
                 const int b = n0 + j;
                 if (b < B) {
-                    if (use_atomics) atomicAdd(&Y[(size_t)b * M + m], accr[j]);
-                    else Y[(size_t)b * M + m] = accr[j];
+                    if (use_atomics) atomicAdd(&Y[(size_t)b * M + m], accr[j] * inv_gain);
+                    else Y[(size_t)b * M + m] = accr[j] * inv_gain;
                 }
             }
         }
@@ -234,8 +233,15 @@ int tc_split_f32(const float* d_src, int rows, int cols, float* d_hi, float* d_l
 }
 
 // Y[B][M] (float, overwritten) = U[M][K] F[B][K]^T from pre-split planes (pitch tc_pitch(K)).
+static float g_proj_gm1[64];
+static bool g_proj_cal[64], g_proj_calibrating = false;
+static int tc_project_calibrate(int dev, int sm_count);
+
 int tc_project(const float* d_Uhi, const float* d_Ulo, int M, const float* d_Fhi, const float* d_Flo, int B, int K,
                float* d_Y, int sm_count, cudaStream_t s) {
+    int dev_c = 0; cudaGetDevice(&dev_c);
+    if (!g_proj_cal[dev_c & 63] && !g_proj_calibrating) { if (int rc = tc_project_calibrate(dev_c, sm_count)) return rc; }
+    const float gm1 = g_proj_calibrating ? 0.f : g_proj_gm1[dev_c & 63];
     const int pitch = tc_pitch(K);
     CUtensorMap mAh, mAl, mBh, mBl;
     if (int rc = encode_map(&mAh, d_Uhi, M, pitch)) return rc;
@@ -264,9 +270,50 @@ int tc_project(const float* d_Uhi, const float* d_Ulo, int M, const float* d_Fhi
     splits = div_up(kb_total, kb_per);
     if (splits > 1) PBSO_CUDA(cudaMemsetAsync(d_Y, 0, sizeof(float) * (size_t)B * M, s));
     k_project_tc<<<dim3(mt, nt, splits), TC_THREADS, TC_SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, d_Y, M, B, kb_total, kb_per,
-                                                                      splits > 1 ? 1 : 0);
+                                                                      splits > 1 ? 1 : 0, gm1);
     PBSO_CUDA(cudaGetLastError());
     return PBSO_OK;
 }
+
+// gm1 = (gain - 1) of a full hi*hi chain (TC_CHUNK K blocks = 32 accumulating MMAs): a 128 x 128 x 4096 product of
+// N(0,1) operands by k_project_tc (gm1 = 0) against the same product in FP64 on the host.
+static int tc_project_calibrate(int dev, int sm_count) {
+    const int M = 128, B = 128, K = 4096, pitch = tc_pitch(K);
+    std::vector<float> U((size_t)M * K), F((size_t)B * K);
+    unsigned st = 88172645u;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 17; st ^= st << 5; return (float)((double)(st >> 8) / 8388608.0 - 1.0); };
+    for (auto& v : U) v = rnd() + rnd() + rnd();
+    for (auto& v : F) v = rnd() + rnd() + rnd();
+    float *dU, *dF, *dUh, *dUl, *dFh, *dFl, *dY;
+    PBSO_CUDA(cudaMalloc(&dU, U.size() * 4)); PBSO_CUDA(cudaMalloc(&dF, F.size() * 4));
+    PBSO_CUDA(cudaMalloc(&dUh, (size_t)M * pitch * 4)); PBSO_CUDA(cudaMalloc(&dUl, (size_t)M * pitch * 4));
+    PBSO_CUDA(cudaMalloc(&dFh, (size_t)B * pitch * 4)); PBSO_CUDA(cudaMalloc(&dFl, (size_t)B * pitch * 4));
+    PBSO_CUDA(cudaMalloc(&dY, (size_t)B * M * 4));
+    PBSO_CUDA(cudaMemcpy(dU, U.data(), U.size() * 4, cudaMemcpyHostToDevice));
+    PBSO_CUDA(cudaMemcpy(dF, F.data(), F.size() * 4, cudaMemcpyHostToDevice));
+    g_proj_calibrating = true;
+    int rc = tc_split_f32(dU, M, K, dUh, dUl, 0);
+    if (!rc) rc = tc_split_f32(dF, B, K, dFh, dFl, 0);
+    // one CTA, one K split: 16 full chains (the launch heuristics would split K; call the kernel's geometry directly)
+    if (!rc) rc = tc_project(dUh, dUl, M, dFh, dFl, B, K, dY, 1, 0);
+    g_proj_calibrating = false;
+    std::vector<float> Y((size_t)B * M);
+    if (!rc && cudaMemcpy(Y.data(), dY, Y.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_error(PBSO_ERR_CUDA, "calibration copy failed");
+    cudaFree(dU); cudaFree(dF); cudaFree(dUh); cudaFree(dUl); cudaFree(dFh); cudaFree(dFl); cudaFree(dY);
+    if (rc) return rc;
+    double num = 0.0, den = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int m = 0; m < M; ++m) {
+            double acc = 0.0;
+            const float* u = &U[(size_t)m * K]; const float* f = &F[(size_t)b * K];
+            for (int k = 0; k < K; ++k) acc += (double)u[k] * (double)f[k];
+            num += (double)Y[(size_t)b * M + m] * acc; den += acc * acc;
+        }
+    const double gain = den > 0.0 ? num / den : 1.0;
+    if (!(gain > 0.9999 && gain < 1.0001)) return set_error(PBSO_ERR_CUDA, "projection gain calibration out of range: %.9f", gain);
+    g_proj_gm1[dev & 63] = (float)(gain - 1.0); g_proj_cal[dev & 63] = true;
+    return PBSO_OK;
+}
+double tc_project_gain(int dev) { return g_proj_cal[dev & 63] ? 1.0 + (double)g_proj_gm1[dev & 63] : 0.0; }
 
 }  // namespace pbso

@@ -369,10 +369,11 @@ def test_modes_file_roundtrip(pbso, orc, tmp_path):
     assert e.value.code == 3
 
 
-@pytest.mark.parametrize("M,K,B", [(128, 64, 128), (128, 256, 16), (96, 1500, 9), (300, 4100, 200), (2048, 6000, 580)])
+@pytest.mark.parametrize("M,K,B", [(128, 64, 128), (128, 256, 16), (96, 1500, 9), (300, 4100, 200), (2048, 6000, 580), (2048, 60000, 580)])
 def test_projection_tensor_core_3xtf32(pbso, M, K, B):
     """K5: tcgen05 3xTF32 batched projection; column rel-L2 <= 1e-5 against float64 numpy.
-    Ragged M, K (not multiples of the 128 x 32 tiles), B below and above one N tile, split-K."""
+    Ragged M, K (not multiples of the 128 x 32 tiles), B below and above one N tile, split-K; the last case is cfg3 itself:
+    2048 modes x 20 000 vertices (K = 60 000), 580 impulses = one 256-sample buffer of the 100 k impulses/s contact storm."""
     rng = np.random.default_rng(M + K + B)
     U = rng.standard_normal((M, K)); F = rng.standard_normal((B, K))
     md = pbso.ModeShapes(U)
@@ -383,6 +384,39 @@ def test_projection_tensor_core_3xtf32(pbso, M, K, B):
     assert err.max() <= 1e-5
     Y2 = md.project_dense(F[:, :], forceDim=M - 5, precision=pbso.PREC_TF32X3)      # forceDim < M (culled modes)
     assert np.allclose(Y2, Y[:, :M - 5], rtol=0, atol=1e-4 * np.abs(Yr).max())
+
+
+def test_contact_storm_pipeline_vs_oracle(pbso, orc):
+    """cfg3 on the device: B vertex impulses per buffer -> projection (sparse FP64 gather, or dense load vectors through
+    the tensor-core GEMM) -> summed modal load -> integrator, against the oracle's GetModalForceVertex + ModalSolver::step
+    fed with the summed load; state carries over the buffers, the impulse count changes per buffer."""
+    M, V, T = 96, 300, 256
+    f = synth.mode_frequencies(M, 1003); a, b = synth.ab_from_material(f, synth.MATERIALS["low_damping"])
+    U = synth.mode_shapes(M, 3 * V, 1003)
+    md = pbso.ModeShapes(U)
+    rng = np.random.default_rng(1003)
+    tr = np.abs(rng.standard_normal(M)) + 0.1
+    outs = {}
+    for prec in (pbso.PREC_F64, pbso.PREC_TF32X3):
+        it = pbso.ModalIntegrator(M, H, a, b); it.set_transfer(tr)
+        ref = orc.Solver(orc.Integrator(H, a, b), T); ref.enqueue_trans(tr)
+        rs = np.random.default_rng(7)
+        ys, yr = [], []
+        for bi, B in enumerate((37, 1, 130, 580, 5)):
+            vids = rs.integers(0, V, B); vn = synth.unit_vectors(B, 100 + bi)
+            y, qn = md.storm_buffer(it, vids, vn, T, prec, want_qnorm=True)
+            space = sum(orc.project_vertex(U, int(v), n) for v, n in zip(vids, vn))
+            ref.enqueue_force(space)
+            r = ref.step()
+            ys.append(y[0]); yr.append(r[0])
+            assert np.allclose(qn, r[1], rtol=1e-9 if prec == pbso.PREC_F64 else 2e-5)
+        ys = np.concatenate(ys); yr = np.concatenate(yr)
+        if prec == pbso.PREC_F64: assert_waveform_parity(ys, yr, rel=1e-9, mx=1e-9)
+        else: outs["rel"], outs["mx"] = assert_waveform_parity(ys, yr)
+        it.close()
+    print("contact storm, tensor-core projection: rel-L2 %.2e max-abs %.2e" % (outs["rel"], outs["mx"]))
+    with pytest.raises(pbso.PbsoError):
+        md.storm_buffer(pbso.ModalIntegrator(M, H, a, b), [V], [[1.0, 0.0, 0.0]], T)        # vertex id out of range
 
 
 # --------------------------------------------------------------------------- batch renderer
