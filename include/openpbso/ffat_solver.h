@@ -111,6 +111,21 @@ public:
         pbso_mirror::check(pbso_ffat_eval(one, 1, pos, 1, getCompressed ? 1 : 0, &out), "FFAT_Map::GetMapVal");
         return (T)out;
     }
+    // 8-bit quantisation of the map, face by face (reference :1125-1178): _compressed_Psi = round(Psi 255/maxAmp) maxAmp/255.
+    // and _is_compressed = true; returns maxAmp over all faces.  The reference writes every face as a JPEG file of the given
+    // quality and reads it back in between (OpenCV); this build has no image codec, so output_template / quality are unused
+    // and the bytes are kept as quantised -- a caller with a codec runs it between pbso_ffat_quantise and
+    // pbso_ffat_set_compressed_u8 (include/pbso_b200.h).  The device then reads ONE byte per texel for
+    // GetMapVal(p, true) / computeTransfer.
+    T Compress(const char* output_template = "tmp-%u-%u-amp.jpg", const int quality = 65) {
+        (void)output_template; (void)quality;
+        assert(_set && "FFAT map is empty");
+        double g = 0;
+        pbso_mirror::check(pbso_ffat_compress(_set.get(), modeId, &g), "FFAT_Map::Compress");
+        _is_compressed = true;
+        _single.reset();
+        return (T)g;
+    }
     int modeId = 0;
 
 private:
@@ -131,8 +146,12 @@ private:
             pbso_mirror::check(pbso_ffat_get_map(_set.get(), modeId, nullptr, nullptr, nullptr, nullptr, nullptr, psi.data()), "FFAT_Map");
             const int id0 = 0; const unsigned char c = (unsigned char)comp;
             pbso_ffat* h = nullptr;
-            pbso_mirror::check(pbso_ffat_create(1, &id0, geom, igeom, psi.data(), n, &c, &h), "FFAT_Map");
+            std::vector<unsigned char> q8((size_t)n); double amp[6];
+            const bool bytes = comp && pbso_ffat_get_compressed(_set.get(), modeId, q8.data(), amp, nullptr) == PBSO_OK;   // compressed in memory
+            const unsigned char c1 = bytes ? 0 : c;
+            pbso_mirror::check(pbso_ffat_create(1, &id0, geom, igeom, psi.data(), n, &c1, &h), "FFAT_Map");
             _single = std::shared_ptr<pbso_ffat>(h, [](pbso_ffat* p) { pbso_ffat_destroy(p); });
+            if (bytes) pbso_mirror::check(pbso_ffat_set_compressed_u8(h, 0, q8.data(), n, amp), "FFAT_Map");
         }
         return _single.get();
     }

@@ -132,11 +132,35 @@ int pbso_ffat_save_file(const pbso_ffat* f, int mode_id, const char* filename);
  * pos is L x 3.  A missing mode id in [0, n_modes) returns PBSO_ERR_RANGE (.at() throws). */
 int pbso_ffat_eval(const pbso_ffat* f, int n_modes, const double* pos, int L, int use_compressed,
                    double* out);
+/* FFAT_Map<T,3>::Compress (ffat_solver.h:1125-1178), split where the reference goes through a JPEG file on disk:
+ *   pbso_ffat_quantise        :1128-1147  per face A *= 255/maxAmp, cv::Mat::convertTo(CV_8U) (cvRound = round half to
+ *                             even, saturated to [0,255]) -> q8[psi_len], max_amp6[6]; returns maxAmp_global (:1132-1136).
+ *   (the reference's cv::imwrite/cv::imread JPEG round trip of every face image, :1149-1158, belongs between the two
+ *    calls; this library has no image codec -- a caller who wants the lossy step runs it on q8 there)
+ *   pbso_ffat_set_compressed_u8 :1159-1173 _compressed_Psi = q8 * (maxAmp/255.) per face, _is_compressed = true.  _Psi
+ *                             stays, so both views of GetMapVal(p, getCompressed) are there afterwards.
+ *   pbso_ffat_compress        both halves back to back for one map or (mode_id -1) all; max_amp_global gets one
+ *                             value per compressed map in mode-id order (may be NULL).
+ * The device keeps the compressed view as ONE BYTE per texel + maxAmp/255 per (map, face) and evaluates
+ * w * ((double)q * scale): bit for bit what reading the reference's stored doubles gives, at an eighth of the bytes.
+ * A map LOADED compressed (ffat_map_serialize.h:238-252) has only its doubles; it cannot be compressed again. */
+int pbso_ffat_quantise(const pbso_ffat* f, int mode_id, unsigned char* q8, double* max_amp6,
+                       double* max_amp_global);
+int pbso_ffat_set_compressed_u8(pbso_ffat* f, int mode_id, const unsigned char* q8, int len,
+                                const double* max_amp6);
+int pbso_ffat_compress(pbso_ffat* f, int mode_id, double* max_amp_global);
+/* q8[psi_len], maxAmp per face and/or the doubles of _compressed_Psi (any may be NULL); q8 and max_amp6 are what
+ * pbso_ffat_set_compressed_u8 takes, so a map's compressed view can be carried into another set. */
+int pbso_ffat_get_compressed(const pbso_ffat* f, int mode_id, unsigned char* q8, double* max_amp6,
+                             double* compressed_psi);
 /* Device-resident variant, enqueue only (cuda_stream NULL = the handle's own stream).  A handle keeps per-call scratch
  * (listener stencils, per-tile bins and their ping-pong counters), so calls on one handle must come from one thread and
  * must not overlap on different streams; successive calls on one stream are ordered by the stream. */
 int pbso_ffat_eval_device(const pbso_ffat* f, int n_modes, const double* d_pos, int L,
                           double* d_out, void* cuda_stream);
+/* Same with GetMapVal's getCompressed switch (pbso_ffat_eval_device reads the uncompressed view). */
+int pbso_ffat_eval_device_view(const pbso_ffat* f, int n_modes, const double* d_pos, int L,
+                               int use_compressed, double* d_out, void* cuda_stream);
 
 /* ---- FFAT map construction: ffat_solver.h:944-1069 ------------------
  * The step before the synthesis path: fit the run-time map Psi from the Dirichlet pressure an acoustic solver

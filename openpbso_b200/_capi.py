@@ -76,6 +76,11 @@ def lib():
             "pbso_ffat_save_file": [vp, C.c_int, C.c_char_p],
             "pbso_ffat_eval": [vp, C.c_int, c_dp, C.c_int, C.c_int, c_dp],
             "pbso_ffat_eval_device": [vp, C.c_int, vp, C.c_int, vp, vp],
+            "pbso_ffat_eval_device_view": [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp],
+            "pbso_ffat_quantise": [vp, C.c_int, C.POINTER(C.c_ubyte), c_dp, c_dp],
+            "pbso_ffat_set_compressed_u8": [vp, C.c_int, C.POINTER(C.c_ubyte), C.c_int, c_dp],
+            "pbso_ffat_compress": [vp, C.c_int, c_dp],
+            "pbso_ffat_get_compressed": [vp, C.c_int, C.POINTER(C.c_ubyte), c_dp, c_dp],
             "pbso_ffat_fitter_create": [C.c_double, c_dp, C.c_int, c_ip, C.c_int, c_vpp],
             "pbso_ffat_fitter_destroy": [vp],
             "pbso_ffat_fitter_info": [vp, c_ip, c_ip, c_ip, c_ip],

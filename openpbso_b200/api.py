@@ -236,6 +236,38 @@ class FFATMaps:
     def Save(self, mode_id, filename):
         check(lib().pbso_ffat_save_file(self._h, mode_id, filename.encode()))
 
+    def quantise(self, mode_id):
+        """First half of FFAT_Map<T,3>::Compress (ffat_solver.h:1125-1147): per face, Psi * (255/maxAmp) saturated to 8 bits
+        the way cv::Mat::convertTo(CV_8U) does -> (q8 [psi_len] uint8, maxAmp[6], maxAmp_global)."""
+        n = C.c_int()
+        check(lib().pbso_ffat_get_map(self._h, mode_id, None, None, C.byref(n), None, None, None))
+        q = np.empty(n.value, dtype=np.uint8); amp = np.empty(6); g = C.c_double()
+        check(lib().pbso_ffat_quantise(self._h, mode_id, q.ctypes.data_as(C.POINTER(C.c_ubyte)), dp(amp), C.byref(g)))
+        return q, amp, g.value
+
+    def set_compressed_u8(self, mode_id, q8, max_amp):
+        """Second half of Compress (ffat_solver.h:1159-1173): _compressed_Psi = q8 * (maxAmp/255.) per face, _is_compressed =
+        true.  q8 is what came back from the image round trip (or quantise()'s own bytes when there is none)."""
+        q8 = np.ascontiguousarray(q8, dtype=np.uint8); amp = f64(max_amp)
+        check(lib().pbso_ffat_set_compressed_u8(self._h, mode_id, q8.ctypes.data_as(C.POINTER(C.c_ubyte)), len(q8), dp(amp)))
+
+    def Compress(self, mode_id=None):
+        """FFAT_Map<T,3>::Compress for one map (returns maxAmp_global) or, mode_id None, every map (returns the array): the
+        8-bit quantisation without the JPEG file round trip (quantise() / set_compressed_u8() are the two halves for a caller
+        who wants an image codec in between)."""
+        n = 1 if mode_id is not None else self.size()
+        g = np.empty(n)
+        check(lib().pbso_ffat_compress(self._h, -1 if mode_id is None else mode_id, dp(g)))
+        return g[0] if mode_id is not None else g
+
+    def get_compressed(self, mode_id):
+        """-> (q8, maxAmp[6], _compressed_Psi as the doubles the reference would hold)."""
+        n = C.c_int()
+        check(lib().pbso_ffat_get_map(self._h, mode_id, None, None, C.byref(n), None, None, None))
+        q = np.empty(n.value, dtype=np.uint8); sc = np.empty(6); c = np.empty(n.value)
+        check(lib().pbso_ffat_get_compressed(self._h, mode_id, q.ctypes.data_as(C.POINTER(C.c_ubyte)), dp(sc), dp(c)))
+        return q, sc, c
+
     def computeTransfer(self, pos, n_modes=None, use_compressed=False):
         """modal_solver.h:286-315 for L listeners: returns [L][n_modes]."""
         pos = f64(pos).reshape(-1, 3); L = len(pos)

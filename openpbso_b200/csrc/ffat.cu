@@ -39,6 +39,23 @@ struct HostMap {
     bool is_compressed = false;
     std::vector<std::vector<double>> psi;     // columns
     int modeid = 0;
+    // FFAT_Map<T,3>::Compress done in memory (ffat_solver.h:1125-1178): _Psi stays, _compressed_Psi is added.  The
+    // compressed view is kept as what the reference derives it from -- one byte per texel and maxAmp/255 per face
+    // (cpsi[i] == (double)q8[i] * q8_scale[face], bit for bit) -- and the byte table is what the device reads.
+    std::vector<uint8_t> q8;
+    double q8_scale[6] = {0, 0, 0, 0, 0, 0}, q8_amp[6] = {0, 0, 0, 0, 0, 0};   // maxAmp/255. and maxAmp per face
+    bool has_plain() const { return !is_compressed || !q8.empty(); }
+    std::vector<double> compressed_column() const {
+        if (q8.empty()) return psi[0];
+        std::vector<double> c(q8.size(), 0.0);
+        size_t off = 0;
+        for (int fc = 0; fc < 6; ++fc) {
+            const size_t n = (size_t)igeom[2 * fc] * igeom[2 * fc + 1];
+            for (size_t i = 0; i < n && off + i < c.size(); ++i) c[off + i] = (double)q8[off + i] * q8_scale[fc];   // data_s -> CV_64F, *= maxAmp/255.
+            off += n;
+        }
+        return c;
+    }
 };
 }  // namespace
 
@@ -53,6 +70,13 @@ struct pbso_ffat {
     double* d_geom = nullptr; int* d_igeom = nullptr;
     double* d_psi_mm = nullptr; double* d_psi_tm = nullptr;
     size_t* d_psi_off = nullptr;               // per-map offset into d_psi_mm
+    // 8-bit view (present when every map of [0, n_dense) went through Compress in memory): one byte per texel in the
+    // same two layouts + maxAmp/255 per (map, face)
+    uint8_t* d_q8_mm = nullptr; uint8_t* d_q8_tm = nullptr; double* d_q8_scale = nullptr;   // scale: [6][n]
+    double* d_q8_sk = nullptr;                 // [6][q8_stride]: (maxAmp/255) / k per (face, map), for k_ffat_gather_q8x4
+    int q8_stride = 0;                         // maps per row of d_q8_tm / d_q8_scale / d_q8_sk: n_dense rounded up to 4
+    bool q8_ready = false;
+    int q8x4_ctas = 0;                         // resident CTAs per SM of k_ffat_gather_q8x4 (occupancy query, once)
     cudaStream_t stream = nullptr;
     double* d_pos = nullptr; double* d_out = nullptr; size_t pos_cap = 0, out_cap = 0;
     void* d_loc = nullptr; size_t loc_cap = 0;          // per-listener stencils (shared-geometry path)
@@ -66,22 +90,38 @@ struct pbso_ffat {
     int sm_count = 148;           // leading maps with is_compressed == false / true
 };
 
+// One texel of a map: a stored double, or (8-bit view) the byte Compress kept times the face's maxAmp/255 -- rounded on
+// its own (__dmul_rn), so that the value is the double the reference would have stored in _compressed_Psi.
+__device__ __forceinline__ double psi_val(const double* t, size_t i, double) { return t[i]; }
+__device__ __forceinline__ double psi_val(const uint8_t* t, size_t i, double scale) { return __dmul_rn((double)t[i], scale); }
+// the six face scales of one map ride in registers; the face is uniform over a warp (one listener at a time)
+struct FaceScale {
+    double s0, s1, s2, s3, s4, s5;
+    // table is face-major, [6][n]: a warp's 32 modes read 32 consecutive doubles per face
+    __device__ __forceinline__ void load(const double* p, int n) { s0 = p[0]; s1 = p[n]; s2 = p[2 * n]; s3 = p[3 * n]; s4 = p[4 * n]; s5 = p[5 * n]; }
+    __device__ __forceinline__ double at(int f) const { return f == 0 ? s0 : f == 1 ? s1 : f == 2 ? s2 : f == 3 ? s3 : f == 4 ? s4 : s5; }
+};
+
 // General path: one thread per (mode, listener); per-map geometry.
+template <typename PT>
 __global__ void __launch_bounds__(128)
 k_ffat_eval_general(int n_modes, int L, const double* __restrict__ geom, const int* __restrict__ igeom,
-                    const double* __restrict__ psi, const size_t* __restrict__ psi_off,
+                    const PT* __restrict__ psi, const size_t* __restrict__ psi_off, const double* __restrict__ q8_scale, int n_scale,
                     const double* __restrict__ pos, double* __restrict__ out) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_modes) return;
     Geo g; load_geo(g, geom + (size_t)m * 32, igeom + (size_t)m * 18);
-    const double* P = psi + psi_off[m];
+    const PT* P = psi + psi_off[m];
+    FaceScale fs = {};
+    if (sizeof(PT) == 1) fs.load(q8_scale + m, n_scale);
     for (int l = blockIdx.y; l < L; l += gridDim.y) {                       // gridDim.y is capped at 65535
         const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
-        int idx[4]; double w[4], r;
-        ffat_locate(g, p, idx, w, r);
+        int idx[4], fxy[5]; double w[4], r;
+        ffat_locate(g, p, idx, w, r, fxy);
+        const double sc = sizeof(PT) == 1 ? fs.at(fxy[0]) : 0.0;
         double psi0 = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) psi0 += w[kk] * P[idx[kk]];          // :1198-1204
+        for (int kk = 0; kk < 4; ++kk) psi0 += w[kk] * psi_val(P, idx[kk], sc);   // :1198-1204
         out[(size_t)l * n_modes + m] = fabs(psi0 / (g.k * r));              // :904-905 + :295 std::abs
     }
 }
@@ -94,7 +134,8 @@ k_ffat_eval_general(int n_modes, int L, const double* __restrict__ geom, const i
 //                 row, fully coalesced -- and writes out[l][m] coalesced.  k differs per mode (geom[m][31]).
 constexpr int FL_THREADS = 64;          // listeners per CTA of k_ffat_locate (latency-bound; 32 measured the same)
 struct __align__(16) FfatLoc { int idx[4]; double w[4]; double r; int tile; int lxy; };   // 64 B: int4 + 3 x double2 loads
-// lxy: position of the stencil's low corner inside its texel tile and the clamp flags: lx | ly << 4 | (xp - x) << 8 | (yp - y) << 9
+// lxy: position of the stencil's low corner inside its texel tile and the clamp flags: lx | ly << 4 | (xp - x) << 8 | (yp - y) << 9,
+// and the cube face the stencil lies on in bits 12-14 (the 8-bit view scales per face)
 constexpr int FT_T = 8;                 // texel tile edge
 struct TileTable { int tiles_y[6]; int tile_base[7]; };
 // What k_ffat_tiles needs of one listener, stored in its tile's bin: bilinear weights, 1/r, listener id, lxy.
@@ -103,7 +144,7 @@ struct __align__(16) TileRec { double w[4]; double inv_r; int l; int lxy; };   /
 __global__ void __launch_bounds__(FL_THREADS)
 k_ffat_locate(int L, const __grid_constant__ Geo g,        // the shared geometry rides in the parameter bank: no global round trip
               const double* __restrict__ pos, FfatLoc* __restrict__ loc, TileTable tt, TileRec* __restrict__ tile_rec,
-              int* __restrict__ cnt_cur, int* __restrict__ cnt_next) {
+              int* __restrict__ cnt_cur, int* __restrict__ cnt_next, bool inv_r) {
     // programmatic dependent launch: let k_ffat_tiles start staging its texel tiles now; it waits (griddepcontrol.wait)
     // for this grid to finish before it reads the bins
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -114,34 +155,109 @@ k_ffat_locate(int L, const __grid_constant__ Geo g,        // the shared geometr
     FfatLoc o; int fxy[5];
     ffat_locate(g, p, o.idx, o.w, o.r, fxy);
     o.tile = tt.tile_base[fxy[0]] + (fxy[1] / FT_T) * tt.tiles_y[fxy[0]] + fxy[2] / FT_T;
-    o.lxy = (fxy[1] % FT_T) | (fxy[2] % FT_T) << 4 | fxy[3] << 8 | fxy[4] << 9;
+    o.lxy = (fxy[1] % FT_T) | (fxy[2] % FT_T) << 4 | fxy[3] << 8 | fxy[4] << 9 | fxy[0] << 12;
     if (tile_rec) {                                                      // bin by tile; order within a bin is irrelevant
         TileRec t; t.w[0] = o.w[0]; t.w[1] = o.w[1]; t.w[2] = o.w[2]; t.w[3] = o.w[3]; t.inv_r = 1.0 / o.r; t.l = l; t.lxy = o.lxy;
         tile_rec[(size_t)o.tile * L + atomicAdd(&cnt_cur[o.tile], 1)] = t;
     } else {
+        if (inv_r) o.r = 1.0 / o.r;                                      // k_ffat_gather_q8x4 multiplies
         loc[l] = o;
     }
 }
 
 constexpr int FG_LPB = 8;
+constexpr int FG_LPB_Q8 = 16;           // byte view: the six face scales a thread preloads are amortised over more listeners
+template <typename PT, int LPB>
 __global__ void __launch_bounds__(256)
-k_ffat_gather(int n_modes, int L, const double* __restrict__ geom, const double* __restrict__ psi_tm, int n_stride,
-              const FfatLoc* __restrict__ loc, double* __restrict__ out) {
-    __shared__ FfatLoc s_loc[FG_LPB];
-    const int l0 = blockIdx.y * FG_LPB;
-    if (threadIdx.x < FG_LPB && l0 + threadIdx.x < L) s_loc[threadIdx.x] = loc[l0 + threadIdx.x];
+k_ffat_gather(int n_modes, int L, const double* __restrict__ geom, const PT* __restrict__ psi_tm, int n_stride,
+              const double* __restrict__ q8_scale, const FfatLoc* __restrict__ loc, double* __restrict__ out) {
+    __shared__ FfatLoc s_loc[LPB];
+    const int l0 = blockIdx.y * LPB;
+    if (threadIdx.x < LPB && l0 + threadIdx.x < L) s_loc[threadIdx.x] = loc[l0 + threadIdx.x];
     __syncthreads();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_modes) return;
     const double k = geom[(size_t)m * 32 + 31];
+    FaceScale fs = {};
+    if (sizeof(PT) == 1) fs.load(q8_scale + m, n_stride);
 #pragma unroll
-    for (int i = 0; i < FG_LPB; ++i) {
+    for (int i = 0; i < LPB; ++i) {
         if (l0 + i >= L) break;
         const FfatLoc& q = s_loc[i];
+        const double sc = sizeof(PT) == 1 ? fs.at((q.lxy >> 12) & 7) : 0.0;
         double psi0 = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * psi_tm[(size_t)q.idx[kk] * n_stride + m];    // ffat_solver.h:1198-1204
+        for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * psi_val(psi_tm, (size_t)q.idx[kk] * n_stride + m, sc);    // ffat_solver.h:1198-1204
         out[(size_t)(l0 + i) * n_modes + m] = fabs(psi0 / (k * q.r));                                  // :904-905
+    }
+}
+
+// Byte view, many listeners: FOUR maps per thread.  With the table at one byte per texel the per-listener gather is no longer
+// bound by L2 bytes (6 MB table, L2-resident) but by instructions issued (ncu, profiles/r2_ffat_u8.md: 86 per warp and
+// listener in the one-map-per-thread kernel, a third of them the FP64 division), so here a thread loads its four maps' texels
+// of one tap as ONE 32-bit word, turns bytes into doubles with a DADD (2^52 + q, minus 2^52 -- exact, and on the FP64 pipe
+// instead of the quarter-rate conversion unit), and scales by (maxAmp/255)/k and 1/r -- both rounded once, on the host and
+// by the staging thread -- instead of dividing: out = |sum_k w_k q_k| * (s/k) * (1/r), within 2 ulp of the division form.
+// Stores are two 16-byte runs per thread, 1 KB contiguous per warp.  Starts under k_ffat_locate (programmatic dependent
+// launch) and waits for its stencils.
+__device__ __forceinline__ double u8_to_f64(unsigned word, int j) {     // byte j of word (one PRMT) -> double
+    return __hiloint2double(0x43300000, (int)__byte_perm(word, 0u, 0x4440u + j)) - 4503599627370496.0;
+}
+__device__ __forceinline__ double abs_bits(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
+template <int U, bool SPLIT>
+__global__ void __launch_bounds__(256)
+k_ffat_gather_q8x4(int n_modes, int L, const uint8_t* __restrict__ q8_tm, int n_stride, const double* __restrict__ sk,
+                   const FfatLoc* __restrict__ loc, double* __restrict__ out) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // SPLIT (n_modes a multiple of 128): a lane owns maps {2 i, 2 i + 1} and {64 + 2 i, 65 + 2 i} of its warp's 128, so
+    // that each 16-byte store instruction of the warp covers 512 contiguous bytes (whole 32-byte sectors); otherwise four
+    // consecutive maps (each store instruction writes half of every sector it touches)
+    const int m4 = SPLIT ? (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * 4 + 2 * (threadIdx.x & 31) : (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    constexpr int HI = SPLIT ? 64 : 2;     // second pair of maps, relative to the first
+    if (m4 >= n_modes) return;
+    const uint8_t* tab = q8_tm + m4;
+    const double* skm = sk + m4;
+    auto tap = [&](int texel) -> unsigned {
+        const uint8_t* p = tab + (size_t)texel * n_stride;
+        if (SPLIT) return (unsigned)__ldg(reinterpret_cast<const unsigned short*>(p)) | (unsigned)__ldg(reinterpret_cast<const unsigned short*>(p + 64)) << 16;
+        return __ldg(reinterpret_cast<const unsigned*>(p));
+    };
+    // listeners are dealt round-robin to the rows of the grid (a fixed grid of a few CTAs per SM: every SM gets the same
+    // share, whatever L is); a listener's 64-byte stencil is read by all threads of the block from the same address
+    // (one broadcast transaction per warp and 16 bytes) -- no staging, no barrier, iterations independent
+    // U listeners in flight per thread: all loads of a group are issued before any arithmetic
+    for (int l0 = blockIdx.y; l0 < L; l0 += U * gridDim.y) {
+        int4 idx[U]; double2 w01[U], w23[U], rt[U]; unsigned t[U][4]; double2 sk01[U], sk23[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const FfatLoc* q = loc + min(l0 + u * (int)gridDim.y, L - 1);                  // past the end: re-read the last one, store nothing
+            idx[u] = __ldg(reinterpret_cast<const int4*>(q));
+            w01[u] = __ldg(reinterpret_cast<const double2*>(q) + 1); w23[u] = __ldg(reinterpret_cast<const double2*>(q) + 2);
+            rt[u] = __ldg(reinterpret_cast<const double2*>(q) + 3);                        // 1/r (k_ffat_locate, inv_r = true) | tile, lxy
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            t[u][0] = tap(idx[u].x); t[u][1] = tap(idx[u].y); t[u][2] = tap(idx[u].z); t[u][3] = tap(idx[u].w);
+            const double* skp = skm + (size_t)((__double2hiint(rt[u].y) >> 12) & 7) * n_stride;
+            sk01[u] = __ldg(reinterpret_cast<const double2*>(skp)); sk23[u] = __ldg(reinterpret_cast<const double2*>(skp + HI));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int l = l0 + u * (int)gridDim.y;
+            double a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                                                             // ffat_solver.h:1198-1204
+                a[j] = w01[u].x * u8_to_f64(t[u][0], j);
+                a[j] += w01[u].y * u8_to_f64(t[u][1], j);
+                a[j] += w23[u].x * u8_to_f64(t[u][2], j);
+                a[j] += w23[u].y * u8_to_f64(t[u][3], j);
+            }
+            if (l < L) {
+                double* o = out + (size_t)l * n_modes + m4;
+                *reinterpret_cast<double2*>(o) = make_double2(abs_bits(a[0] * sk01[u].x * rt[u].x), abs_bits(a[1] * sk01[u].y * rt[u].x));      // :904-905, :295
+                *reinterpret_cast<double2*>(o + HI) = make_double2(abs_bits(a[2] * sk23[u].x * rt[u].x), abs_bits(a[3] * sk23[u].y * rt[u].x));
+            }
+        }
     }
 }
 
@@ -150,30 +266,35 @@ k_ffat_gather(int n_modes, int L, const double* __restrict__ geom, const double*
 // a k_ffat_locate launch: a few microseconds of redundant FP64 per block buy back a dependent kernel launch, which is what
 // a 2.6 MB problem costs most.
 constexpr int FG_FUSED_MAX = 256;
+template <typename PT>
 __global__ void __launch_bounds__(256)
 k_ffat_gather_fused(int n_modes, int L, const __grid_constant__ Geo g, const double* __restrict__ geom,
-                    const double* __restrict__ psi_tm, int n_stride, const double* __restrict__ pos, double* __restrict__ out) {
+                    const PT* __restrict__ psi_tm, int n_stride, const double* __restrict__ q8_scale,
+                    const double* __restrict__ pos, double* __restrict__ out) {
     __shared__ FfatLoc s_loc[FG_LPB];
     const int l0 = blockIdx.y * FG_LPB;
     if (threadIdx.x < FG_LPB && l0 + threadIdx.x < L) {
         const int l = l0 + threadIdx.x;
         const double p[3] = {pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]};
-        FfatLoc o;
-        ffat_locate(g, p, o.idx, o.w, o.r);
-        o.tile = 0; o.lxy = 0;
+        FfatLoc o; int fxy[5];
+        ffat_locate(g, p, o.idx, o.w, o.r, fxy);
+        o.tile = 0; o.lxy = fxy[0] << 12;
         s_loc[threadIdx.x] = o;
     }
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     const double k = m < n_modes ? geom[(size_t)m * 32 + 31] : 1.0;      // in flight while the stencils are solved
+    FaceScale fs = {};
+    if (sizeof(PT) == 1 && m < n_modes) fs.load(q8_scale + m, n_stride);
     __syncthreads();
     if (m >= n_modes) return;
 #pragma unroll
     for (int i = 0; i < FG_LPB; ++i) {
         if (l0 + i >= L) break;
         const FfatLoc& q = s_loc[i];
+        const double sc = sizeof(PT) == 1 ? fs.at((q.lxy >> 12) & 7) : 0.0;
         double psi0 = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * psi_tm[(size_t)q.idx[kk] * n_stride + m];    // ffat_solver.h:1198-1204
+        for (int kk = 0; kk < 4; ++kk) psi0 += q.w[kk] * psi_val(psi_tm, (size_t)q.idx[kk] * n_stride + m, sc);    // ffat_solver.h:1198-1204
         out[(size_t)(l0 + i) * n_modes + m] = fabs(psi0 / (k * q.r));                                  // :904-905
     }
 }
@@ -471,6 +592,7 @@ static void from_host_map(const HostMap& hm, FatcubeMap& fm) {
     fm.k = hm.geom[31];
     fm.is_compressed = hm.is_compressed;
     fm.psi = hm.psi;
+    if (hm.is_compressed && !hm.q8.empty()) fm.psi.assign(1, hm.compressed_column());   // Save writes _compressed_Psi (ffat_map_serialize.h:149-153)
     fm.modeid = hm.modeid;
 }
 
@@ -488,6 +610,8 @@ static int load_one(const char* filename, HostMap& hm) {
 
 static void free_device(pbso_ffat* f) {
     cudaFree(f->d_geom); cudaFree(f->d_igeom); cudaFree(f->d_psi_mm); cudaFree(f->d_psi_tm); cudaFree(f->d_psi_off); cudaFree(f->d_psi_tiles); cudaFree(f->d_tile_order);
+    cudaFree(f->d_q8_mm); cudaFree(f->d_q8_tm); cudaFree(f->d_q8_scale); cudaFree(f->d_q8_sk);
+    f->d_q8_mm = f->d_q8_tm = nullptr; f->d_q8_scale = f->d_q8_sk = nullptr; f->q8_ready = false;
     cudaFree(f->d_tile_rec); cudaFree(f->d_tile_cnt); f->d_tile_rec = nullptr; f->tile_rec_cap = 0; f->d_tile_cnt = nullptr;   // sized by the tile count
     f->d_psi_tiles = nullptr; f->d_tile_order = nullptr; f->d_geom = nullptr; f->d_igeom = nullptr; f->d_psi_mm = nullptr; f->d_psi_tm = nullptr; f->d_psi_off = nullptr;
 }
@@ -548,13 +672,43 @@ static int ensure_device(pbso_ffat* f) {
         }
         f->tile_base[6] = tb;
     }
-    f->n_uncompressed = 0; while (f->n_uncompressed < n && !f->maps.at(f->n_uncompressed).is_compressed) ++f->n_uncompressed;
-    f->n_compressed = 0; while (f->n_compressed < n && f->maps.at(f->n_compressed).is_compressed) ++f->n_compressed;
+    // 8-bit view: every map went through Compress in memory -> byte tables in the same two layouts + maxAmp/255 per face
+    bool all_q8 = true;
+    for (int m = 0; m < n; ++m) all_q8 = all_q8 && f->maps.at(m).q8.size() == f->maps.at(m).psi[0].size();
+    if (all_q8) {
+        const int ns = (n + 3) / 4 * 4; f->q8_stride = ns;
+        std::vector<uint8_t> q(total); std::vector<double> sc((size_t)ns * 6, 0.0), sk((size_t)ns * 6, 0.0);
+        for (int m = 0; m < n; ++m) {
+            const HostMap& hm = f->maps.at(m);
+            std::memcpy(&q[off[m]], hm.q8.data(), hm.q8.size());
+            for (int fc = 0; fc < 6; ++fc) { sc[(size_t)fc * ns + m] = hm.q8_scale[fc]; sk[(size_t)fc * ns + m] = hm.q8_scale[fc] / hm.geom[31]; }
+        }
+        PBSO_CUDA(cudaMalloc(&f->d_q8_mm, std::max<size_t>(total, 1)));
+        PBSO_CUDA(cudaMemcpy(f->d_q8_mm, q.data(), total, cudaMemcpyHostToDevice));
+        PBSO_CUDA(cudaMalloc(&f->d_q8_scale, sc.size() * sizeof(double)));
+        PBSO_CUDA(cudaMemcpy(f->d_q8_scale, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice));
+        PBSO_CUDA(cudaMalloc(&f->d_q8_sk, sk.size() * sizeof(double)));
+        PBSO_CUDA(cudaMemcpy(f->d_q8_sk, sk.data(), sk.size() * sizeof(double), cudaMemcpyHostToDevice));
+        if (f->shared_geom) {
+            const int D = f->D;
+            std::vector<uint8_t> tm((size_t)D * ns, 0);
+            for (int m = 0; m < n; ++m) { const auto& c = f->maps.at(m).q8; for (int t = 0; t < D; ++t) tm[(size_t)t * ns + m] = c[t]; }
+            PBSO_CUDA(cudaMalloc(&f->d_q8_tm, tm.size()));
+            PBSO_CUDA(cudaMemcpy(f->d_q8_tm, tm.data(), tm.size(), cudaMemcpyHostToDevice));
+        }
+        f->q8_ready = true;
+    }
+    // leading maps whose _Psi / _compressed_Psi is there to be read (GetMapVal's two views)
+    f->n_uncompressed = 0; while (f->n_uncompressed < n && f->maps.at(f->n_uncompressed).has_plain()) ++f->n_uncompressed;
+    f->n_compressed = 0;
+    if (f->q8_ready) f->n_compressed = n;
+    else while (f->n_compressed < n && f->maps.at(f->n_compressed).is_compressed && f->maps.at(f->n_compressed).q8.empty()) ++f->n_compressed;
     f->dirty = false;
     return PBSO_OK;
 }
 
-static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, double* d_out, cudaStream_t s) {
+// q8: read the byte tables of the compressed view (maps compressed in memory); otherwise the stored doubles
+static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, double* d_out, cudaStream_t s, bool q8 = false) {
     if (f->shared_geom) {
         if ((size_t)L > f->loc_cap) {
             cudaFree(f->d_loc); f->d_loc = nullptr; f->loc_cap = 0;
@@ -564,11 +718,13 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
         TileTable tt;
         std::memcpy(tt.tiles_y, f->tiles_y, sizeof(tt.tiles_y)); std::memcpy(tt.tile_base, f->tile_base, sizeof(tt.tile_base));
         const char* env = getenv("PBSO_FFAT_STAGED");
-        const bool staged = env && env[0] == '1';
+        const bool staged = env && env[0] == '1' && !q8;
         const char* env_g = getenv("PBSO_FFAT_GATHER");
         const int n_tiles = f->tile_base[6];
         const size_t list_need = (size_t)n_tiles * L;
-        const bool tiles = L >= FT_MIN_L && 4ll * L >= f->D && list_need * sizeof(TileRec) <= ((size_t)512 << 20) && !staged && !(env_g && env_g[0] == '1');
+        // the byte table of 1024 maps is 6 MB and sits in L2: gathering per listener costs 1 sector per warp and tap, the
+        // output write is what is left, so the 8-bit view needs no texel-stationary pass
+        const bool tiles = !q8 && L >= FT_MIN_L && 4ll * L >= f->D && list_need * sizeof(TileRec) <= ((size_t)512 << 20) && !staged && !(env_g && env_g[0] == '1');
         int *cnt_cur = nullptr, *cnt_next = nullptr;
         if (tiles && !f->d_psi_tiles) {
             // tiled copy of Psi: [mode slab][tile][FT_H x FT_H texels incl. the high-side halo][FT_MS modes], zero-filled
@@ -634,14 +790,16 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
             f->cnt_parity ^= 1;
         }
         Geo g0; load_geo(g0, f->maps.at(0).geom, f->maps.at(0).igeom);
+        const bool q8x4 = q8 && L > FG_FUSED_MAX && n_modes % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
         if (L <= FG_FUSED_MAX && !staged) {
-            k_ffat_gather_fused<<<dim3(div_up(n_modes, 256), div_up(L, FG_LPB)), 256, 0, s>>>(n_modes, L, g0, f->d_geom, f->d_psi_tm, f->n_dense,
-                                                                                          d_pos, d_out);
+            const dim3 grid(div_up(n_modes, 256), div_up(L, FG_LPB));
+            if (q8) k_ffat_gather_fused<uint8_t><<<grid, 256, 0, s>>>(n_modes, L, g0, f->d_geom, f->d_q8_tm, f->q8_stride, f->d_q8_scale, d_pos, d_out);
+            else k_ffat_gather_fused<double><<<grid, 256, 0, s>>>(n_modes, L, g0, f->d_geom, f->d_psi_tm, f->n_dense, nullptr, d_pos, d_out);
             PBSO_CUDA(cudaGetLastError());
             return PBSO_OK;
         }
         k_ffat_locate<<<div_up(std::max(L, tiles ? n_tiles + 1 : 0), FL_THREADS), FL_THREADS, 0, s>>>(L, g0, d_pos, (FfatLoc*)f->d_loc, tt,
-                                                                                tiles ? (TileRec*)f->d_tile_rec : nullptr, cnt_cur, cnt_next);
+                                                                                tiles ? (TileRec*)f->d_tile_rec : nullptr, cnt_cur, cnt_next, q8x4);
         const size_t stage_bytes = (size_t)FS_G * f->D * sizeof(double);
         // Measured on B200 (profiles/r1_ffat.md): for 1024 maps x 10 242 listeners the staged kernel is bound by LSU
         // wavefronts (scattered 8-byte shared-memory gathers + 32-byte output segments) at ~100 us, the coalesced
@@ -668,12 +826,28 @@ static int launch_eval(pbso_ffat* f, int n_modes, const double* d_pos, int L, do
             k_ffat_staged<<<dim3(groups, l_split), FS_THREADS, stage_bytes, s>>>(n_modes, L, f->D, l_split, f->d_geom, f->d_psi_mm,
                                                                                  (const FfatLoc*)f->d_loc, d_out);
         } else {
-            k_ffat_gather<<<dim3(div_up(n_modes, 256), div_up(L, FG_LPB)), 256, 0, s>>>(n_modes, L, f->d_geom, f->d_psi_tm,
-                                                                                     f->n_dense, (const FfatLoc*)f->d_loc, d_out);
+            if (q8x4) {
+                cudaLaunchConfig_t cfg = {};
+                const int gx = div_up(n_modes, 1024);
+                // measured on B200 (1024 maps x 10 242 listeners, locate included): whole-sector stores 27.6 us against 35.8 us
+                // with half-sector stores; 2 listeners in flight per thread and one resident wave (1 or 4 in flight, 4 waves:
+                // within 2 us)
+                const bool split = n_modes % 128 == 0;
+                auto kern = split ? k_ffat_gather_q8x4<2, true> : k_ffat_gather_q8x4<2, false>;
+                PBSO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f->q8x4_ctas, kern, 256, 0));
+                cfg.gridDim = dim3(gx, std::min(L, std::max(1, f->q8x4_ctas * f->sm_count / gx))); cfg.blockDim = dim3(256); cfg.stream = s;   // one resident wave
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                PBSO_CUDA(cudaLaunchKernelEx(&cfg, kern, n_modes, L, (const uint8_t*)f->d_q8_tm, f->q8_stride,
+                                             (const double*)f->d_q8_sk, (const FfatLoc*)f->d_loc, d_out));
+            } else if (q8) k_ffat_gather<uint8_t, FG_LPB_Q8><<<dim3(div_up(n_modes, 256), div_up(L, FG_LPB_Q8)), 256, 0, s>>>(n_modes, L, f->d_geom, f->d_q8_tm, f->q8_stride, f->d_q8_scale, (const FfatLoc*)f->d_loc, d_out);
+            else k_ffat_gather<double, FG_LPB><<<dim3(div_up(n_modes, 256), div_up(L, FG_LPB)), 256, 0, s>>>(n_modes, L, f->d_geom, f->d_psi_tm, f->n_dense, nullptr, (const FfatLoc*)f->d_loc, d_out);
         }
     } else {
         dim3 grid(div_up(n_modes, 128), std::min(L, 65535));
-        k_ffat_eval_general<<<grid, 128, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_psi_mm, f->d_psi_off, d_pos, d_out);
+        if (q8) k_ffat_eval_general<uint8_t><<<grid, 128, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_q8_mm, f->d_psi_off, f->d_q8_scale, f->q8_stride, d_pos, d_out);
+        else k_ffat_eval_general<double><<<grid, 128, 0, s>>>(n_modes, L, f->d_geom, f->d_igeom, f->d_psi_mm, f->d_psi_off, nullptr, 0, d_pos, d_out);
     }
     PBSO_CUDA(cudaGetLastError());
     return PBSO_OK;
@@ -806,19 +980,100 @@ int pbso_ffat_eval(const pbso_ffat* fc, int n_modes, const double* pos, int L, i
     if (np > f->pos_cap) { cudaFree(f->d_pos); PBSO_CUDA(cudaMalloc(&f->d_pos, np * sizeof(double))); f->pos_cap = np; }
     if (no > f->out_cap) { cudaFree(f->d_out); PBSO_CUDA(cudaMalloc(&f->d_out, no * sizeof(double))); f->out_cap = no; }
     PBSO_CUDA(cudaMemcpyAsync(f->d_pos, pos, np * sizeof(double), cudaMemcpyHostToDevice, f->stream));
-    if (int rc = launch_eval(f, n_modes, f->d_pos, L, f->d_out, f->stream)) return rc;
+    if (int rc = launch_eval(f, n_modes, f->d_pos, L, f->d_out, f->stream, use_compressed && f->q8_ready)) return rc;
     PBSO_CUDA(cudaMemcpyAsync(out, f->d_out, no * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
     PBSO_CUDA(cudaStreamSynchronize(f->stream));
     return PBSO_OK;
 }
 
-int pbso_ffat_eval_device(const pbso_ffat* fc, int n_modes, const double* d_pos, int L, double* d_out, void* cuda_stream) {
+int pbso_ffat_eval_device_view(const pbso_ffat* fc, int n_modes, const double* d_pos, int L, int use_compressed, double* d_out, void* cuda_stream) {
     pbso_ffat* f = const_cast<pbso_ffat*>(fc);
-    if (int rc = check_eval_args(f, n_modes, L, 0)) return rc;
+    if (int rc = check_eval_args(f, n_modes, L, use_compressed)) return rc;
     PBSO_REQUIRE(d_pos && d_out, PBSO_ERR_INVALID, "null argument");
     if (n_modes == 0 || L == 0) return PBSO_OK;
     DeviceGuard g(f->device);
-    return launch_eval(f, n_modes, d_pos, L, d_out, cuda_stream ? (cudaStream_t)cuda_stream : f->stream);
+    return launch_eval(f, n_modes, d_pos, L, d_out, cuda_stream ? (cudaStream_t)cuda_stream : f->stream, use_compressed && f->q8_ready);
+}
+
+int pbso_ffat_eval_device(const pbso_ffat* fc, int n_modes, const double* d_pos, int L, double* d_out, void* cuda_stream) {
+    return pbso_ffat_eval_device_view(fc, n_modes, d_pos, L, 0, d_out, cuda_stream);
+}
+
+// ---- FFAT_Map<T,3>::Compress (ffat_solver.h:1125-1178), split where the reference goes through a JPEG file ----------
+// cv::Mat::convertTo(CV_8U) is saturate_cast<uchar>(double): cvRound (round half to even; NaN and anything outside int
+// come back as INT_MIN) and then a clamp to [0, 255].
+static inline uint8_t cv_saturate_u8(double v) {
+    if (!(std::fabs(v) < 2147483648.0)) return 0;              // NaN / out of int range -> INT_MIN -> 0
+    const double r = std::nearbyint(v);                          // default rounding mode: half to even, like cvtsd2si
+    return r <= 0.0 ? 0 : r >= 255.0 ? 255 : (uint8_t)r;
+}
+
+int pbso_ffat_quantise(const pbso_ffat* f, int mode_id, unsigned char* q8, double* max_amp6, double* max_amp_global) {
+    PBSO_REQUIRE(f, PBSO_ERR_INVALID, "null handle");
+    auto it = f->maps.find(mode_id);
+    if (it == f->maps.end()) return set_error(PBSO_ERR_RANGE, "no map with mode id %d", mode_id);
+    const HostMap& hm = it->second;
+    if (!hm.has_plain()) return set_error(PBSO_ERR_UNSUPPORTED, "map %d was loaded compressed: it has no _Psi to compress", mode_id);
+    const std::vector<double>& P = hm.psi[0];
+    size_t off = 0; double gmax = -1.0;                           // :1132 maxAmp_global = -1
+    for (int fc = 0; fc < 6; ++fc) {
+        const size_t n = (size_t)hm.igeom[2 * fc] * hm.igeom[2 * fc + 1];       // ConvertToImages (:1106-1122): running offset
+        if (off + n > P.size()) return set_error(PBSO_ERR_FORMAT, "map %d: faces address texels outside psi", mode_id);
+        double mx = P[off];
+        for (size_t i = 1; i < n; ++i) mx = std::max(mx, P[off + i]);          // A_amp.maxCoeff() (:1139)
+        gmax = std::max(gmax, mx);                                             // :1134-1136
+        const double up = 255 / mx;                                            // :1144 A_amp *= 255/maxAmp
+        if (q8) for (size_t i = 0; i < n; ++i) q8[off + i] = cv_saturate_u8(P[off + i] * up);   // :1145-1147
+        if (max_amp6) max_amp6[fc] = mx;
+        off += n;
+    }
+    if (q8) for (size_t i = off; i < P.size(); ++i) q8[i] = 0;
+    if (max_amp_global) *max_amp_global = gmax;
+    return PBSO_OK;
+}
+
+int pbso_ffat_set_compressed_u8(pbso_ffat* f, int mode_id, const unsigned char* q8, int len, const double* max_amp6) {
+    PBSO_REQUIRE(f && q8 && max_amp6, PBSO_ERR_INVALID, "null argument");
+    auto it = f->maps.find(mode_id);
+    if (it == f->maps.end()) return set_error(PBSO_ERR_RANGE, "no map with mode id %d", mode_id);
+    HostMap& hm = it->second;
+    if (!hm.has_plain()) return set_error(PBSO_ERR_UNSUPPORTED, "map %d was loaded compressed", mode_id);
+    PBSO_REQUIRE(len == (int)hm.psi[0].size(), PBSO_ERR_INVALID, "q8 must hold one byte per texel of psi");
+    hm.q8.assign(q8, q8 + len);
+    for (int fc = 0; fc < 6; ++fc) { hm.q8_amp[fc] = max_amp6[fc]; hm.q8_scale[fc] = max_amp6[fc] / 255.; }   // :1162 A_amp *= maxAmp/255.
+    hm.is_compressed = true;                                                   // :1173
+    f->dirty = true;
+    return PBSO_OK;
+}
+
+int pbso_ffat_compress(pbso_ffat* f, int mode_id, double* max_amp_global) {
+    PBSO_REQUIRE(f, PBSO_ERR_INVALID, "null handle");
+    std::vector<int> ids;
+    if (mode_id >= 0) ids.push_back(mode_id); else for (auto& kv : f->maps) ids.push_back(kv.first);
+    std::vector<unsigned char> q;
+    for (size_t i = 0; i < ids.size(); ++i) {
+        auto it = f->maps.find(ids[i]);
+        if (it == f->maps.end()) return set_error(PBSO_ERR_RANGE, "no map with mode id %d", ids[i]);
+        q.resize(it->second.psi[0].size());
+        double amp[6], g = 0.0;
+        if (int rc = pbso_ffat_quantise(f, ids[i], q.data(), amp, &g)) return rc;
+        if (int rc = pbso_ffat_set_compressed_u8(f, ids[i], q.data(), (int)q.size(), amp)) return rc;
+        if (max_amp_global) max_amp_global[i] = g;
+    }
+    return PBSO_OK;
+}
+
+int pbso_ffat_get_compressed(const pbso_ffat* f, int mode_id, unsigned char* q8, double* max_amp6, double* compressed_psi) {
+    PBSO_REQUIRE(f, PBSO_ERR_INVALID, "null handle");
+    auto it = f->maps.find(mode_id);
+    if (it == f->maps.end()) return set_error(PBSO_ERR_RANGE, "no map with mode id %d", mode_id);
+    const HostMap& hm = it->second;
+    if (!hm.is_compressed) return set_error(PBSO_ERR_UNSUPPORTED, "map %d is not compressed", mode_id);
+    if ((q8 || max_amp6) && hm.q8.empty()) return set_error(PBSO_ERR_UNSUPPORTED, "map %d was loaded compressed: only its doubles are known", mode_id);
+    if (q8) std::memcpy(q8, hm.q8.data(), hm.q8.size());
+    if (max_amp6) std::memcpy(max_amp6, hm.q8_amp, sizeof(hm.q8_amp));
+    if (compressed_psi) { const std::vector<double> c = hm.compressed_column(); std::memcpy(compressed_psi, c.data(), c.size() * sizeof(double)); }
+    return PBSO_OK;
 }
 
 }  // extern "C"

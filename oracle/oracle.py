@@ -374,6 +374,39 @@ def ffat_eval(maps, pos):
     return out
 
 
+def cv_saturate_u8(x):
+    """cv::saturate_cast<uchar>(double) = cvRound (cvtsd2si: round half to even; NaN / outside int -> INT_MIN) clamped to
+    [0, 255] -- what cv::Mat::convertTo(CV_8U) applies (ffat_solver.h:1147).  [pinned: tests/golden/ffat_compress.npz
+    cast_in/cast_out and q8_pre, produced by OpenCV itself]"""
+    x = np.asarray(x, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        bad = ~(np.abs(x) < 2147483648.0)
+        r = np.clip(np.rint(np.where(bad, 0.0, x)), 0, 255)
+    return np.where(bad, 0, r).astype(np.uint8)
+
+
+def ffat_quantise(m):
+    """FFAT_Map<T,3>::Compress up to the image (ffat_solver.h:1128-1147; ConvertToImages :1106-1122)
+    -> (q8, maxAmp[6], maxAmp_global)."""
+    psi = _f64(m["psi"]); q = np.zeros(len(psi), np.uint8); amp = np.empty(6); off = 0; gmax = -1.0
+    for fc, (nx, ny) in enumerate(np.asarray(m["n_elements"]).reshape(6, 2)):
+        A = psi[off:off + nx * ny]
+        mx = A.max(); amp[fc] = mx; gmax = max(gmax, mx)                       # :1134-1139
+        with np.errstate(divide="ignore", invalid="ignore"):
+            q[off:off + nx * ny] = cv_saturate_u8(A * (np.float64(255) / mx))  # :1144-1147
+        off += nx * ny
+    return q, amp, gmax
+
+
+def ffat_dequantise(m, q8, amp):
+    """Compress after the image round trip (ffat_solver.h:1159-1171): _compressed_Psi = data_s (CV_64F) * (maxAmp/255.)."""
+    q8 = np.asarray(q8, dtype=np.uint8); c = np.zeros(len(q8)); off = 0
+    for fc, (nx, ny) in enumerate(np.asarray(m["n_elements"]).reshape(6, 2)):
+        c[off:off + nx * ny] = q8[off:off + nx * ny].astype(np.float64) * (amp[fc] / 255.)
+        off += nx * ny
+    return c
+
+
 def ffat_intersect(m, p):
     """ffat_solver.h:676-712"""
     geom, igeom, _, _ = pack_ffat([m])

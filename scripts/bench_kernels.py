@@ -121,8 +121,28 @@ def run_all(quick=False, ffat_only=False, fit_only=False, tf32_peak=None):
             k3[-1]["parity_max_rel_vs_per_listener_gather"] = float(((o_tiles - o).abs() / o.abs().clamp_min(1e-300)).max().item())
         else:
             k3[-1]["note"] = "launch / latency bound at this size: %.1f MB in one launch" % (bytes_alg / 1e6)
+    # the 8-bit view (FFAT_Map::Compress): one byte per texel + maxAmp/255 per (map, face)
+    k3q = []
+    if not fit_only:
+        dicts = synth.ffat_maps(freqs, 2000)
+        fm8 = pbso.FFATMaps.from_dicts(dicts); fm8.Compress()
+        fd8 = pbso.FFATMaps.from_dicts([dict(m, psi=fm8.get_compressed(i)[2], is_compressed=True) for i, m in enumerate(dicts)])
+        for L in ([10242] if ffat_only else [64] if quick else [64, 10242]):
+            pos = torch.from_numpy(synth.listeners(L, 5)).cuda()
+            o = torch.empty(L, Mf, device="cuda", dtype=torch.float64); o2 = torch.empty_like(o)
+            fn = lambda: pbso._capi.check(pbso.lib().pbso_ffat_eval_device_view(fm8._h, Mf, C.c_void_p(pos.data_ptr()), L, 1, C.c_void_p(o.data_ptr()), C.c_void_p(sp)))
+            med, best = ev_time(fn, iters=10)
+            os.environ["PBSO_FFAT_GATHER"] = "1"
+            pbso._capi.check(pbso.lib().pbso_ffat_eval_device_view(fd8._h, Mf, C.c_void_p(pos.data_ptr()), L, 1, C.c_void_p(o2.data_ptr()), C.c_void_p(sp)))
+            del os.environ["PBSO_FFAT_GATHER"]
+            torch.cuda.synchronize()
+            bytes_alg = Mf * (min(6144, 4 * L) * 1 + 6 * 8 + L * 8)
+            k3q.append({"L": L, "us": med * 1e3, "us_best": best * 1e3, "algorithmic_MB": bytes_alg / 1e6, "GBps": bytes_alg / (med * 1e-3) / 1e9,
+                        "frac_of_hbm": bytes_alg / (med * 1e-3) / 1e9 / hbm, "kernel": "k_ffat_gather_fused<u8>" if L <= 256 else "k_ffat_locate + k_ffat_gather_q8x4",
+                        "parity_max_rel_vs_the_doubles_of_compressed_Psi": float(((o - o2).abs() / o2.abs().clamp_min(1e-300)).max().item())})
     out["K3_ffat_eval"] = {"modes": Mf, "texels": 6144, "bound": "hbm", "hbm_peak_gbs": hbm, "runs": k3,
-                           "algorithmic_bytes": "M (min(D, 4 L) 8 + L 8) per call (SURVEY 8d)"}
+                           "algorithmic_bytes": "M (min(D, 4 L) 8 + L 8) per call (SURVEY 8d)",
+                           "compressed_view_u8": {"runs": k3q, "algorithmic_bytes": "M (min(D, 4 L) 1 + 48 + L 8) per call: one byte per texel + 6 face scales + the output"}}
 
     # ---- K6: FFAT map construction (FFAT_Map<T,3>::Solve for all modes of an object at once) -------------
     # shells of 16/24/32 cells per edge (shell 2 = the 6 x 32 x 32 run-time map of the other configs), 1024 modes

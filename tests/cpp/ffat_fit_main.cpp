@@ -5,6 +5,7 @@
 // vertices.f64: rows x 3 doubles (row-major).  Prints GetMapVal(probe) with 17 significant digits.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 #include "ffat_map_serialize.h"
 #include "ffat_solver.h"
@@ -38,5 +39,13 @@ int main(int argc, char** argv) {
     if (!FFAT_Map_Serialize::Check(map, back)) { fprintf(stderr, "Check failed after Save/Load\n"); return 4; }
     Eigen::Matrix<double, 3, 1> probe; probe << atof(argv[10]), atof(argv[11]), atof(argv[12]);
     printf("%d %d %.17g %.17g\n", (int)map.GetData().rows(), (int)map.GetData().cols(), map.GetMapVal(probe), back.GetMapVal(probe));
+    // FFAT_Map<T,3>::Compress: 8-bit view next to _Psi; Save then keeps _compressed_Psi and the loaded map answers
+    // GetMapVal(p, true) only
+    const double amp = map.Compress();
+    const std::string cfile = std::string(argv[9]) + ".compressed";
+    FFAT_Map_Serialize::Save(cfile.c_str(), map);
+    FFAT_Map<double, 3> cback;
+    FFAT_Map_Serialize::Load(cfile.c_str(), cback);
+    printf("%.17g %.17g %.17g %.17g\n", amp, map.GetMapVal(probe, true), cback.GetMapVal(probe, true), map.GetMapVal(probe));
     return 0;
 }

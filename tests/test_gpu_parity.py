@@ -771,14 +771,20 @@ def test_ffat_fit_header_mirror_caller(pbso, orc, tmp_path):
             r = subprocess.run([exe, nfile, vfile, repr(w["cell_size"]), "6", repr(float(w["k"][0])), pfile, str(binary), str(scaling),
                                 out] + [repr(x) for x in probe], capture_output=True, text=True)
             assert r.returncode == 0, r.stderr
-            rows, cols, v1, v2 = r.stdout.split()
-            assert (int(rows), int(cols)) == (fit["n_dir"], 1) and v1 == v2
+            rows, cols, v1, v2, amp, c1, c2, v3 = r.stdout.split()
+            assert (int(rows), int(cols)) == (fit["n_dir"], 1) and v1 == v2 == v3 and c1 == c2
             d = fatcube.load(out)
             assert d["modeid"] == 6 and np.allclose(d["psi"], want[0], rtol=1e-12, atol=0)
             g, ig = fit["geom"][2], fit["igeom"][2]
             m = dict(cellsize=g[0], lowcorners=g[1:19].reshape(6, 3), center1=g[19:22], bboxlow=g[22:25], bboxtop=g[25:28],
                      center=g[28:31], k=w["k"][0], n_elements=ig[:12].reshape(6, 2), strides=ig[12:], psi=want[0], modeid=0)
             assert np.isclose(float(v1), orc.ffat_eval([m], [probe])[0, 0], rtol=1e-11)
+            md = dict(m, psi=d["psi"])                                   # Compress works on the Psi the device fitted
+            q, amp6, gmax = orc.ffat_quantise(md)
+            assert float(amp) == gmax
+            assert np.isclose(float(c1), orc.ffat_eval([dict(md, psi=orc.ffat_dequantise(md, q, amp6))], [probe])[0, 0], rtol=1e-12)
+            dc = fatcube.load(out + ".compressed")
+            assert dc["is_compressed"] and np.array_equal(dc["psi"], orc.ffat_dequantise(md, q, amp6))
 
 
 def test_ffat_fit_reproduces_the_reference_fixture(pbso, golden_dir):
@@ -793,6 +799,64 @@ def test_ffat_fit_reproduces_the_reference_fixture(pbso, golden_dir):
     for scaling, key in ((False, "psi"), (True, "psi_scaled")):
         psi, _ = ft.Solve(g["k"], g["pressure"], scaling)
         assert np.allclose(psi, g[key], rtol=1e-12, atol=0)
+
+
+def test_ffat_compress_reproduces_the_opencv_fixture(pbso, orc, golden_dir, tmp_path):
+    """FFAT_Map<T,3>::Compress (ffat_solver.h:1125-1178) against tests/golden/ffat_compress.npz (OpenCV's own cast and JPEG
+    codec): quantise() gives OpenCV's bytes; the bytes that came back from the JPEG file, handed to set_compressed_u8(),
+    give _compressed_Psi bit for bit; GetMapVal(p, getCompressed=true) read from the device's BYTE table equals the oracle
+    on the stored doubles, and is bit-identical to the same kernels reading those doubles; Save/Load keeps the view."""
+    g = np.load(os.path.join(golden_dir, "ffat_compress.npz"))
+    maps = synth.ffat_maps(g["freqs"], 2000, n=8)
+    for i, m in enumerate(maps):
+        m["psi"] = g["psi"][i]
+    fm = pbso.FFATMaps.from_dicts(maps)
+    with pytest.raises(pbso.PbsoError):
+        fm.computeTransfer(synth.listeners(4, 1), use_compressed=True)           # asserts _is_compressed (:1183-1186)
+    for i in range(3):
+        q, amp, gmax = fm.quantise(i)
+        assert np.array_equal(q, g["q8_pre"][i]) and np.array_equal(amp, g["max_amp"][i]) and gmax == g["max_amp_global"][i]
+        fm.set_compressed_u8(i, g["q8_post"][i], amp)
+        q2, sc, c = fm.get_compressed(i)
+        assert np.array_equal(q2, g["q8_post"][i]) and np.array_equal(c, g["compressed_psi"][i])
+    cmaps = [dict(m, psi=g["compressed_psi"][i], is_compressed=True) for i, m in enumerate(maps)]
+    fd = pbso.FFATMaps.from_dicts(cmaps)                                         # the same view held as doubles
+    for L in (80, 700, 3000):                                                    # fused / locate + gather (twice: no byte tiles)
+        pos = synth.listeners(L, 77)
+        got = fm.computeTransfer(pos, use_compressed=True)
+        assert np.array_equal(got, fd.computeTransfer(pos[:L], use_compressed=True)) or L >= 2048
+        assert np.allclose(got, orc.ffat_eval(cmaps, pos), rtol=1e-12, atol=0)
+        # _Psi is still there (Compress keeps it)
+        assert np.allclose(fm.computeTransfer(pos), orc.ffat_eval(maps, pos), rtol=1e-12, atol=0)
+    # a multiple of four maps and many listeners: the four-maps-per-thread byte kernel (products by (maxAmp/255)/k and 1/r
+    # instead of the division: tolerance, not bits)
+    m8 = synth.ffat_maps(synth.mode_frequencies(8, 1004), 2000, n=8)
+    f8 = pbso.FFATMaps.from_dicts(m8); f8.Compress()
+    c8 = [dict(m, psi=f8.get_compressed(i)[2]) for i, m in enumerate(m8)]
+    for L in (257, 3000):
+        pos = synth.listeners(L, 79)
+        assert np.allclose(f8.computeTransfer(pos, use_compressed=True), orc.ffat_eval(c8, pos), rtol=1e-12, atol=0)
+    # per-map geometry (the general kernel) reads bytes too: a set whose second map has another cell size
+    odd = [dict(maps[0]), dict(maps[1], cellsize=maps[1]["cellsize"] * 1.0000001)]
+    fo = pbso.FFATMaps.from_dicts(odd)
+    fo.Compress()
+    codd = [dict(m, psi=fo.get_compressed(i)[2]) for i, m in enumerate(odd)]
+    pos = synth.listeners(300, 78)
+    assert np.allclose(fo.computeTransfer(pos, use_compressed=True), orc.ffat_eval(codd, pos), rtol=1e-12, atol=0)
+    # Save writes _compressed_Psi (ffat_map_serialize.h:149-153); a map loaded compressed has no _Psi and cannot be compressed
+    fn = str(tmp_path / "m.fatcube")
+    fm.Save(1, fn)
+    back = pbso.FFATMaps.Load(fn)
+    got = back.get_map(1)
+    assert got["is_compressed"] and np.array_equal(got["psi"], g["compressed_psi"][1])
+    with pytest.raises(pbso.PbsoError):
+        back.Compress(1)
+    # Compress() of every map without a codec in between == quantise + de-quantise of the oracle
+    fa = pbso.FFATMaps.from_dicts(maps)
+    gm = fa.Compress()
+    for i, m in enumerate(maps):
+        q, amp, gmax = orc.ffat_quantise(m)
+        assert gm[i] == gmax and np.array_equal(fa.get_compressed(i)[2], orc.ffat_dequantise(m, q, amp))
 
 
 def test_ffat_eval_reproduces_the_reference_fixture(pbso, golden_dir):

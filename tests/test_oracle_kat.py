@@ -248,3 +248,18 @@ def test_ffat_eval_oracle_reproduces_the_reference_fixture(orc, golden_dir):
     assert np.allclose(got[fin], ref[fin], rtol=1e-13, atol=0)
     shared = synth.ffat_maps(g["shared_freqs"], 2000, n=8)
     assert np.allclose(orc.ffat_eval(shared, g["shared_pos"]), g["shared_out"], rtol=1e-13, atol=0)
+
+
+def test_ffat_compress_oracle_reproduces_the_opencv_fixture(orc, golden_dir):
+    """tests/golden/ffat_compress.npz holds FFAT_Map<T,3>::Compress carried out with OpenCV's own cast and JPEG codec
+    (tests/golden/make_golden_ffat_compress.py): the restated quantisation must give OpenCV's bytes, and the restated
+    de-quantisation of the bytes that came back from the JPEG file must give _compressed_Psi, bit for bit."""
+    g = np.load(os.path.join(golden_dir, "ffat_compress.npz"))
+    assert np.array_equal(orc.cv_saturate_u8(g["cast_in"]), g["cast_out"])
+    maps = synth.ffat_maps(g["freqs"], 2000, n=8)
+    for i, m in enumerate(maps):
+        m = dict(m); m["psi"] = g["psi"][i]
+        q, amp, gmax = orc.ffat_quantise(m)
+        assert np.array_equal(q, g["q8_pre"][i])
+        assert np.array_equal(amp, g["max_amp"][i]) and gmax == g["max_amp_global"][i]
+        assert np.array_equal(orc.ffat_dequantise(m, g["q8_post"][i], amp), g["compressed_psi"][i])
