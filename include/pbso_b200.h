@@ -272,6 +272,16 @@ int pbso_batch_render_mix_device(pbso_batch* bt, int buf_size, int n_buffers, in
 /* Per-object stems: y[n_obj][n_buffers*buf_size] float32 (y as in SoundMessage, before /1e10). */
 int pbso_batch_render_stems(pbso_batch* bt, int buf_size, int n_buffers, int precision,
                             float* stems);
+/* Stateful range renders.  A render normally starts from the zero state of a fresh ModalSolver; pbso_batch_set_state
+ * makes the next renders start from (q_km1, q_km2) = (q[k-1], q[k-2]) per (object, mode) -- the pair ModalIntegrator keeps
+ * (modal_integrator.h:106-113) and pbso_integrator_get_state returns -- and pbso_batch_get_end_state returns that pair
+ * after n_buffers x buf_size samples of the current state + impulse script, in closed form (FP64 pole powers, whatever
+ * precision the audio was rendered in).  A long script is then rendered range by range: a TransMessage that arrives in
+ * mid-render (modal_solver.h:249-252) is a range boundary with pbso_batch_set_transfer in between, and buffers in which a
+ * Gaussian or autoregressive force is alive (forces.h:92-137) go through the per-buffer path (pbso_render_buffer on a
+ * pbso_integrator holding the same state) between two batch ranges.  Both arrays NULL = back to the zero state. */
+int pbso_batch_set_state(pbso_batch* bt, const double* q_km1, const double* q_km2);
+int pbso_batch_get_end_state(pbso_batch* bt, int buf_size, int n_buffers, double* q_km1, double* q_km2);
 int pbso_batch_sync(pbso_batch* bt);
 /* Run this handle's work on a caller-owned CUDA stream (cudaStream_t as void*; NULL restores the
  * handle's own stream) so that renders order with the caller's copies / NCCL calls without host syncs. */

@@ -108,6 +108,8 @@ def lib():
             "pbso_batch_render_mix_device": [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
             "pbso_batch_render_stems": [vp, C.c_int, C.c_int, C.c_int, c_fp],
             "pbso_batch_sync": [vp],
+            "pbso_batch_set_state": [vp, c_dp, c_dp],
+            "pbso_batch_get_end_state": [vp, C.c_int, C.c_int, c_dp, c_dp],
             "pbso_batch_set_stream": [vp, vp],
             "pbso_batch_last_kernel_ms": [vp, c_fp, c_ip],
             "pbso_comm_unique_id": [C.POINTER(C.c_ubyte)],

@@ -466,6 +466,20 @@ class BatchRenderer:
         check(lib().pbso_batch_render_stems(self._h, buf_size, n_buffers, precision, st.ctypes.data_as(capi.c_fp)))
         return st
 
+    def set_state(self, q_km1=None, q_km2=None):
+        """Stateful range renders: the next renders start from (q[k-1], q[k-2]) per (object, mode), the pair
+        ModalIntegrator keeps (modal_integrator.h:106-113); None = the zero state of a fresh solver."""
+        if q_km1 is None:
+            check(lib().pbso_batch_set_state(self._h, None, None)); return
+        q1 = f64(q_km1).reshape(self.n_obj, self.n_modes); q2 = f64(q_km2).reshape(self.n_obj, self.n_modes)
+        check(lib().pbso_batch_set_state(self._h, dp(q1), dp(q2)))
+
+    def end_state(self, buf_size, n_buffers):
+        """(q[k-1], q[k-2]) after n_buffers x buf_size samples of the current state + impulse script (FP64, closed form)."""
+        q1 = np.empty((self.n_obj, self.n_modes)); q2 = np.empty((self.n_obj, self.n_modes))
+        check(lib().pbso_batch_get_end_state(self._h, buf_size, n_buffers, dp(q1), dp(q2)))
+        return q1, q2
+
     def sync(self):
         check(lib().pbso_batch_sync(self._h))
 

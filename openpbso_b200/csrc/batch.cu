@@ -50,6 +50,9 @@ struct pbso_batch {
     int sm_count = 148;
     std::vector<int> h_ev_off, h_ev_buf;      // host copy of the impulse CSR (unit list of the tensor-core path)
     unsigned trans_ver = 0, ev_ver = 0;
+    // state at the start of the render (stateful range renders): q[-1] | q[-2] as ModalIntegrator keeps them, and the
+    // same state as the complex carrier v0 (q[j] = Im(v0 w^j) for the free response) | 4 arrays of n_obj*n_modes
+    double* d_state = nullptr; bool has_state = false;
     TcState* tc = nullptr;
     size_t npm() const { return (size_t)n_obj * n_modes; }
     double* lneps() const { return d_par; }
@@ -59,7 +62,52 @@ struct pbso_batch {
     double* c3() const { return d_par + 4 * npm(); }
     double* cot() const { return d_par + 5 * npm(); }
     double* trans() const { return d_par + 6 * npm(); }
+    const double* q10() const { return has_state ? d_state : nullptr; }
+    const double* q20() const { return has_state ? d_state + npm() : nullptr; }
+    const double* v0r() const { return has_state ? d_state + 2 * npm() : nullptr; }
+    const double* v0i() const { return has_state ? d_state + 3 * npm() : nullptr; }
 };
+
+// (q[-1], q[-2]) -> carrier at sample 0: with u = x + i q[-1] the state one sample earlier, Im(u / w) = q[-2] gives
+// x = (q[-1] cos(theta) - eps q[-2]) / sin(theta), and v0 = u w.  Im(v0) = c1 q[-1] + c2 q[-2], the recurrence's q[0].
+__global__ void k_batch_state_to_carrier(size_t n, const double* __restrict__ lneps, const double* __restrict__ theta,
+                                         const double* __restrict__ q1, const double* __restrict__ q2,
+                                         double* __restrict__ v0r, double* __restrict__ v0i) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c; sincos(theta[i], &s, &c);
+    const double eps = exp(lneps[i]);
+    const double x = (q1[i] * c - eps * q2[i]) / s;
+    v0r[i] = eps * (x * c - q1[i] * s);
+    v0i[i] = eps * (x * s + q1[i] * c);
+}
+
+// State after n_samples: v_N = v0 w^N + sum_e inj_e w^(N - t_e) in closed form (FP64 exp / sincos of the total angle per
+// term), then q[N-1] = Im(v_N / w), q[N-2] = Im(v_N / w^2) -- what ModalIntegrator would hold after the same steps.
+__global__ void k_batch_end_state(int n_obj, int n_modes, long long n_samples, int BUF,
+                                  const double* __restrict__ lneps, const double* __restrict__ theta,
+                                  const double* __restrict__ c3a, const double* __restrict__ cota,
+                                  const int* __restrict__ ev_off, const int* __restrict__ ev_buf, const double* __restrict__ ev_space,
+                                  const double* __restrict__ v0r, const double* __restrict__ v0i,
+                                  double* __restrict__ q1, double* __restrict__ q2) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_obj * n_modes) return;
+    const int o = (int)(i / n_modes), m = (int)(i % n_modes);
+    const double le = lneps[i], th = theta[i];
+    auto powr = [&](double k, double& pr, double& pi) { double s, c; sincos(k * th, &s, &c); const double e = exp(k * le); pr = e * c; pi = e * s; };
+    double vr = 0.0, vi = 0.0, pr, pi;
+    if (v0r) { powr((double)n_samples, pr, pi); vr = v0r[i] * pr - v0i[i] * pi; vi = v0r[i] * pi + v0i[i] * pr; }
+    const double inji = c3a[i], injr = inji * cota[i];
+    for (int e = ev_off[o]; e < ev_off[o + 1]; ++e) {
+        const long long t = (long long)ev_buf[e] * BUF;
+        if (t >= n_samples) break;
+        powr((double)(n_samples - t), pr, pi);
+        const double sp = ev_space[(size_t)e * n_modes + m];
+        vr += sp * (injr * pr - inji * pi); vi += sp * (injr * pi + inji * pr);
+    }
+    powr(-1.0, pr, pi); q1[i] = vr * pi + vi * pr;
+    powr(-2.0, pr, pi); q2[i] = vr * pi + vi * pr;
+}
 
 // row r of dst = row src[r] of stage (impulse scripts that arrive unsorted)
 __global__ void k_gather_rows(int n_modes, const int* __restrict__ src, const double* __restrict__ stage,
@@ -105,7 +153,8 @@ __global__ void __launch_bounds__(BF_TPB)
 k_batch_f64(int n_modes, int slabs, int BUF, int n_buf,
             const double* __restrict__ c1a, const double* __restrict__ c2a, const double* __restrict__ c3a,
             const double* __restrict__ trans, const int* __restrict__ ev_off, const int* __restrict__ ev_buf,
-            const double* __restrict__ ev_space, double* __restrict__ mix, float* __restrict__ stems) {
+            const double* __restrict__ ev_space, const double* __restrict__ q10, const double* __restrict__ q20,
+            double* __restrict__ mix, float* __restrict__ stems) {
     __shared__ double s_part[BF_TPB / 32][32];
     const int obj = blockIdx.x / slabs, slab = blockIdx.x % slabs;
     const int m = slab * BF_TPB + threadIdx.x;
@@ -114,7 +163,7 @@ k_batch_f64(int n_modes, int slabs, int BUF, int n_buf,
     const size_t pm = (size_t)obj * n_modes + (live ? m : 0);
     const double c1 = live ? c1a[pm] : 0.0, c2 = live ? c2a[pm] : 0.0, c3 = live ? c3a[pm] : 0.0;
     const double T = live ? trans[pm] : 0.0;
-    double q1 = 0.0, q2 = 0.0;
+    double q1 = (live && q10) ? q10[pm] : 0.0, q2 = (live && q20) ? q20[pm] : 0.0;
     int ev = ev_off[obj];
     const int ev_end = ev_off[obj + 1];
     int next_buf = ev < ev_end ? ev_buf[ev] : INT_MAX;
@@ -175,6 +224,7 @@ k_batch_pow(int n_modes, int slabs, int n_buf,
             const double* __restrict__ lneps, const double* __restrict__ theta,
             const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
             const int* __restrict__ ev_off, const int* __restrict__ ev_buf, const double* __restrict__ ev_space,
+            const double* __restrict__ v0r, const double* __restrict__ v0i,
             double* __restrict__ mix, float* __restrict__ stems) {
     constexpr int BUF = FB_L * TT;
     __shared__ __align__(16) float sV[FB_WARPS][FB_MB][2 * TT];      // tile-start states (re[TT] | im[TT])
@@ -214,6 +264,7 @@ k_batch_pow(int n_modes, int slabs, int n_buf,
         Wr = e * c; Wi = e * s;                            // w^L
         inji = c3a[obase + my_m];                          // Im part of c3 (wr/wi + i)
         injr = inji * cota[obase + my_m];
+        if (v0r) { vr = v0r[obase + my_m]; vi = v0i[obase + my_m]; }   // stateful range render
     }
     int ev = ev_off[obj];
     const int ev_end = ev_off[obj + 1];
@@ -307,6 +358,7 @@ k_batch_pow_g(int n_modes, int slabs, int n_buf, int n_chunks, int bufs_per_chun
               const double* __restrict__ lneps, const double* __restrict__ theta,
               const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
               const int* __restrict__ ev_off, const int* __restrict__ ev_buf, const double* __restrict__ ev_space,
+              const double* __restrict__ v0r, const double* __restrict__ v0i,
               double* __restrict__ mix, float* __restrict__ stems) {
     constexpr int BUF = 256, L = 32 * JJ, TT = BUF / L, SLAB = WARPS * MB, NT = WARPS * 32;
     static_assert(BUF % L == 0 && (JJ % 2 == 0) && MB <= 32, "bad tile configuration");
@@ -360,6 +412,13 @@ k_batch_pow_g(int n_modes, int slabs, int n_buf, int n_chunks, int bufs_per_chun
     }
     int ev = ev_off[obj];
     const int ev_end = ev_off[obj + 1];
+    if (owner && v0r) {                                               // stateful range render: v0 w^(samples before the chunk)
+        const double n = (double)BUF * (double)b_begin;
+        double s, c; sincos(n * theta[obase + my_m], &s, &c);
+        const double e = exp(n * lneps[obase + my_m]);
+        const double ar = v0r[obase + my_m], ai = v0i[obase + my_m];
+        vr = e * (ar * c - ai * s); vi = e * (ar * s + ai * c);
+    }
     // impulses before this chunk: advance each with the exact pole power (FP64 exp / sincos of the total angle)
     while (ev < ev_end && ev_buf[ev] < b_begin) {
         if (owner) {
@@ -476,7 +535,7 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
         const int grid = bt->n_obj * slabs;
 #define PBSO_LAUNCH_POW(TT)                                                                              \
         k_batch_pow<TT><<<grid, FB_WARPS * 32, 0, bt->stream>>>(bt->n_modes, slabs, n_buffers, bt->lneps(), \
-            bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, d_mix, d_stems)
+            bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, bt->v0r(), bt->v0i(), d_mix, d_stems)
         // 16 warps x 16 modes, 64-sample tiles, packed FFMA2: the best of the variants measured in round 1
         // (profiles/r1_k_batch_pow.md); the others are gone
 #define PBSO_LAUNCH_G(W, MB, JJ, ...)                                                                      \
@@ -487,7 +546,7 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
              const int bpc = div_up(n_buffers, nc); nc = div_up(n_buffers, bpc);                           \
              k_batch_pow_g<W, MB, JJ, __VA_ARGS__><<<bt->n_obj * sl * nc, (W) * 32, 0, bt->stream>>>(bt->n_modes, sl, n_buffers, nc, bpc, \
                  bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->trans(), bt->d_ev_off, bt->d_ev_buf,  \
-                 bt->d_ev_space, d_mix, d_stems); } while (0)
+                 bt->d_ev_space, bt->v0r(), bt->v0i(), d_mix, d_stems); } while (0)
         if (buf_size == 256) PBSO_LAUNCH_G(16, 16, 2, true);
         else if (buf_size == 64) PBSO_LAUNCH_POW(1);
         else if (buf_size == 128) PBSO_LAUNCH_POW(2);
@@ -497,7 +556,7 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
         PBSO_REQUIRE(d_mix && !d_stems, PBSO_ERR_UNSUPPORTED, "PBSO_PREC_TC3X renders the mix only");
         TcArgs ta{bt->n_obj, bt->n_modes, buf_size, n_buffers, bt->sm_count, bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->trans(),
                   bt->h_ev_off.data(), bt->h_ev_buf.data(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, bt->n_events,
-                  bt->trans_ver, bt->ev_ver, d_mix, bt->stream};
+                  bt->trans_ver, bt->ev_ver, bt->v0r(), bt->v0i(), d_mix, bt->stream};
         int nl = 0;
         if (int rc = tc_render(&bt->tc, ta, &nl)) return rc;
         PBSO_CUDA(cudaEventRecord(bt->e1, bt->stream));
@@ -506,7 +565,7 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
     } else if (precision == PBSO_PREC_F64) {
         const int slabs = div_up(bt->n_modes, BF_TPB);
         k_batch_f64<<<bt->n_obj * slabs, BF_TPB, 0, bt->stream>>>(bt->n_modes, slabs, buf_size, n_buffers, bt->c1(),
-            bt->c2(), bt->c3(), bt->trans(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, d_mix, d_stems);
+            bt->c2(), bt->c3(), bt->trans(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, bt->q10(), bt->q20(), d_mix, d_stems);
     } else {
         return set_error(PBSO_ERR_INVALID, "unknown precision %d", precision);
     }
@@ -551,7 +610,7 @@ int pbso_batch_destroy(pbso_batch* bt) {
     if (!bt) return PBSO_OK;
     DeviceGuard g(bt->device);
     if (bt->stream) cudaStreamSynchronize(bt->stream);
-    cudaFree(bt->d_par); cudaFree(bt->d_ev_off); cudaFree(bt->d_ev_buf); cudaFree(bt->d_ev_space); cudaFree(bt->d_mix); cudaFree(bt->d_ev_src); cudaFree(bt->d_ev_stage);
+    cudaFree(bt->d_par); cudaFree(bt->d_ev_off); cudaFree(bt->d_ev_buf); cudaFree(bt->d_ev_space); cudaFree(bt->d_mix); cudaFree(bt->d_ev_src); cudaFree(bt->d_ev_stage); cudaFree(bt->d_state);
     tc_free(bt->tc);
     if (bt->e0) cudaEventDestroy(bt->e0);
     if (bt->e1) cudaEventDestroy(bt->e1);
@@ -673,6 +732,40 @@ int pbso_batch_render_stems(pbso_batch* bt, int buf_size, int n_buffers, int pre
     }
     cudaFree(d_stems);
     return rc;
+}
+
+int pbso_batch_set_state(pbso_batch* bt, const double* q_km1, const double* q_km2) {
+    PBSO_REQUIRE(bt, PBSO_ERR_INVALID, "null handle");
+    PBSO_REQUIRE((q_km1 == nullptr) == (q_km2 == nullptr), PBSO_ERR_INVALID, "q_km1 and q_km2 go together");
+    DeviceGuard g(bt->device);
+    if (!q_km1) { bt->has_state = false; return PBSO_OK; }          // back to the zero state of a fresh solver
+    const size_t n = bt->npm();
+    if (!bt->d_state) PBSO_CUDA(cudaMalloc(&bt->d_state, sizeof(double) * 4 * n));
+    PBSO_CUDA(cudaMemcpyAsync(bt->d_state, q_km1, sizeof(double) * n, cudaMemcpyHostToDevice, bt->stream));
+    PBSO_CUDA(cudaMemcpyAsync(bt->d_state + n, q_km2, sizeof(double) * n, cudaMemcpyHostToDevice, bt->stream));
+    k_batch_state_to_carrier<<<(unsigned)((n + 255) / 256), 256, 0, bt->stream>>>(n, bt->lneps(), bt->theta(), bt->d_state, bt->d_state + n,
+                                                                                   bt->d_state + 2 * n, bt->d_state + 3 * n);
+    PBSO_CUDA(cudaGetLastError());
+    PBSO_CUDA(cudaStreamSynchronize(bt->stream));                    // the caller may reuse its buffers on return
+    bt->has_state = true;
+    return PBSO_OK;
+}
+
+int pbso_batch_get_end_state(pbso_batch* bt, int buf_size, int n_buffers, double* q_km1, double* q_km2) {
+    PBSO_REQUIRE(bt && q_km1 && q_km2 && buf_size > 0 && n_buffers > 0, PBSO_ERR_INVALID, "bad argument");
+    DeviceGuard g(bt->device);
+    const size_t n = bt->npm();
+    if (!bt->d_ev_off) { if (int rc = pbso_batch_set_impulses(bt, 0, nullptr, nullptr, nullptr)) return rc; }
+    double* d_q; PBSO_CUDA(cudaMalloc(&d_q, sizeof(double) * 2 * n));
+    k_batch_end_state<<<(unsigned)((n + 127) / 128), 128, 0, bt->stream>>>(bt->n_obj, bt->n_modes, (long long)buf_size * n_buffers, buf_size,
+        bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, bt->v0r(), bt->v0i(), d_q, d_q + n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q_km1, d_q, sizeof(double) * n, cudaMemcpyDeviceToHost, bt->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q_km2, d_q + n, sizeof(double) * n, cudaMemcpyDeviceToHost, bt->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(bt->stream);
+    cudaFree(d_q);
+    if (e != cudaSuccess) return set_error(PBSO_ERR_CUDA, "end state failed: %s", cudaGetErrorString(e));
+    return PBSO_OK;
 }
 
 int pbso_batch_sync(pbso_batch* bt) {

@@ -161,7 +161,8 @@ __global__ void k_tc_carrier(int n_obj, int n_modes, int n_it, int tiles_per_buf
                              const double* __restrict__ lneps, const double* __restrict__ theta,
                              const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
                              const int* __restrict__ ev_off, const int* __restrict__ ev_buf,
-                             const double* __restrict__ ev_space, float2* __restrict__ V) {
+                             const double* __restrict__ ev_space, const double* __restrict__ v0r, const double* __restrict__ v0i,
+                             float2* __restrict__ V) {
     const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (idx >= (size_t)n_obj * n_modes) return;
     const int o = (int)(idx / n_modes), m = (int)(idx % n_modes);
@@ -170,6 +171,7 @@ __global__ void k_tc_carrier(int n_obj, int n_modes, int n_it, int tiles_per_buf
     const Cplx Wm = pole_pow64(le, th, (double)(TCB_L * TCB_ROWS));
     const double inji = c3a[g], injr = inji * cota[g];
     Cplx v{0.0, 0.0};
+    if (v0r) v = Cplx{v0r[g], v0i[g]};                       // stateful range render: the state the range starts from
     int e = ev_off[obj0 + o];
     const int e_end = ev_off[obj0 + o + 1];
     for (int it = 0; it < n_it; ++it) {
@@ -643,7 +645,7 @@ struct TcState {
     int tab_obj0 = -1, tab_nobj = 0, batch_obj = 0; // objects [tab_obj0, tab_obj0 + tab_nobj) have tables resident
     size_t npm = 0;
     // cached unit list
-    unsigned ev_ver = ~0u; int list_tiles = -1, list_buf = -1, list_obj0 = -1, list_nobj = -1, n_units = 0;
+    unsigned ev_ver = ~0u; int list_state = -1; int list_tiles = -1, list_buf = -1, list_obj0 = -1, list_nobj = -1, n_units = 0;
     std::vector<Unit> h_units; std::vector<int> h_first;
     std::vector<int> h_ev_obj;
 };
@@ -682,7 +684,7 @@ static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tile
                     const int it = t * PAIR + r;
                     if (it >= n_it) continue;
                     const long long row0 = (long long)it * TCB_ROWS, row1 = row0 + TCB_ROWS;
-                    if (e_begin < e_end && (long long)a.h_ev_buf[e_begin] * tpb < row0) u[r].push_back({(unsigned)((size_t)it * no + o), -1});
+                    if (a.v0r || (e_begin < e_end && (long long)a.h_ev_buf[e_begin] * tpb < row0)) u[r].push_back({(unsigned)((size_t)it * no + o), -1});
                     int& e = cur[o];
                     while (e < e_end && (long long)a.h_ev_buf[e] * tpb < row1) {
                         const long long row = (long long)a.h_ev_buf[e] * tpb;
@@ -776,7 +778,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             st->tab_obj0 = o0; st->tab_nobj = no; ++*launches;
         }
         // unit list (depends on the impulse script, the render length and the batch)
-        const bool relist = st->ev_ver != a.ev_ver || st->list_tiles != n_tiles || st->list_buf != a.buf_size || st->list_obj0 != o0 || st->list_nobj != no;
+        const bool relist = st->ev_ver != a.ev_ver || st->list_state != (a.v0r ? 1 : 0) || st->list_tiles != n_tiles || st->list_buf != a.buf_size || st->list_obj0 != o0 || st->list_nobj != no;
         if (relist) {
             build_units(st, a, o0, no, n_tiles, n_it, tpb);
             if ((size_t)st->n_units > st->unit_cap) {
@@ -791,7 +793,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
                 for (int o = 0; o < a.n_obj; ++o) for (int e = a.h_ev_off[o]; e < a.h_ev_off[o + 1]; ++e) st->h_ev_obj[e] = o;
                 PBSO_CUDA(cudaMemcpyAsync(st->ev_obj, st->h_ev_obj.data(), sizeof(int) * a.n_events, cudaMemcpyHostToDevice, a.stream));
             }
-            st->ev_ver = a.ev_ver; st->list_tiles = n_tiles; st->list_buf = a.buf_size; st->list_obj0 = o0; st->list_nobj = no;
+            st->ev_ver = a.ev_ver; st->list_state = a.v0r ? 1 : 0; st->list_tiles = n_tiles; st->list_buf = a.buf_size; st->list_obj0 = o0; st->list_nobj = no;
         }
         if (st->n_units == 0) continue;                               // silence: the mix is already zeroed
         // state blocks: carrier [n_it][no] | impulses of the batch
@@ -808,7 +810,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
         }
         st->v_nit = n_it; st->v_no = no; st->v_ne = ne;
         k_tc_carrier<<<(unsigned)(((size_t)no * a.n_modes + 255) / 256), 256, 0, a.stream>>>(no, a.n_modes, n_it, tpb, mp, o0, a.lneps, a.theta, a.c3, a.cot,
-                                                                                       a.trans, a.d_ev_off, a.d_ev_buf, a.d_ev_space, st->V);
+                                                                                       a.trans, a.d_ev_off, a.d_ev_buf, a.d_ev_space, a.v0r, a.v0i, st->V);
         PBSO_CUDA(cudaGetLastError());
         ++*launches;
         if (ne > 0) {

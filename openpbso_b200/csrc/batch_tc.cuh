@@ -13,6 +13,7 @@ struct TcArgs {
     const int *d_ev_off, *d_ev_buf; const double* d_ev_space;  // impulse CSR, device
     int n_events;
     unsigned trans_ver, ev_ver;                                // bumped by set_transfer / set_impulses
+    const double *v0r, *v0i;                                   // carrier at sample 0 (stateful range render), or NULL
     double* d_mix;                                             // zeroed by the caller
     cudaStream_t stream;
 };

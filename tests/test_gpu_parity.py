@@ -607,6 +607,88 @@ def test_batch_tc3x_longer_render_after_shorter(pbso):
         assert_waveform_parity(br.render_mix(256, n_buf, pbso.PREC_TC3X), br.render_mix(256, n_buf, pbso.PREC_F64))
 
 
+def test_batch_stateful_ranges(pbso, orc):
+    """Stateful range renders (pbso_batch_set_state / pbso_batch_get_end_state): a script rendered as two ranges with the
+    state handed over equals the one-shot render in every arithmetic; a TransMessage swapped in at the range boundary
+    (modal_solver.h:249-252) is the oracle's own solver loop with enqueue_trans; the end state is the pair the oracle's
+    ModalIntegrator holds after the same steps; and a range can hand over to the per-buffer path (a Gaussian force,
+    forces.h:92-113) and back."""
+    n_obj, n_modes, BUF, n1, n2 = 3, 300, 256, 10, 14
+    w = synth.batch_workload(n_obj, n_modes, n1 + n2, 91, "low_damping")
+    rng = np.random.default_rng(91)
+    obj = np.repeat(np.arange(n_obj), 4)
+    buf = np.concatenate([[1 + o, 7 - o, 10 + o, 19 + o] for o in range(n_obj)])
+    space = rng.standard_normal((len(obj), n_modes))
+    T1 = w["trans"]; T2 = T1 * rng.uniform(0.2, 3.0, T1.shape)
+    br = pbso.BatchRenderer(H, w["a"], w["b"])
+
+    def ranges(prec):
+        br.set_state(None); br.set_transfer(T1)
+        first = buf < n1
+        br.set_impulses(obj[first], buf[first], space[first])
+        y1 = br.render_mix(BUF, n1, prec)
+        st = br.end_state(BUF, n1)
+        br.set_state(*st); br.set_transfer(T2)
+        br.set_impulses(obj[~first], buf[~first] - n1, space[~first])
+        y2 = br.render_mix(BUF, n2, prec)
+        end = br.end_state(BUF, n2)
+        br.set_state(None)
+        return np.concatenate([y1, y2]), st, end
+
+    # the oracle's solver loop, one object at a time, with the transfer swapped by a TransMessage dequeued in step n1
+    want = np.zeros((n1 + n2) * BUF); states_mid = []; states_end = []
+    for o in range(n_obj):
+        integ = orc.Integrator(H, w["a"][o], w["b"][o]); sv = orc.Solver(integ, BUF)
+        assert sv.enqueue_trans(T1[o])
+        ev = {int(b_): space[i] for i, b_ in enumerate(buf) if obj[i] == o}
+        for bi in range(n1 + n2):
+            if bi in ev:
+                assert sv.enqueue_force(ev[bi])
+            if bi == n1:
+                assert sv.enqueue_trans(T2[o])
+                states_mid.append(integ.state())
+            y, _ = sv.step()
+            want[bi * BUF:(bi + 1) * BUF] += y
+        states_end.append(integ.state())
+    scale = np.abs(want).max()
+    for prec, tol in ((pbso.PREC_F64, 1e-11), (pbso.PREC_F32_TILED, 2e-6), (pbso.PREC_TC3X, 2e-6)):
+        got, st, end = ranges(prec)
+        assert np.abs(got - want).max() <= tol * scale, prec
+        for o in range(n_obj):
+            for k in range(2):
+                ref_mid, ref_end = states_mid[o][k], states_end[o][k]
+                assert np.abs(st[k][o] - ref_mid).max() <= 1e-10 * np.abs(ref_mid).max()
+                assert np.abs(end[k][o] - ref_end).max() <= 1e-10 * np.abs(ref_end).max()
+    # hand-over to the per-buffer path and back: impulses (batch range) -> a Gaussian force alive for 4 buffers (per-buffer
+    # path from the batch's end state) -> free decay (batch range from the integrator's state), against the oracle's solver
+    o = 1
+    integ = orc.Integrator(H, w["a"][o], w["b"][o]); sv = orc.Solver(integ, BUF)
+    assert sv.enqueue_trans(T1[o])
+    ev = {int(b_): space[i] for i, b_ in enumerate(buf) if obj[i] == o and b_ < n1}
+    g_space = rng.standard_normal(n_modes); want = []
+    for bi in range(n1 + 4 + 6):
+        if bi in ev:
+            assert sv.enqueue_force(ev[bi])
+        if bi == n1:
+            assert sv.enqueue_force(g_space, orc.GAUSSIAN, 2000.0)
+        want.append(sv.step()[0])
+    want = np.concatenate(want)
+    b1 = pbso.BatchRenderer(H, w["a"][o:o + 1], w["b"][o:o + 1]); b1.set_transfer(T1[o:o + 1])
+    sel = (obj == o) & (buf < n1)
+    b1.set_impulses(np.zeros(sel.sum(), dtype=np.int32), buf[sel], space[sel])
+    got = [b1.render_mix(BUF, n1, pbso.PREC_TC3X)]
+    q1, q2 = b1.end_state(BUF, n1)
+    it = pbso.ModalIntegrator(n_modes, H, w["a"][o], w["b"][o]); it.set_state(q1[0], q2[0]); it.set_transfer(T1[o][None, :])
+    prof, alive = orc.force_profile(orc.GAUSSIAN, 2000.0, BUF, 5)
+    assert list(alive) == [1, 1, 1, 1, 0]
+    for k in range(4):
+        got.append(it.render_buffer(g_space, prof[k])[0][0])
+    b1.set_state(*[x[None, :] for x in it.get_state()]); b1.set_impulses([], [], np.zeros((0, n_modes)))
+    got.append(b1.render_mix(BUF, 6, pbso.PREC_TC3X))
+    got = np.concatenate(got)
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
 def test_batch_tc3x_object_batches(pbso, monkeypatch):
     """Operand tables larger than the table budget: the renderer walks the objects in batches and rebuilds the tables per
     batch; same waveform as the FP64 kernel."""
