@@ -553,10 +553,10 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
         else return set_error(PBSO_ERR_UNSUPPORTED, "PBSO_PREC_F32_TILED needs buf_size in {64,128,256}; got %d (use PBSO_PREC_F64)", buf_size);
 #undef PBSO_LAUNCH_POW
     } else if (precision == PBSO_PREC_TC3X) {
-        PBSO_REQUIRE(d_mix && !d_stems, PBSO_ERR_UNSUPPORTED, "PBSO_PREC_TC3X renders the mix only");
+
         TcArgs ta{bt->n_obj, bt->n_modes, buf_size, n_buffers, bt->sm_count, bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->trans(),
                   bt->h_ev_off.data(), bt->h_ev_buf.data(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, bt->n_events,
-                  bt->trans_ver, bt->ev_ver, bt->v0r(), bt->v0i(), d_mix, bt->stream};
+                  bt->trans_ver, bt->ev_ver, bt->v0r(), bt->v0i(), d_mix, d_stems, bt->stream};
         int nl = 0;
         if (int rc = tc_render(&bt->tc, ta, &nl)) return rc;
         PBSO_CUDA(cudaEventRecord(bt->e1, bt->stream));

@@ -12,21 +12,25 @@
 // [3446 x 128] output contracted over K = 4096*512*2 = 4.2 M, run by tcgen05.mma kind::tf32 with accumulators in
 // TMEM.
 //
-// Round-2 structure (profiles/r2_k_batch_tc_ablation.md: round 1 was latency-bound on its own five-role pipeline):
-//  * Operand B depends on the object only, not on time or on the impulse script: it is PRECOMPUTED once per
-//    handle (k_tc_btiles: FP64 pole powers, split into TF32 hi / lo, stored as ready-made UMMA tiles -- K-major,
-//    128-byte swizzle) and streamed into shared memory with bulk copies.  A CTA PAIR (cluster of 2) renders two
-//    M-tiles (128 time tiles each) of the SAME object and shares the stream: each CTA fetches half of every
-//    32 KB tile pair and multicasts it to both (cp.async.bulk ... .multicast::cluster), so L2 -> SM traffic is
-//    16 KB per 16-mode K chunk and CTA.  Work items are (window of 8 objects, M-tile pair), dealt round-robin to
-//    the clusters, so the 14 clusters rendering the 14 M-tile pairs of one object window read the same tiles
-//    at about the same time: HBM sees every tile about once per render (4.3 GB for cfg5), L2 serves the rest.
+// Round-2 structure (profiles/r2_k_batch_tc.md; round 1 was latency-bound on its own five-role pipeline):
+//  * CTA PAIRS (cluster of 2, tcgen05.mma cta_group::2, M = 256): the pair renders two M-tiles (128 time tiles each) of
+//    the SAME object.  Operand B depends on the object only, so each CTA generates HALF of it (64 of the 128 rows of
+//    every K chunk: pole powers from table factors by FP32 complex products, split into TF32 hi / lo, stored as UMMA
+//    tiles -- K-major, 128-byte swizzle) and the tensor cores of both SMs read the two halves: B generation, its
+//    shared-memory stores and the UMMA operand fetches per output halve.  The leader CTA issues the MMAs for both;
+//    generators of both CTAs arrive on the leader's barriers through plain (CTA-scope) remote arrives -- the
+//    .release.cluster / .acquire.cluster forms compile to GPU-scope fences and L1 invalidations and cost 30 %.
+//    (Streaming precomputed B tiles from L2 with multicast bulk copies was built and measured first: correct, but
+//    no faster than generating -- the per-SM ingest of bulk copies (~35 B/clk) and L2 bandwidth bound it.)
+//    Work items are (window of 8 objects, M-tile pair), dealt round-robin to the clusters, so the clusters rendering
+//    the M-tile pairs of one object window read the same 5.4 KB table blocks at about the same time: HBM sees every
+//    block about once per render (1.2 GB for cfg5 in total), L2 serves the rest.
 //  * Operand A (tile-start states) is generated on the SM straight into TMEM (tcgen05.st, MMA in TS mode):
 //    A[row] = X[blk] * R[j] (row = 16 blk + j), X[blk] = v W^(16 blk) from a seed warp, R[j] = W^j, W = w^L, all
 //    FP32 complex products (fma.rn.f32x2) of table factors computed in FP64 and rounded once (k_tc_tabs); v comes
 //    from the FP64 carrier pass (k_tc_carrier, per render; impulses injected in FP64, transfer folded in).
-//    Everything a chunk needs -- 3 KB of table, 128 B of states -- rides the same bulk-copy ring as B: no role
-//    ever waits on a global load.
+//    Everything a chunk needs -- 5.4 KB of table, 128 B of states -- arrives through a ring of bulk copies
+//    (cp.async.bulk + mbarrier) requested eight chunks ahead: no role ever waits on a global load.
 //  * "3xTF32": every FP32 element x is split x = hi + lo (the tensor core ignores the low 13 mantissa bits itself,
 //    so the raw x is the hi operand; lo = x - trunc(x) rounded to nearest TF32); hi*lo + lo*hi + hi*hi.  The tensor
 //    core truncates when it adds into its FP32 accumulator, so accumulation is two-level: chains of two K chunks
@@ -256,7 +260,7 @@ template <int PAIR>
 __global__ void __launch_bounds__(TCB_THREADS, 1)
 k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Unit* __restrict__ units,
            const uint8_t* __restrict__ tab, const float2* __restrict__ V, int obj0,
-           double* __restrict__ mix, double inv_gain, int ablate, unsigned long long* __restrict__ prof) {
+           double* __restrict__ mix, float* __restrict__ stems, double inv_gain, int ablate, unsigned long long* __restrict__ prof) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* tabs = smem + TCB_NB * TCB_BT_BYTES;
@@ -268,9 +272,7 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
     uint64_t* t_empty = t_full + TCB_NT;           // [NT] consumed (seed warp + 4 A-generator + 4 B-generator warps)
     uint64_t* s_full = t_empty + TCB_NT;           // [NS] seeds written (seed warp)
     uint64_t* s_empty = s_full + TCB_NS;           // [NS] consumed (4 A-generator warps)
-    uint64_t* a_full = s_empty + TCB_NS;           // [NA] A stage stored to TMEM (4 generator warps)
-    uint64_t* a_empty = a_full + TCB_NA;           // [NA] MMAs reading it retired
-    uint64_t* acc_full = a_empty + TCB_NA;         // [2]  chain's MMAs finished
+    uint64_t* acc_full = s_empty + TCB_NS;         // [2]  chain's MMAs finished
     uint64_t* acc_empty = acc_full + 2;            // [2]  drained (4 epilogue warps)
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
@@ -293,7 +295,6 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
         for (int s = 0; s < TCB_NB; ++s) { mbar_init(&b_full[s], 8 * PAIR); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < TCB_NT; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 9); }
         for (int s = 0; s < TCB_NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
-        for (int s = 0; s < TCB_NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4 * PAIR); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -458,22 +459,8 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
                 PBSO_TW(0, mbar_wait(&acc_full[buf], (g >> 1) & 1));
                 tcgen05_fence_after();
                 if (!(ablate & 4)) {
-                    if (true) {
 #pragma unroll
-                        for (int qd = 0; qd < TCB_L / 32; ++qd) tmem_ld_add_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), &acc[qd * 16]);
-                    } else {
-#pragma unroll
-                        for (int qd = 0; qd < TCB_L / 32; ++qd) {
-                            uint32_t vm[32];
-                            tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), vm);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float a, b; upk(acc[qd * 16 + j], a, b);
-                                acc[qd * 16 + j] = pk(a + __uint_as_float(vm[2 * j]), b + __uint_as_float(vm[2 * j + 1]));
-                            }
-                        }
-                    }
+                    for (int qd = 0; qd < TCB_L / 32; ++qd) tmem_ld_add_32x32(tmem_base + lane_off + (uint32_t)(buf * TCB_L + qd * 32), &acc[qd * 16]);
                 }
                 tcgen05_fence_before();
                 __syncwarp();
@@ -482,13 +469,23 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
             const Unit un = units[u];
             if (un.flush) {
                 const long long tile = ((long long)un.it * PAIR + rank) * TCB_ROWS + row;
-                if (tile < n_tiles) {
+                if (tile < n_tiles && mix) {
                     double* dst = mix + tile * TCB_L;
 #pragma unroll
                     for (int j = 0; j < TCB_L / 2; ++j) {
                         float a, b; upk(acc[j], a, b);
                         atomicAdd(dst + 2 * j, (double)a * inv_gain);
                         atomicAdd(dst + 2 * j + 1, (double)b * inv_gain);
+                    }
+                }
+                if (tile < n_tiles && stems) {                       // per-object stems: the host flushes at every object change
+                    float* dst = stems + ((size_t)un.obj * n_tiles + tile) * TCB_L;
+                    const float ig = (float)inv_gain;
+#pragma unroll
+                    for (int j = 0; j < TCB_L / 2; ++j) {
+                        float a, b; upk(acc[j], a, b);
+                        atomicAdd(dst + 2 * j, a * ig);
+                        atomicAdd(dst + 2 * j + 1, b * ig);
                     }
                 }
 #pragma unroll
@@ -706,7 +703,12 @@ static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tile
             if (tmp.empty()) continue;
             std::vector<Unit>& out = per[item++ % ncl];
             int since = 0;
-            for (Unit& un : tmp) { un.flush = (short)(++since >= flush_units); if (un.flush) since = 0; out.push_back(un); }
+            for (size_t i = 0; i < tmp.size(); ++i) {
+                Unit& un = tmp[i];
+                un.flush = (short)(++since >= flush_units || (a.d_stems && i + 1 < tmp.size() && tmp[i + 1].obj != un.obj));   // stems: at every object change
+                if (un.flush) since = 0;
+                out.push_back(un);
+            }
             out.back().flush = 1;                                    // the M-tiles change with the item
         }
     }
@@ -778,7 +780,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             st->tab_obj0 = o0; st->tab_nobj = no; ++*launches;
         }
         // unit list (depends on the impulse script, the render length and the batch)
-        const bool relist = st->ev_ver != a.ev_ver || st->list_state != (a.v0r ? 1 : 0) || st->list_tiles != n_tiles || st->list_buf != a.buf_size || st->list_obj0 != o0 || st->list_nobj != no;
+        const bool relist = st->ev_ver != a.ev_ver || st->list_state != (a.v0r ? 1 : 0) + (a.d_stems ? 2 : 0) || st->list_tiles != n_tiles || st->list_buf != a.buf_size || st->list_obj0 != o0 || st->list_nobj != no;
         if (relist) {
             build_units(st, a, o0, no, n_tiles, n_it, tpb);
             if ((size_t)st->n_units > st->unit_cap) {
@@ -793,7 +795,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
                 for (int o = 0; o < a.n_obj; ++o) for (int e = a.h_ev_off[o]; e < a.h_ev_off[o + 1]; ++e) st->h_ev_obj[e] = o;
                 PBSO_CUDA(cudaMemcpyAsync(st->ev_obj, st->h_ev_obj.data(), sizeof(int) * a.n_events, cudaMemcpyHostToDevice, a.stream));
             }
-            st->ev_ver = a.ev_ver; st->list_state = a.v0r ? 1 : 0; st->list_tiles = n_tiles; st->list_buf = a.buf_size; st->list_obj0 = o0; st->list_nobj = no;
+            st->ev_ver = a.ev_ver; st->list_state = (a.v0r ? 1 : 0) + (a.d_stems ? 2 : 0); st->list_tiles = n_tiles; st->list_buf = a.buf_size; st->list_obj0 = o0; st->list_nobj = no;
         }
         if (st->n_units == 0) continue;                               // silence: the mix is already zeroed
         // state blocks: carrier [n_it][no] | impulses of the batch
@@ -830,10 +832,10 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             cfg.attrs = at; cfg.numAttrs = 1;
             if (st->pair == 2)
                 PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<2>, a.n_modes, n_tiles, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
-                                             (const float2*)st->V, o0, a.d_mix, inv_gain, ablate, d_prof));
+                                             (const float2*)st->V, o0, a.d_mix, a.d_stems, inv_gain, ablate, d_prof));
             else
                 PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<1>, a.n_modes, n_tiles, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
-                                             (const float2*)st->V, o0, a.d_mix, inv_gain, ablate, d_prof));
+                                             (const float2*)st->V, o0, a.d_mix, a.d_stems, inv_gain, ablate, d_prof));
         }
         if (d_prof) {
             unsigned long long h[24 * 8];

@@ -14,7 +14,8 @@ struct TcArgs {
     int n_events;
     unsigned trans_ver, ev_ver;                                // bumped by set_transfer / set_impulses
     const double *v0r, *v0i;                                   // carrier at sample 0 (stateful range render), or NULL
-    double* d_mix;                                             // zeroed by the caller
+    double* d_mix;                                             // zeroed by the caller (or NULL)
+    float* d_stems;                                            // [n_obj][n_buffers*buf_size], zeroed by the caller (or NULL)
     cudaStream_t stream;
 };
 

@@ -458,12 +458,22 @@ def test_batch_multiple_events_and_stems(pbso, orc):
             for e in np.nonzero((obj == o) & (buf == bi))[0]:
                 s.enqueue_force(space[e])
             ref[bi * 256:(bi + 1) * 256] += s.step()[0]
-    for prec, tol in ((pbso.PREC_F64, 1e-10), (pbso.PREC_F32_TILED, None)):
+    per_obj = np.zeros((n_obj, n_buf * 256))
+    for o in range(n_obj):
+        s = orc.Solver(orc.Integrator(H, w["a"][o], w["b"][o]), 256)
+        s.enqueue_trans(w["trans"][o])
+        for bi in range(n_buf):
+            for e in np.nonzero((obj == o) & (buf == bi))[0]:
+                s.enqueue_force(space[e])
+            per_obj[o, bi * 256:(bi + 1) * 256] = s.step()[0]
+    for prec, tol in ((pbso.PREC_F64, 1e-10), (pbso.PREC_F32_TILED, None), (pbso.PREC_TC3X, None)):
         mix = br.render_mix(256, n_buf, prec)
         if tol: assert_waveform_parity(mix, ref, rel=tol, mx=tol)
         else: assert_waveform_parity(mix, ref)
         stems = br.render_stems(256, n_buf, prec)
         assert_waveform_parity(stems.astype(np.float64).sum(0), ref, rel=1e-5, mx=2e-6)
+        for o in range(n_obj):                               # every stem is its own object's solver loop (float32 storage)
+            assert np.abs(stems[o] - per_obj[o]).max() <= 3e-6 * np.abs(per_obj).max(), (prec, o)
     with pytest.raises(pbso.PbsoError):                      # one message per object per buffer (modal_solver.h:184)
         br.set_impulses([0, 0], [3, 3], space[:2])
     with pytest.raises(pbso.PbsoError):
