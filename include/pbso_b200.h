@@ -44,7 +44,7 @@ enum {
 #define PBSO_PREC_F64 0        /* FP64: the reference's arithmetic */
 #define PBSO_PREC_F32_TILED 1  /* batch renderer: FP32 pole-power tiles evaluated from an FP64 carrier */
 #define PBSO_PREC_TF32X3 2     /* batched projection: tcgen05 tensor cores, 3xTF32 split, FP32 accumulate */
-#define PBSO_PREC_TC3X 3       /* batch renderer: pole-power synthesis as one tcgen05 3xTF32 contraction (buf_size % 128 == 0) */
+#define PBSO_PREC_TC3X 3       /* batch renderer: pole-power synthesis as one tcgen05 3xTF32 contraction (any buf_size, 513 included) */
 
 typedef struct pbso_integrator pbso_integrator;  /* ModalIntegrator<double> + per-buffer renderer */
 typedef struct pbso_ffat pbso_ffat;              /* std::map<int, FFAT_Map<double,3>> */

@@ -210,6 +210,72 @@ k_batch_f64(int n_modes, int slabs, int BUF, int n_buf,
     }
 }
 
+// The "scalar tail" of the tensor-core path when buf_size is not a multiple of its 128-sample tiles (the reference's
+// default FRAMES_PER_BUFFER is 513): an impulse then lands inside a tile, and its samples up to the next tile boundary --
+// at most 127 -- are rendered here with the reference recurrence, one thread per mode, CTA = (event, slab of 256 modes);
+// from the boundary on the impulse is part of the contraction (k_tc_impulse carries its state there).
+__global__ void __launch_bounds__(BF_TPB)
+k_batch_event_heads(int n_modes, int slabs, int BUF, long long n_samples, int e0,
+                    const double* __restrict__ c1a, const double* __restrict__ c2a, const double* __restrict__ c3a,
+                    const double* __restrict__ trans, const int* __restrict__ ev_obj, const int* __restrict__ ev_buf,
+                    const double* __restrict__ ev_space, double* __restrict__ mix, float* __restrict__ stems) {
+    __shared__ double s_part[BF_TPB / 32][32];
+    const int e = e0 + blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    const long long t_e = (long long)ev_buf[e] * BUF;
+    const int s0 = (int)(t_e % 128);
+    if (s0 == 0 || t_e >= n_samples) return;
+    const int len = (int)min((long long)(128 - s0), n_samples - t_e);
+    const int obj = ev_obj[e];
+    const int m = slab * BF_TPB + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = m < n_modes;
+    const size_t pm = (size_t)obj * n_modes + (live ? m : 0);
+    const double c1 = live ? c1a[pm] : 0.0, c2 = live ? c2a[pm] : 0.0, c3 = live ? c3a[pm] : 0.0, T = live ? trans[pm] : 0.0;
+    const double Q0 = live ? ev_space[(size_t)e * n_modes + m] : 0.0;
+    double q1 = 0.0, q2 = 0.0;
+    for (int t0 = 0; t0 < len; t0 += 32) {
+        double v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            double qk = 0.0;
+            if (t0 + j < len) {
+                qk = c1 * q1 + c2 * q2 + c3 * ((t0 + j == 0) ? Q0 : 0.0);       // modal_integrator.h:109-110
+                q2 = q1; q1 = qk;
+            }
+            v[j] = T * qk;
+        }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const bool up = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+                const double keep = up ? v[i + s] : v[i];
+                const double send = up ? v[i] : v[i + s];
+                v[i] = keep + bshfl_xor_f64(send, s);
+            }
+        }
+        s_part[warp][lane] = v[0];
+        __syncthreads();
+        if (threadIdx.x < 32 && t0 + threadIdx.x < len) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < BF_TPB / 32; ++w) s += s_part[w][threadIdx.x];
+            const long long i = t_e + t0 + threadIdx.x;
+            if (mix) atomicAdd(&mix[i], s);
+            if (stems) atomicAdd(&stems[(size_t)obj * n_samples + i], (float)s);
+        }
+        __syncthreads();
+    }
+}
+
+int pbso::batch_event_heads(const TcArgs& a, int e0, int ne, const int* d_ev_obj) {
+    const int slabs = div_up(a.n_modes, BF_TPB);
+    k_batch_event_heads<<<ne * slabs, BF_TPB, 0, a.stream>>>(a.n_modes, slabs, a.buf_size, (long long)a.buf_size * a.n_buffers, e0, a.c1, a.c2, a.c3,
+                                                             a.trans, d_ev_obj, a.d_ev_buf, a.d_ev_space, a.d_mix, a.d_stems);
+    PBSO_CUDA(cudaGetLastError());
+    return PBSO_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fast path: pole-power tiles.  CTA = (object, slab of 256 modes), 16 warps x 16 modes.
 // ---------------------------------------------------------------------------------------------
@@ -554,7 +620,7 @@ static int launch_render(pbso_batch* bt, int buf_size, int n_buffers, int precis
 #undef PBSO_LAUNCH_POW
     } else if (precision == PBSO_PREC_TC3X) {
 
-        TcArgs ta{bt->n_obj, bt->n_modes, buf_size, n_buffers, bt->sm_count, bt->lneps(), bt->theta(), bt->c3(), bt->cot(), bt->trans(),
+        TcArgs ta{bt->n_obj, bt->n_modes, buf_size, n_buffers, bt->sm_count, bt->lneps(), bt->theta(), bt->c1(), bt->c2(), bt->c3(), bt->cot(), bt->trans(),
                   bt->h_ev_off.data(), bt->h_ev_buf.data(), bt->d_ev_off, bt->d_ev_buf, bt->d_ev_space, bt->n_events,
                   bt->trans_ver, bt->ev_ver, bt->v0r(), bt->v0i(), d_mix, d_stems, bt->stream};
         int nl = 0;

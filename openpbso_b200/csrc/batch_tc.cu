@@ -161,7 +161,7 @@ __global__ void k_tc_tabs(int n_obj, int n_modes, int cpu, int obj0, const doubl
 // ---- FP64 carrier: T * state of every (object, mode) at the start of every M-tile -----------------------------
 // V[it] excludes impulses landing at rows >= it*128 (those are impulse units of M-tile it).  Layout: blocks of mp
 // float2 (mp = modes padded to whole chunks; pad entries stay zero), block it * n_obj + o.
-__global__ void k_tc_carrier(int n_obj, int n_modes, int n_it, int tiles_per_buf, int mp, int obj0,
+__global__ void k_tc_carrier(int n_obj, int n_modes, int n_it, int buf_size, int mp, int obj0,
                              const double* __restrict__ lneps, const double* __restrict__ theta,
                              const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
                              const int* __restrict__ ev_off, const int* __restrict__ ev_buf,
@@ -183,9 +183,10 @@ __global__ void k_tc_carrier(int n_obj, int n_modes, int n_it, int tiles_per_buf
         v = cmul(v, Wm);
         const long long row_end = (long long)(it + 1) * TCB_ROWS;
         while (e < e_end) {
-            const long long row = (long long)ev_buf[e] * tiles_per_buf;
+            const long long t_e = (long long)ev_buf[e] * buf_size;           // the impulse's sample; it joins the tensor-core
+            const long long row = (t_e + TCB_L - 1) / TCB_L;                  // path at the next tile boundary (row)
             if (row >= row_end) break;
-            const Cplx z = pole_pow64(le, th, (double)(row_end - row) * TCB_L);   // from the impulse to the next M-tile start
+            const Cplx z = pole_pow64(le, th, (double)(row_end * TCB_L - t_e));   // from the impulse to the next M-tile start
             const double sp = ev_space[(size_t)e * n_modes + m];
             v.x += sp * (injr * z.x - inji * z.y);
             v.y += sp * (injr * z.y + inji * z.x);
@@ -194,7 +195,10 @@ __global__ void k_tc_carrier(int n_obj, int n_modes, int n_it, int tiles_per_buf
     }
 }
 // state injected by impulse e (forces.h:87, sample 0 of its buffer): T * space * c3 (cot theta + i); block vimp0 + e
-__global__ void k_tc_impulse(int n_modes, int mp, int e0, int n_ev, const int* __restrict__ ev_obj,
+// An impulse that does not land on a tile boundary (buf_size not a multiple of 128) is carried to the next boundary by
+// the exact pole power w^(boundary - t_e); the samples in between are k_batch_event_heads' (batch.cu).
+__global__ void k_tc_impulse(int n_modes, int mp, int e0, int n_ev, int buf_size, const int* __restrict__ ev_obj, const int* __restrict__ ev_buf,
+                             const double* __restrict__ lneps, const double* __restrict__ theta,
                              const double* __restrict__ c3a, const double* __restrict__ cota, const double* __restrict__ trans,
                              const double* __restrict__ ev_space, float2* __restrict__ Vimp) {
     const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -202,7 +206,11 @@ __global__ void k_tc_impulse(int n_modes, int mp, int e0, int n_ev, const int* _
     const int e = (int)(idx / n_modes), m = (int)(idx % n_modes);
     const size_t g = (size_t)ev_obj[e0 + e] * n_modes + m;
     const double sp = ev_space[(size_t)(e0 + e) * n_modes + m] * trans[g], inji = c3a[g];
-    Vimp[(size_t)e * mp + m] = make_float2((float)(sp * inji * cota[g]), (float)(sp * inji));
+    Cplx v{sp * inji * cota[g], sp * inji};
+    const long long t_e = (long long)ev_buf[e0 + e] * buf_size;
+    const int ahead = (int)((TCB_L - t_e % TCB_L) % TCB_L);
+    if (ahead) v = cmul(v, pole_pow64(lneps[g], theta[g], (double)ahead));
+    Vimp[(size_t)e * mp + m] = make_float2((float)v.x, (float)v.y);
 }
 
 // ---- device helpers of the main kernel ----------------------------------------------------------------------
@@ -258,7 +266,7 @@ __device__ __forceinline__ void tmem_ld_add_32x32(uint32_t taddr, c32* acc) {
 // CTA generates only HALF of operand B (64 of its 128 rows) -- the tensor cores fetch the other half from the peer.
 template <int PAIR>
 __global__ void __launch_bounds__(TCB_THREADS, 1)
-k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Unit* __restrict__ units,
+k_batch_tc(int n_modes, int n_tiles, long long n_samples, const int* __restrict__ cta_first, const Unit* __restrict__ units,
            const uint8_t* __restrict__ tab, const float2* __restrict__ V, int obj0,
            double* __restrict__ mix, float* __restrict__ stems, double inv_gain, int ablate, unsigned long long* __restrict__ prof) {
     extern __shared__ uint8_t smem_raw[];
@@ -469,23 +477,25 @@ k_batch_tc(int n_modes, int n_tiles, const int* __restrict__ cta_first, const Un
             const Unit un = units[u];
             if (un.flush) {
                 const long long tile = ((long long)un.it * PAIR + rank) * TCB_ROWS + row;
-                if (tile < n_tiles && mix) {
+                // the last tile of a render whose length is not a multiple of 128 is cut at n_samples
+                const int lim = tile < n_tiles ? (int)min((long long)TCB_L, n_samples - tile * TCB_L) : 0;
+                if (lim > 0 && mix) {
                     double* dst = mix + tile * TCB_L;
 #pragma unroll
                     for (int j = 0; j < TCB_L / 2; ++j) {
                         float a, b; upk(acc[j], a, b);
-                        atomicAdd(dst + 2 * j, (double)a * inv_gain);
-                        atomicAdd(dst + 2 * j + 1, (double)b * inv_gain);
+                        if (2 * j < lim) atomicAdd(dst + 2 * j, (double)a * inv_gain);
+                        if (2 * j + 1 < lim) atomicAdd(dst + 2 * j + 1, (double)b * inv_gain);
                     }
                 }
-                if (tile < n_tiles && stems) {                       // per-object stems: the host flushes at every object change
-                    float* dst = stems + ((size_t)un.obj * n_tiles + tile) * TCB_L;
+                if (lim > 0 && stems) {                              // per-object stems: the host flushes at every object change
+                    float* dst = stems + (size_t)un.obj * n_samples + tile * TCB_L;
                     const float ig = (float)inv_gain;
 #pragma unroll
                     for (int j = 0; j < TCB_L / 2; ++j) {
                         float a, b; upk(acc[j], a, b);
-                        atomicAdd(dst + 2 * j, a * ig);
-                        atomicAdd(dst + 2 * j + 1, b * ig);
+                        if (2 * j < lim) atomicAdd(dst + 2 * j, a * ig);
+                        if (2 * j + 1 < lim) atomicAdd(dst + 2 * j + 1, b * ig);
                     }
                 }
 #pragma unroll
@@ -657,7 +667,9 @@ void tc_free(TcState* st) {
 // round-robin to the CTAs (clusters) in (window, M-tile) order -- the CTAs rendering the M-tiles of one window run at about the same time, so a
 // window's table blocks are read from HBM once and from L2 by the rest; a CTA keeps one M-tile's partial mix in
 // registers across the units of an item.
-static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tiles, int n_it, int tpb) {
+static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tiles, int n_it) {
+    // an impulse joins the contraction at the first tile boundary at or after its sample (row = ceil(t_e / 128))
+    auto ev_row = [&](int e) { return ((long long)a.h_ev_buf[e] * a.buf_size + TCB_L - 1) / TCB_L; };
     const int PAIR = st->pair, ncl = st->grid / PAIR, n_grp = div_up(n_it, PAIR);
     const unsigned imp_blk0 = (unsigned)((size_t)n_it * no);
     const int e_base = a.h_ev_off[o0];
@@ -681,10 +693,10 @@ static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tile
                     const int it = t * PAIR + r;
                     if (it >= n_it) continue;
                     const long long row0 = (long long)it * TCB_ROWS, row1 = row0 + TCB_ROWS;
-                    if (a.v0r || (e_begin < e_end && (long long)a.h_ev_buf[e_begin] * tpb < row0)) u[r].push_back({(unsigned)((size_t)it * no + o), -1});
+                    if (a.v0r || (e_begin < e_end && ev_row(e_begin) < row0)) u[r].push_back({(unsigned)((size_t)it * no + o), -1});
                     int& e = cur[o];
-                    while (e < e_end && (long long)a.h_ev_buf[e] * tpb < row1) {
-                        const long long row = (long long)a.h_ev_buf[e] * tpb;
+                    while (e < e_end && ev_row(e) < row1) {
+                        const long long row = ev_row(e);
                         if (row >= row0 && row < n_tiles) u[r].push_back({imp_blk0 + (unsigned)(e - e_base), (int)(row - row0)});
                         ++e;
                     }
@@ -727,7 +739,6 @@ static bool g_calibrating = false;
 static int tc_calibrate(int device, int sm_count);
 
 int tc_render(TcState** pst, const TcArgs& a, int* launches) {
-    PBSO_REQUIRE(a.buf_size % TCB_L == 0, PBSO_ERR_UNSUPPORTED, "PBSO_PREC_TC3X needs buf_size to be a multiple of 128");
     if (!*pst) *pst = new TcState();
     TcState* st = *pst;
     *launches = 0;
@@ -737,9 +748,8 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     const size_t npm = (size_t)a.n_obj * a.n_modes;
     const int cpu = div_up(a.n_modes, TCB_KMODES), mp = cpu * TCB_KMODES;
     const long long n_samples = (long long)a.buf_size * a.n_buffers;
-    const int n_tiles = (int)(n_samples / TCB_L);
+    const int n_tiles = (int)((n_samples + TCB_L - 1) / TCB_L);       // 128-sample tiles; the last one may be cut
     const int n_it = div_up(n_tiles, TCB_ROWS);
-    const int tpb = a.buf_size / TCB_L;                               // tiles per buffer
     static const int force_pair = getenv("PBSO_TC_PAIR") ? atoi(getenv("PBSO_TC_PAIR")) : 0;
     st->pair = (force_pair == 1 || a.sm_count < 2) ? 1 : 2;
     st->grid = std::max(st->pair, a.sm_count / st->pair * st->pair);
@@ -782,7 +792,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
         // unit list (depends on the impulse script, the render length and the batch)
         const bool relist = st->ev_ver != a.ev_ver || st->list_state != (a.v0r ? 1 : 0) + (a.d_stems ? 2 : 0) || st->list_tiles != n_tiles || st->list_buf != a.buf_size || st->list_obj0 != o0 || st->list_nobj != no;
         if (relist) {
-            build_units(st, a, o0, no, n_tiles, n_it, tpb);
+            build_units(st, a, o0, no, n_tiles, n_it);
             if ((size_t)st->n_units > st->unit_cap) {
                 cudaFree(st->units); st->units = nullptr; st->unit_cap = 0;
                 PBSO_CUDA(cudaMalloc(&st->units, sizeof(Unit) * st->n_units)); st->unit_cap = st->n_units;
@@ -811,15 +821,19 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             else PBSO_CUDA(cudaMemsetAsync(st->V + (vneed - mp), 0, sizeof(float2) * mp, a.stream));          // the zero block
         }
         st->v_nit = n_it; st->v_no = no; st->v_ne = ne;
-        k_tc_carrier<<<(unsigned)(((size_t)no * a.n_modes + 255) / 256), 256, 0, a.stream>>>(no, a.n_modes, n_it, tpb, mp, o0, a.lneps, a.theta, a.c3, a.cot,
+        k_tc_carrier<<<(unsigned)(((size_t)no * a.n_modes + 255) / 256), 256, 0, a.stream>>>(no, a.n_modes, n_it, a.buf_size, mp, o0, a.lneps, a.theta, a.c3, a.cot,
                                                                                        a.trans, a.d_ev_off, a.d_ev_buf, a.d_ev_space, a.v0r, a.v0i, st->V);
         PBSO_CUDA(cudaGetLastError());
         ++*launches;
         if (ne > 0) {
-            k_tc_impulse<<<(unsigned)(((size_t)ne * a.n_modes + 255) / 256), 256, 0, a.stream>>>(a.n_modes, mp, e0, ne, st->ev_obj, a.c3, a.cot, a.trans,
+            k_tc_impulse<<<(unsigned)(((size_t)ne * a.n_modes + 255) / 256), 256, 0, a.stream>>>(a.n_modes, mp, e0, ne, a.buf_size, st->ev_obj, a.d_ev_buf, a.lneps, a.theta, a.c3, a.cot, a.trans,
                                                                                               a.d_ev_space, st->V + (size_t)n_it * no * mp);
             PBSO_CUDA(cudaGetLastError());
             ++*launches;
+            if (a.buf_size % TCB_L != 0) {                            // impulses inside a tile: their samples up to the next boundary
+                if (int rc = batch_event_heads(a, e0, ne, st->ev_obj)) return rc;
+                ++*launches;
+            }
         }
         static const bool want_prof = getenv("PBSO_TC_PROF") != nullptr;
         unsigned long long* d_prof = nullptr;
@@ -831,10 +845,10 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = st->pair; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             if (st->pair == 2)
-                PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<2>, a.n_modes, n_tiles, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
+                PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<2>, a.n_modes, n_tiles, n_samples, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
                                              (const float2*)st->V, o0, a.d_mix, a.d_stems, inv_gain, ablate, d_prof));
             else
-                PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<1>, a.n_modes, n_tiles, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
+                PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<1>, a.n_modes, n_tiles, n_samples, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
                                              (const float2*)st->V, o0, a.d_mix, a.d_stems, inv_gain, ablate, d_prof));
         }
         if (d_prof) {

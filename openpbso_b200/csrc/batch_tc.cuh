@@ -8,7 +8,7 @@ struct TcState;      // device tables / unit list cached across renders, owned b
 
 struct TcArgs {
     int n_obj, n_modes, buf_size, n_buffers, sm_count;
-    const double *lneps, *theta, *c3, *cot, *trans;            // [n_obj][n_modes], device
+    const double *lneps, *theta, *c1, *c2, *c3, *cot, *trans;  // [n_obj][n_modes], device
     const int *h_ev_off, *h_ev_buf;                            // impulse CSR, host copy
     const int *d_ev_off, *d_ev_buf; const double* d_ev_space;  // impulse CSR, device
     int n_events;
@@ -20,6 +20,8 @@ struct TcArgs {
 };
 
 int tc_render(TcState** st, const TcArgs& a, int* launches);
+// batch.cu: FP64 direct-form samples of events [e0, e0 + ne) from their impulse to the next 128-sample boundary
+int batch_event_heads(const TcArgs& a, int e0, int ne, const int* d_ev_obj);
 void tc_free(TcState* st);
 double tc_gain(int device);   // calibrated accumulate-truncation gain of the tensor-core path (0 = not calibrated yet)
 

@@ -571,8 +571,8 @@ def test_batch_tc3x_many_events(pbso):
     br.set_impulses(obj[::3], buf[::3], space[::3]); br.set_transfer(2.0 * w["trans"])
     assert_waveform_parity(br.render_mix(256, n_buf, pbso.PREC_TC3X), br.render_mix(256, n_buf, pbso.PREC_F64))
     assert_waveform_parity(br.render_mix(128, 2 * n_buf - 3, pbso.PREC_TC3X), br.render_mix(128, 2 * n_buf - 3, pbso.PREC_F64))
-    with pytest.raises(pbso.PbsoError):
-        br.render_mix(64, n_buf, pbso.PREC_TC3X)              # buf_size must be a multiple of the 128-sample tile
+    # 64-sample buffers: impulses land inside the 128-sample tiles (k_batch_event_heads renders up to the boundary)
+    assert_waveform_parity(br.render_mix(64, n_buf, pbso.PREC_TC3X), br.render_mix(64, n_buf, pbso.PREC_F64))
 
 
 @pytest.mark.parametrize("material", ["low_damping", "high_damping"])
@@ -615,6 +615,43 @@ def test_batch_tc3x_longer_render_after_shorter(pbso):
     br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"]); br.set_impulses(obj, buf, space)
     for n_buf in (100, 120, 40, 120):
         assert_waveform_parity(br.render_mix(256, n_buf, pbso.PREC_TC3X), br.render_mix(256, n_buf, pbso.PREC_F64))
+
+
+@pytest.mark.parametrize("BUF", [513, 100, 129, 640])
+def test_batch_tc3x_any_buffer_size(pbso, orc, BUF):
+    """The tensor-core path at buffer sizes that are not multiples of its 128-sample tiles -- 513 is the reference's
+    default FRAMES_PER_BUFFER (modal_solver.h:100): impulses land inside a tile (their first samples come from the
+    FP64 recurrence, k_batch_event_heads; from the next tile boundary on they are part of the contraction), the last tile
+    is cut at the end of the render.  Mix against the oracle's solver loop, stems against the FP64 kernel, and a
+    two-range render with the state handed over."""
+    n_obj, n_modes = 5, 200
+    n_buf = max(12, 9000 // BUF)
+    w = synth.batch_workload(n_obj, n_modes, n_buf, 17, "low_damping")
+    rng = np.random.default_rng(17 + BUF)
+    obj = np.repeat(np.arange(n_obj), 3)
+    buf = np.concatenate([rng.choice(n_buf, 3, replace=False) for _ in range(n_obj)])
+    buf[0] = 0; buf[3] = n_buf - 1                                           # first sample of the render / last buffer
+    space = rng.standard_normal((len(obj), n_modes))
+    want = np.zeros(n_buf * BUF)
+    for o in range(n_obj):
+        sv = orc.Solver(orc.Integrator(H, w["a"][o], w["b"][o]), BUF); sv.enqueue_trans(w["trans"][o])
+        for bi in range(n_buf):
+            for e in np.nonzero((obj == o) & (buf == bi))[0]:
+                sv.enqueue_force(space[e])
+            want[bi * BUF:(bi + 1) * BUF] += sv.step()[0]
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"]); br.set_impulses(obj, buf, space)
+    y64 = br.render_mix(BUF, n_buf, pbso.PREC_F64)
+    assert_waveform_parity(y64, want, rel=1e-10, mx=1e-10)
+    ytc = br.render_mix(BUF, n_buf, pbso.PREC_TC3X)
+    assert_waveform_parity(ytc, want)
+    s64 = br.render_stems(BUF, n_buf, pbso.PREC_F64); stc = br.render_stems(BUF, n_buf, pbso.PREC_TC3X)
+    assert np.abs(stc - s64).max() <= 3e-6 * np.abs(s64).max()
+    n1 = n_buf // 2
+    first = buf < n1
+    br.set_impulses(obj[first], buf[first], space[first]); y1 = br.render_mix(BUF, n1, pbso.PREC_TC3X)
+    br.set_state(*br.end_state(BUF, n1)); br.set_impulses(obj[~first], buf[~first] - n1, space[~first])
+    y2 = br.render_mix(BUF, n_buf - n1, pbso.PREC_TC3X)
+    assert_waveform_parity(np.concatenate([y1, y2]), want)
 
 
 def test_batch_stateful_ranges(pbso, orc):
