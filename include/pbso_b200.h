@@ -308,6 +308,9 @@ int pbso_comm_destroy(pbso_comm* c);
 int pbso_comm_info(const pbso_comm* c, int* nranks, int* rank, int* nccl_version);
 int pbso_comm_shard(const pbso_comm* c, long long n_units, long long* lo, long long* hi);
 int pbso_comm_reduce_audio(pbso_comm* c, double* d_audio, size_t n, int root, void* cuda_stream);
+/* Same with the audio in host memory (staged through a device buffer inside; blocking) -- for callers that hold no
+ * device pointers of their own, like tools/pbso_render -batch -gpus N.  Ranks other than root keep their input. */
+int pbso_comm_reduce_audio_host(pbso_comm* c, double* audio, size_t n, int root);
 
 /* ---- measurement helpers (device micro-benchmarks used by bench.py for roofline peaks) -- */
 /* kind 0: FP32 FFMA (uniform operands); 1: packed fma.rn.f32x2 (uniform operands); 2: FP64 DFMA;

@@ -118,6 +118,7 @@ def lib():
             "pbso_comm_info": [vp, c_ip, c_ip, c_ip],
             "pbso_comm_shard": [vp, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
             "pbso_comm_reduce_audio": [vp, vp, C.c_size_t, C.c_int, vp],
+            "pbso_comm_reduce_audio_host": [vp, c_dp, C.c_size_t, C.c_int],
             "pbso_measure_fma_peak": [C.c_int, c_dp, c_dp],
             "pbso_measure_tc_peak": [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp],
             "pbso_measure_tc_peak_sustained": [C.c_int, C.c_int, C.c_int, C.c_double, c_dp],

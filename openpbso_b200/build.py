@@ -56,9 +56,10 @@ def _build_tool(name):
     src = os.path.join(root, "tools", name + ".cpp")
     out = os.path.join(HERE, "bin", name)
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    if os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(OUT)):
+    deps = [src, OUT] + [os.path.join(root, "tools", f) for f in os.listdir(os.path.join(root, "tools")) if f.endswith(".h")]
+    if os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(d) for d in deps):
         return out
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(inc, "eigen_shim"), "-I" + inc, src,
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I" + os.path.join(inc, "eigen_shim"), "-I" + inc, src,
                            "-L" + HERE, "-lpbso_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/..", "-o", out])
     return out
 

@@ -134,4 +134,24 @@ int pbso_comm_reduce_audio(pbso_comm* c, double* d_audio, size_t n, int root, vo
     return PBSO_OK;
 }
 
+int pbso_comm_reduce_audio_host(pbso_comm* c, double* audio, size_t n, int root) {
+    PBSO_REQUIRE(c && audio, PBSO_ERR_INVALID, "null argument");
+    PBSO_REQUIRE(root >= -1 && root < c->nranks, PBSO_ERR_INVALID, "root outside [-1, nranks)");
+    if (c->nranks == 1 || n == 0) return PBSO_OK;
+    DeviceGuard g(c->device);
+    double* d = nullptr;
+    PBSO_CUDA(cudaMalloc(&d, sizeof(double) * n));
+    cudaError_t e = cudaMemcpy(d, audio, sizeof(double) * n, cudaMemcpyHostToDevice);
+    int rc = PBSO_OK;
+    if (e == cudaSuccess) {
+        rc = pbso_comm_reduce_audio(c, d, n, root, nullptr);           // the default stream: ordered with the copies around it
+        if (rc == PBSO_OK) e = cudaStreamSynchronize(nullptr);
+        if (rc == PBSO_OK && e == cudaSuccess && (root < 0 || root == c->rank)) e = cudaMemcpy(audio, d, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (rc != PBSO_OK) return rc;
+    if (e != cudaSuccess) return set_error(PBSO_ERR_CUDA, "audio reduce staging failed: %s", cudaGetErrorString(e));
+    return PBSO_OK;
+}
+
 }  // extern "C"

@@ -13,7 +13,7 @@ from conftest import ROOT, assert_waveform_parity
 
 INC = os.path.join(ROOT, "include", "openpbso")
 LIBDIR = os.path.join(ROOT, "openpbso_b200")
-GXX = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wno-sign-compare", "-I" + os.path.join(INC, "eigen_shim"), "-I" + INC]
+GXX = ["/usr/bin/g++", "-std=c++17", "-O2", "-pthread", "-Wall", "-Wno-sign-compare", "-I" + os.path.join(INC, "eigen_shim"), "-I" + INC]
 
 
 @pytest.fixture(scope="module")
@@ -293,6 +293,68 @@ def test_driver_renders_script_like_the_oracle(pbso, orc, render_exe, tmp_path, 
     assert fmt[:3] == (3, 2, 44100)
     want = (y / 1e10).astype(np.float32)
     assert np.array_equal(data[0::2], want) and np.array_equal(data[1::2], want)
+
+
+SCRIPT_LONG = """# every command of the driver: impulses in a row (one is dequeued per buffer), a sustained autoregressive force with a
+# parameter change, gaussian taps overlapping an impulse, listener moves in mid-render, the unit transfer, clearAllForces
+listener 0.4 3.0 -2.5
+hit 12
+hit 7
+point 3 0.0 1.0 0.0
+run 9
+gauss 1500 30 0.0 0.6 0.8
+run 1
+hit 20
+run 6
+listener -5.0 1.0 2.0
+run 2
+listener 2.0 2.0 2.0
+listener 9.0 9.0 9.0
+face 1 5 9 0.2 0.3 0.5 0 0 1
+run 5
+ar_start 5 0.0 0.0 1.0
+run 2
+arprm 0.7 0.2 0.002 0.1
+ar_data 6 1.0 0.0 0.0
+run 3
+ar_end
+run 7
+unit_transfer
+hit 2
+run 4
+use_transfer
+listener 1.0 -4.0 0.5
+hit 9
+run 3
+clear
+run 2
+until 0.45
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("BUF,prec", [(256, "tc3x"), (513, "tc3x"), (256, "f32"), (513, "f64")])
+def test_driver_batch_mode(pbso, orc, render_exe, tmp_path, BUF, prec):
+    """pbso_render -batch: the script planned on the host and rendered on the batch path (tools/offline_render.h) -- impulse
+    stretches as stateful batch ranges, transfer swaps as range boundaries, Gaussian / autoregressive buffers on the
+    per-buffer path in between.  The short script against the oracle's solver, the long one (every command) against the
+    tool's own real-time path, which the test above pins to the oracle."""
+    d = str(tmp_path); case = _write_object(d, "bell", orc)
+    tol = dict(rel=1e-9, mx=1e-9) if prec == "f64" else {}
+    for name, text in (("s", SCRIPT), ("l", SCRIPT_LONG)):
+        script = os.path.join(d, name + ".txt"); open(script, "w").write(text)
+        live, off = os.path.join(d, name + "_live.f64"), os.path.join(d, name + "_off.f64")
+        r = subprocess.run([render_exe, "-d", d, "-script", script, "-buf", str(BUF), "-raw", live], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([render_exe, "-d", d, "-script", script, "-buf", str(BUF), "-raw", off, "-batch", "-prec", prec, "-block", "32"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "offline:" in r.stdout and "range(s)" in r.stdout
+        y_live, y_off = np.fromfile(live), np.fromfile(off)
+        assert y_live.size == y_off.size and np.abs(y_live).max() > 0
+        assert_waveform_parity(y_off, y_live, **tol)
+        if name == "s":
+            assert_waveform_parity(y_off, _oracle_script(case, orc, BUF), **tol)
 
 
 @pytest.mark.gpu

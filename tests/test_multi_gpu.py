@@ -73,3 +73,33 @@ def test_single_rank_comm_is_a_no_op(pbso):
     torch.cuda.synchronize()
     assert x.cpu().tolist() == list(range(8))
     c.close()
+
+
+def test_render_tool_batch_mode_over_two_gpus(tmp_path):
+    """tools/pbso_render -batch -gpus 2: one rank (thread + device) per mode block, pbso_comm_reduce_audio_host lands the
+    track on rank 0 -- the same script rendered on one device must give the same waveform."""
+    import subprocess
+    sys.path.insert(0, ROOT)
+    import openpbso_b200 as pbso
+    if pbso.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import oracle as orc
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_headless import _write_object, SCRIPT_LONG, GXX, LIBDIR
+    from conftest import assert_waveform_parity
+    exe = str(tmp_path / "pbso_render")
+    r = subprocess.run(GXX + [os.path.join(ROOT, "tools", "pbso_render.cpp"), "-L" + LIBDIR, "-lpbso_b200", "-Wl,-rpath," + LIBDIR, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = str(tmp_path); _write_object(d, "bell", orc)
+    script = os.path.join(d, "l.txt"); open(script, "w").write(SCRIPT_LONG)
+    outs = []
+    for gpus in (1, 2):
+        raw = os.path.join(d, "g%d.f64" % gpus)
+        r = subprocess.run([exe, "-d", d, "-script", script, "-buf", "513", "-raw", raw, "-batch", "-gpus", str(gpus), "-block", "16"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "on %d device(s)" % gpus in r.stdout
+        outs.append(np.fromfile(raw))
+    assert outs[0].size == outs[1].size and np.abs(outs[0]).max() > 0
+    assert_waveform_parity(outs[1], outs[0])

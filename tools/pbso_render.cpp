@@ -6,6 +6,12 @@
 //
 //   pbso_render (-d DIR [-name N] | -meta FILE.meta | -m MESH.obj -s MODES -t MATERIAL -p FFAT_DIR)
 //               -script SCRIPT [-buf 64|128|256|512|513] [-o OUT.wav] [-raw OUT.f64] [-volume V] [-stats]
+//               [-batch [-prec tc3x|f32|f64] [-gpus N] [-block MODES]]
+//
+// -batch renders the same script OFFLINE on the batch path (tools/offline_render.h): the script is planned on the host
+// with ModalSolver::step's message semantics, impulse stretches become stateful batch renders (tensor cores by default),
+// transfer swaps are range boundaries and buffers with a live Gaussian / autoregressive force use the per-buffer path in
+// between.  -gpus N splits the object's modes over N devices and sum-reduces the track with NCCL.
 //
 // Script: one command per line, `#` starts a comment.  Commands that send a message only enqueue it; `run`
 // steps the solver (which consumes at most one force message per buffer, modal_solver.h:183).
@@ -38,6 +44,7 @@
 #include "modal_force.h"
 #include "modal_solver.h"
 #include "wav_writer.h"
+#include "offline_render.h"
 
 struct Paths { std::string obj, modes, material, ffat; };
 
@@ -110,14 +117,14 @@ int main(int argc, char** argv) {
         std::string k = argv[i];
         if (k.size() < 2 || k[0] != '-') { fprintf(stderr, "pbso_render: unexpected argument %s\n", argv[i]); return 2; }
         k = k.substr(k[1] == '-' ? 2 : 1);
-        if (k == "stats") { opt[k] = "1"; continue; }
+        if (k == "stats" || k == "batch") { opt[k] = "1"; continue; }
         if (i + 1 >= argc) { fprintf(stderr, "pbso_render: -%s needs a value\n", k.c_str()); return 2; }
         opt[k] = argv[++i];
     }
     Paths paths;
     if (opt.count("script") == 0 || !resolve_paths(opt, paths)) {
         fprintf(stderr, "usage: pbso_render (-d DIR [-name N] | -meta FILE | -m OBJ -s MODES -t MATERIAL -p FFAT_DIR) "
-                        "-script FILE [-buf N] [-o OUT.wav] [-raw OUT.f64] [-volume V] [-stats]\n");
+                        "-script FILE [-buf N] [-o OUT.wav] [-raw OUT.f64] [-volume V] [-stats] [-batch [-prec tc3x|f32|f64] [-gpus N] [-block MODES]]\n");
         return 2;
     }
     // BUF_SIZE is a template parameter of the reference's solver (modal_solver.h:100); FRAMES_PER_BUFFER = 513 is its default.
@@ -131,6 +138,55 @@ int main(int argc, char** argv) {
         default: fprintf(stderr, "pbso_render: -buf must be one of 64 128 256 512 %d\n", FRAMES_PER_BUFFER); return 2;
     }
 }
+
+// What a script command acts on: the live solver (real-time path, one buffer per step) or the offline planner.
+template <int BUF>
+struct LiveDriver {
+    ModalSolver<double, BUF>* solver;
+    pbso_wav::StereoFloatWriter* wav; FILE* raw; double volume;
+    std::vector<double> lat_us; long n_produced = 0, n_stepped = 0;
+    SoundMessage<double, BUF> sound;
+    void step() {
+        const auto t0 = std::chrono::steady_clock::now();
+        solver->step();
+        const auto t1 = std::chrono::steady_clock::now();
+        lat_us.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
+        ++n_stepped;
+        if (solver->dequeueSoundMessage(sound)) {
+            ++n_produced;
+            if (wav) wav->write(sound.data.data(), BUF, volume);
+            if (raw) fwrite(sound.data.data(), sizeof(double), BUF, raw);
+        }
+        (void)solver->getQBufferNorm();              // the GUI's consumer; keeps the lossy queue drained
+    }
+    long produced() const { return n_produced; }
+    bool listener(const Eigen::Vector3d& pos) { return solver->computeTransfer(pos); }
+    bool send(const ForceMessage<double, BUF>& m) { return solver->enqueueForceMessage(m); }
+    void arprm(const AutoregressiveForceParam<double>& p) { solver->enqueueArprmMessageNoFail(p, 1000); }
+    void useTransfer(bool s) { solver->setUseTransfer(s); }
+};
+
+template <int BUF>
+struct PlanDriver {
+    ModalSolver<double, BUF>* solver;                // evaluates the FFAT maps (kernel K3) for `listener`
+    pbso_offline::Planner<BUF> planner;
+    PlanDriver(ModalSolver<double, BUF>* s, int N) : solver(s), planner(N) {}
+    void step() { planner.step(); }
+    long produced() const { return planner.produced(); }
+    bool listener(const Eigen::Vector3d& pos) {
+        if (planner.transQueueFull() || !solver->computeTransfer(pos)) return false;     // queue capacity 1 (modal_solver.h:113)
+        TransMessage<double> t;
+        if (!solver->dequeueTransMessage(t)) return false;
+        return planner.enqueueTransMessage(std::vector<double>(t.data.data(), t.data.data() + t.data.size()));
+    }
+    bool send(const ForceMessage<double, BUF>& m) { return planner.enqueueForceMessage(m); }
+    void arprm(const AutoregressiveForceParam<double>& p) { planner.enqueueArprmMessage(p); }
+    void useTransfer(bool s) { planner.setUseTransfer(s); }
+};
+
+template <int BUF, typename Driver>
+static int play_script(const std::string& script_path, int N, const ModeData<double>& modes, const pbso_mesh::TriMesh& mesh,
+                       const std::vector<double>& VN, Driver& drv);
 
 template <int BUF>
 static int render(std::map<std::string, std::string>& opt, const Paths& paths) {
@@ -162,79 +218,39 @@ static int render(std::map<std::string, std::string>& opt, const Paths& paths) {
         FILE* raw = opt.count("raw") ? fopen(opt["raw"].c_str(), "wb") : nullptr;
         std::vector<double> lat_us;
         long produced = 0, stepped = 0;
-        SoundMessage<double, BUF> sound;
-        auto step_once = [&]() {
+        if (opt.count("batch")) {
+            // ---- offline: plan the script, then render it on the batch path ----
+            PlanDriver<BUF> drv(solver.get(), N);
+            if (int rc = play_script<BUF>(opt["script"], N, *modes, mesh, VN, drv)) return rc;
+            pbso_offline::RenderOptions ro;
+            if (opt.count("gpus")) ro.gpus = std::max(1, std::atoi(opt["gpus"].c_str()));
+            if (opt.count("block")) ro.block = std::atoi(opt["block"].c_str());
+            if (opt.count("prec")) {
+                const std::string& pr = opt["prec"];
+                if (pr == "tc3x") ro.precision = PBSO_PREC_TC3X; else if (pr == "f32") ro.precision = PBSO_PREC_F32_TILED; else if (pr == "f64") ro.precision = PBSO_PREC_F64;
+                else { fprintf(stderr, "pbso_render: -prec must be tc3x, f32 or f64\n"); return 2; }
+            }
+            // (a, b) of the audible modes as ModalIntegrator::Build derives them (modal_integrator.h:47-70)
+            std::vector<double> a((size_t)N), b((size_t)N);
+            for (int ii = 0; ii < N; ++ii) {
+                const double omega = sqrt(modes->_omegaSquared.at(ii) / material->density);
+                const double xi = 0.5 * (material->alpha / omega + material->beta * omega);
+                a[(size_t)ii] = 2 * xi * omega; b[(size_t)ii] = omega * omega;
+            }
             const auto t0 = std::chrono::steady_clock::now();
-            solver->step();
-            const auto t1 = std::chrono::steady_clock::now();
-            lat_us.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
-            ++stepped;
-            if (solver->dequeueSoundMessage(sound)) {
-                ++produced;
-                if (wav) wav->write(sound.data.data(), BUF, volume);
-                if (raw) fwrite(sound.data.data(), sizeof(double), BUF, raw);
+            long ranges = 0;
+            const std::vector<double> track = pbso_offline::render_plan<BUF>(drv.planner.plan, a, b, 1. / (double)SAMPLE_RATE, ro, &ranges);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            produced = drv.planner.produced(); stepped = drv.planner.stepped;
+            for (long bi = 0; bi < produced; ++bi) {
+                if (wav) wav->write(track.data() + (size_t)bi * BUF, BUF, volume);
+                if (raw) fwrite(track.data() + (size_t)bi * BUF, sizeof(double), BUF, raw);
             }
-            (void)solver->getQBufferNorm();              // the GUI's consumer; keeps the lossy queue drained
-        };
-
-        std::ifstream script(opt["script"].c_str());
-        if (!script) { fprintf(stderr, "pbso_render: cannot open script %s\n", opt["script"].c_str()); return 3; }
-        std::string line;
-        int lineno = 0;
-        while (std::getline(script, line)) {
-            ++lineno;
-            const size_t hash = line.find('#');
-            if (hash != std::string::npos) line.resize(hash);
-            std::istringstream in(line);
-            std::string kind;
-            if (!(in >> kind)) continue;
-            FMsg msg;
-            bool send = false;
-            auto vertex = [&](ForceType t, double width_us) {
-                int vid = 0; Eigen::Vector3d vn; in >> vid >> vn[0] >> vn[1] >> vn[2];
-                GetModalForceVertex<double, BUF>(N, *modes, vid, vn, msg);
-                set_profile(msg, t, width_us); send = true;
-            };
-            if (kind == "run") { long n = 0; in >> n; for (long i = 0; i < n; ++i) step_once(); }
-            else if (kind == "until") {
-                double sec = 0; in >> sec;
-                while ((double)produced * BUF < sec * SAMPLE_RATE) step_once();
-            }
-            else if (kind == "listener") {
-                Eigen::Vector3d pos; in >> pos[0] >> pos[1] >> pos[2];
-                if (!solver->computeTransfer(pos)) fprintf(stderr, "pbso_render:%d: transfer message dropped\n", lineno);
-            }
-            else if (kind == "hit") {
-                int vid = 0; in >> vid;
-                if (VN.empty() || vid < 0 || vid >= mesh.numVertices()) { fprintf(stderr, "pbso_render:%d: hit needs a mesh and a valid vertex\n", lineno); return 4; }
-                Eigen::Vector3d vn; vn << VN[3 * (size_t)vid], VN[3 * (size_t)vid + 1], VN[3 * (size_t)vid + 2];
-                GetModalForceVertex<double, BUF>(N, *modes, vid, vn, msg);
-                send = true;
-            }
-            else if (kind == "point") vertex(ForceType::PointForce, 0);
-            else if (kind == "gauss") { double w = 0; in >> w; vertex(ForceType::GaussianForce, w); }
-            else if (kind == "face") {
-                Eigen::Vector3i v; Eigen::Vector3d bc, vn;
-                in >> v[0] >> v[1] >> v[2] >> bc[0] >> bc[1] >> bc[2] >> vn[0] >> vn[1] >> vn[2];
-                GetModalForceFace<double, BUF>(N, *modes, v, bc, vn, msg);
-                send = true;
-            }
-            else if (kind == "clear") { msg.data.setZero(N); msg.clearAllForces = true; send = true; }
-            else if (kind == "ar_start") { vertex(ForceType::AutoregressiveForce, 0); msg.sustainedForceStart = true; }
-            else if (kind == "ar_data") vertex(ForceType::AutoregressiveForce, 0);
-            else if (kind == "ar_end") {                 // the tool's dummy end signal (:764-772)
-                GetModalForceVertex<double, BUF>(N, *modes, 0, Eigen::Vector3d::Zero(), msg);
-                set_profile(msg, ForceType::AutoregressiveForce, 0); msg.sustainedForceEnd = true; send = true;
-            }
-            else if (kind == "arprm") {
-                AutoregressiveForceParam<double> p; in >> p.a[0] >> p.a[1] >> p.sigma >> p.mu;
-                solver->enqueueArprmMessageNoFail(p, 1000);
-            }
-            else if (kind == "unit_transfer") solver->setUseTransfer(false);
-            else if (kind == "use_transfer") solver->setUseTransfer(true);
-            else { fprintf(stderr, "pbso_render:%d: unknown command '%s'\n", lineno, kind.c_str()); return 4; }
-            if (in.fail()) { fprintf(stderr, "pbso_render:%d: malformed '%s'\n", lineno, kind.c_str()); return 4; }
-            if (send && !solver->enqueueForceMessage(msg)) { fprintf(stderr, "pbso_render:%d: force queue full\n", lineno); return 4; }
+            std::cout << "offline: " << ranges << " range(s) on " << ro.gpus << " device(s), " << ms << " ms" << std::endl;
+        } else {
+            LiveDriver<BUF> drv{solver.get(), wav.get(), raw, volume};
+            if (int rc = play_script<BUF>(opt["script"], N, *modes, mesh, VN, drv)) return rc;
+            produced = drv.n_produced; stepped = drv.n_stepped; lat_us.swap(drv.lat_us);
         }
         if (wav) wav->close();
         if (raw) fclose(raw);
@@ -250,5 +266,71 @@ static int render(std::map<std::string, std::string>& opt, const Paths& paths) {
         fprintf(stderr, "pbso_render: %s\n", e.what());
         return 1;
     }
+    return 0;
+}
+
+template <int BUF, typename Driver>
+static int play_script(const std::string& script_path, int N, const ModeData<double>& modes, const pbso_mesh::TriMesh& mesh,
+                       const std::vector<double>& VN, Driver& drv) {
+    typedef ForceMessage<double, BUF> FMsg;
+        std::ifstream script(script_path.c_str());
+        if (!script) { fprintf(stderr, "pbso_render: cannot open script %s\n", script_path.c_str()); return 3; }
+        std::string line;
+        int lineno = 0;
+        while (std::getline(script, line)) {
+            ++lineno;
+            const size_t hash = line.find('#');
+            if (hash != std::string::npos) line.resize(hash);
+            std::istringstream in(line);
+            std::string kind;
+            if (!(in >> kind)) continue;
+            FMsg msg;
+            bool send = false;
+            auto vertex = [&](ForceType t, double width_us) {
+                int vid = 0; Eigen::Vector3d vn; in >> vid >> vn[0] >> vn[1] >> vn[2];
+                GetModalForceVertex<double, BUF>(N, modes, vid, vn, msg);
+                set_profile(msg, t, width_us); send = true;
+            };
+            if (kind == "run") { long n = 0; in >> n; for (long i = 0; i < n; ++i) drv.step(); }
+            else if (kind == "until") {
+                double sec = 0; in >> sec;
+                while ((double)drv.produced() * BUF < sec * SAMPLE_RATE) drv.step();
+            }
+            else if (kind == "listener") {
+                Eigen::Vector3d pos; in >> pos[0] >> pos[1] >> pos[2];
+                if (!drv.listener(pos)) fprintf(stderr, "pbso_render:%d: transfer message dropped\n", lineno);
+            }
+            else if (kind == "hit") {
+                int vid = 0; in >> vid;
+                if (VN.empty() || vid < 0 || vid >= mesh.numVertices()) { fprintf(stderr, "pbso_render:%d: hit needs a mesh and a valid vertex\n", lineno); return 4; }
+                Eigen::Vector3d vn; vn << VN[3 * (size_t)vid], VN[3 * (size_t)vid + 1], VN[3 * (size_t)vid + 2];
+                GetModalForceVertex<double, BUF>(N, modes, vid, vn, msg);
+                send = true;
+            }
+            else if (kind == "point") vertex(ForceType::PointForce, 0);
+            else if (kind == "gauss") { double w = 0; in >> w; vertex(ForceType::GaussianForce, w); }
+            else if (kind == "face") {
+                Eigen::Vector3i v; Eigen::Vector3d bc, vn;
+                in >> v[0] >> v[1] >> v[2] >> bc[0] >> bc[1] >> bc[2] >> vn[0] >> vn[1] >> vn[2];
+                GetModalForceFace<double, BUF>(N, modes, v, bc, vn, msg);
+                send = true;
+            }
+            else if (kind == "clear") { msg.data.setZero(N); msg.clearAllForces = true; send = true; }
+            else if (kind == "ar_start") { vertex(ForceType::AutoregressiveForce, 0); msg.sustainedForceStart = true; }
+            else if (kind == "ar_data") vertex(ForceType::AutoregressiveForce, 0);
+            else if (kind == "ar_end") {                 // the tool's dummy end signal (:764-772)
+                GetModalForceVertex<double, BUF>(N, modes, 0, Eigen::Vector3d::Zero(), msg);
+                set_profile(msg, ForceType::AutoregressiveForce, 0); msg.sustainedForceEnd = true; send = true;
+            }
+            else if (kind == "arprm") {
+                AutoregressiveForceParam<double> p; in >> p.a[0] >> p.a[1] >> p.sigma >> p.mu;
+                drv.arprm(p);
+            }
+            else if (kind == "unit_transfer") drv.useTransfer(false);
+            else if (kind == "use_transfer") drv.useTransfer(true);
+            else { fprintf(stderr, "pbso_render:%d: unknown command '%s'\n", lineno, kind.c_str()); return 4; }
+            if (in.fail()) { fprintf(stderr, "pbso_render:%d: malformed '%s'\n", lineno, kind.c_str()); return 4; }
+            if (send && !drv.send(msg)) { fprintf(stderr, "pbso_render:%d: force queue full\n", lineno); return 4; }
+        }
     return 0;
 }
