@@ -188,10 +188,21 @@ int pbso_ffat_fitter_shell(const pbso_ffat_fitter* f, int shell, double* geom32,
  * 2*n_elements_total complex doubles (re,im interleaved; two entries per quad, the even one is read, :1054);
  * psi[n_maps][n_directions];  scale[n_maps] or NULL receives Scaling's return value (1 without power scaling). */
 int pbso_ffat_fitter_solve(pbso_ffat_fitter* f, int n_maps, const double* k, const double* pressure,
-                           int power_scaling, double* psi, double* scale);
+                           int flags, double* psi, double* scale);
+/* `flags` (the reference's bool powerScaling is values 0 and 1):
+ *   PBSO_FIT_POWER_SCALING  Scaling (:909-929) is applied: psi *= sqrt(sum |p_0|^2 / sum (psi/(k r_0))^2)
+ *   PBSO_FIT_DEFER_SCALE    with POWER_SCALING: psi is left unscaled and scale[] (required) holds the factor -- for a consumer
+ *                           that folds it in (K3 evaluates |psi / (k r)|: dividing k by the factor does it) and saves the
+ *                           second pass over Psi
+ *   PBSO_FIT_PACKED         pressure holds ONE complex per quad, n_elements_total per mode -- entry i is the reference
+ *                           layout's entry 2 i (the odd entries, the second triangle of every quad, are never read,
+ *                           :1054-1056): half the bytes and half the sectors for a solver that can write it that way */
+#define PBSO_FIT_POWER_SCALING 1
+#define PBSO_FIT_DEFER_SCALE 2
+#define PBSO_FIT_PACKED 4
 /* Device-resident variant, enqueue only (cuda_stream NULL = the fitter's own stream); d_scale may be NULL. */
 int pbso_ffat_fitter_solve_device(pbso_ffat_fitter* f, int n_maps, const double* d_k,
-                                  const double* d_pressure, int power_scaling, double* d_psi,
+                                  const double* d_pressure, int flags, double* d_psi,
                                   double* d_scale, void* cuda_stream);
 /* CUDA-event time of the kernels of the last pbso_ffat_fitter_solve call (copies excluded). */
 int pbso_ffat_fitter_last_kernel_ms(const pbso_ffat_fitter* f, float* ms);

@@ -308,19 +308,23 @@ class FFATFitter:
         check(lib().pbso_ffat_fitter_shell(self._h, int(s), dp(geom), ip(igeom)))
         return geom, igeom
 
-    def Solve(self, k, pressure, powerScaling=False):
-        """k [n_maps]; pressure complex [n_maps][2*N_elements_total].  Returns (Psi [n_maps][N_directions], scale [n_maps])."""
+    FIT_POWER_SCALING, FIT_DEFER_SCALE, FIT_PACKED = 1, 2, 4
+
+    def Solve(self, k, pressure, powerScaling=False, packed=False):
+        """k [n_maps]; pressure complex [n_maps][2*N_elements_total] (reference layout) or, packed=True, one complex per quad
+        [n_maps][N_elements_total].  Returns (Psi [n_maps][N_directions], scale [n_maps])."""
         k = f64(np.atleast_1d(k)); n = len(k)
-        P = np.ascontiguousarray(pressure, dtype=np.complex128).reshape(n, 2 * self.n_elements_total)
+        P = np.ascontiguousarray(pressure, dtype=np.complex128).reshape(n, (1 if packed else 2) * self.n_elements_total)
         psi = np.empty((n, self.n_directions)); scale = np.empty(n)
-        check(lib().pbso_ffat_fitter_solve(self._h, n, dp(k), P.view(np.float64).ctypes.data_as(capi.c_dp),
-                                           int(bool(powerScaling)), dp(psi), dp(scale)))
+        flags = (self.FIT_POWER_SCALING if powerScaling else 0) | (self.FIT_PACKED if packed else 0)
+        check(lib().pbso_ffat_fitter_solve(self._h, n, dp(k), P.view(np.float64).ctypes.data_as(capi.c_dp), flags, dp(psi), dp(scale)))
         return psi, scale
 
-    def solve_device(self, n_maps, d_k_ptr, d_pressure_ptr, d_psi_ptr, powerScaling=False, d_scale_ptr=0, stream_ptr=0):
-        check(lib().pbso_ffat_fitter_solve_device(self._h, int(n_maps), C.c_void_p(d_k_ptr), C.c_void_p(d_pressure_ptr),
-                                                  int(bool(powerScaling)), C.c_void_p(d_psi_ptr),
-                                                  C.c_void_p(d_scale_ptr) if d_scale_ptr else None,
+    def solve_device(self, n_maps, d_k_ptr, d_pressure_ptr, d_psi_ptr, powerScaling=False, d_scale_ptr=0, stream_ptr=0, packed=False,
+                     defer_scale=False):
+        flags = (self.FIT_POWER_SCALING if powerScaling else 0) | (self.FIT_PACKED if packed else 0) | (self.FIT_DEFER_SCALE if defer_scale else 0)
+        check(lib().pbso_ffat_fitter_solve_device(self._h, int(n_maps), C.c_void_p(d_k_ptr), C.c_void_p(d_pressure_ptr), flags,
+                                                  C.c_void_p(d_psi_ptr), C.c_void_p(d_scale_ptr) if d_scale_ptr else None,
                                                   C.c_void_p(stream_ptr) if stream_ptr else None))
 
     def last_kernel_ms(self):

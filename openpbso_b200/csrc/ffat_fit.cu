@@ -123,7 +123,7 @@ template <int S_T>
 __global__ void __launch_bounds__(FIT_THREADS, S_T ? FIT_MIN_BLOCKS : 1)
 k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, const int* __restrict__ st_idx,
             const double* __restrict__ st_w, const double* __restrict__ st_c, const double* __restrict__ st_inv_r0,
-            const double* __restrict__ kvec, const double2* __restrict__ pressure, double* __restrict__ psi_out,
+            const double* __restrict__ kvec, const double2* __restrict__ pressure, int packed, double* __restrict__ psi_out,
             int power_scaling, double2* __restrict__ partial) {
     const int S = S_T ? S_T : S_rt;
     const int d = blockIdx.x * FIT_THREADS + threadIdx.x;
@@ -137,7 +137,7 @@ k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, co
             c[s] = st_c[(size_t)s * n_dir + dc];
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                idx[s][kk] = st_idx[((size_t)s * 4 + kk) * n_dir + dc];
+                idx[s][kk] = st_idx[((size_t)s * 4 + kk) * n_dir + dc] >> packed;     // packed: one complex per quad
                 w[s][kk] = st_w[((size_t)s * 4 + kk) * n_dir + dc];
             }
         }
@@ -147,7 +147,7 @@ k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, co
     const int m0 = blockIdx.y * maps_per_block, m1 = min(n_maps, m0 + maps_per_block);
     for (int m = m0; m < m1; ++m) {
         const double k = kvec[m];
-        const double2* P = pressure + (size_t)m * 2 * n_total;
+        const double2* P = pressure + (size_t)m * (packed ? n_total : 2 * n_total);
         double acc = 0.0, pa0 = 0.0;
         if (S_T) {
             double2 v[SR][4];
@@ -169,7 +169,7 @@ k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, co
                 double pre = 0.0, pim = 0.0;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const double2 v = __ldg(P + st_idx[((size_t)s * 4 + kk) * n_dir + dc]);
+                    const double2 v = __ldg(P + (st_idx[((size_t)s * 4 + kk) * n_dir + dc] >> packed));
                     const double ww = st_w[((size_t)s * 4 + kk) * n_dir + dc];
                     pre += ww * v.x; pim += ww * v.y;
                 }
@@ -222,6 +222,7 @@ k_fit_scale(int n_dir, int n_blocks, const double2* __restrict__ partial, double
         }
     }
     __syncthreads();
+    if (!psi) return;                                                 // deferred: the caller folds the scale in
     const double sc = s_scale;
     double* row = psi + (size_t)m * n_dir;
     int d = threadIdx.x;
@@ -237,8 +238,10 @@ __global__ void k_fit_fill(int n, double v, double* __restrict__ out) {
     if (i < n) out[i] = v;
 }
 
-static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, const double* d_p, int power_scaling,
+static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, const double* d_p, int flags,
                         double* d_psi, double* d_scale, cudaStream_t s) {
+    const int power_scaling = flags & PBSO_FIT_POWER_SCALING, packed = (flags & PBSO_FIT_PACKED) ? 1 : 0;
+    const bool defer = (flags & PBSO_FIT_DEFER_SCALE) != 0;
     const int gx = div_up(f->n_dir, FIT_THREADS);
     if (power_scaling) {
         const size_t need = (size_t)n_maps * gx;
@@ -253,23 +256,27 @@ static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, cons
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, f->device);
     const double2* P = reinterpret_cast<const double2*>(d_p);
     double2* part = reinterpret_cast<double2*>(f->d_partial);
-    // (a TMA-staged variant -- 16-byte rows at a 32-byte pitch through a shared-memory ring -- was measured in round 1 and was
-    // no faster, profiles/r1_ffat_fit.md: removed)
+    // (measured and removed, profiles/r1_ffat_fit.md and r2_ffat_fit.md: a TMA-staged variant -- 16-byte rows at a 32-byte pitch
+    // through a shared-memory ring; one thread per (direction, shell) -- 56 registers, 36 resident warps instead of 16, 10 %
+    // slower; issuing the y + 1 taps after the y taps so that they hit L1 -- no change.  ncu: L2 sector traffic is 3 x the
+    // algorithmic bytes (the four taps and three shells of neighbouring directions re-read sectors that L1 does not hold
+    // long enough), 5.5 TB/s of L2 traffic is what bounds the kernel)
     {
         // direct gathers: enough blocks for ~16 resident CTAs on every SM before modes are folded into a block
         int mpb = 1;
         while (mpb < 8 && (long long)gx * div_up(n_maps, mpb * 2) >= (long long)sm * 16) mpb *= 2;
         const dim3 grid(gx, div_up(n_maps, mpb));
         if (f->S == 3)
-            k_fit_solve<3><<<grid, FIT_THREADS, 0, s>>>(3, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w, f->d_c, f->d_inv_r0, d_k, P,
+            k_fit_solve<3><<<grid, FIT_THREADS, 0, s>>>(3, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w, f->d_c, f->d_inv_r0, d_k, P, packed,
                                                         d_psi, power_scaling, part);
         else
-            k_fit_solve<0><<<grid, FIT_THREADS, 0, s>>>(f->S, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w, f->d_c, f->d_inv_r0, d_k, P,
+            k_fit_solve<0><<<grid, FIT_THREADS, 0, s>>>(f->S, f->n_dir, f->n_total, n_maps, mpb, f->d_idx, f->d_w, f->d_c, f->d_inv_r0, d_k, P, packed,
                                                         d_psi, power_scaling, part);
     }
     PBSO_CUDA(cudaGetLastError());
     if (power_scaling) {
-        k_fit_scale<<<n_maps, 256, 0, s>>>(f->n_dir, gx, part, d_psi, d_scale);
+        if (defer) PBSO_REQUIRE(d_scale, PBSO_ERR_INVALID, "PBSO_FIT_DEFER_SCALE needs the scale output");
+        k_fit_scale<<<n_maps, defer ? 32 : 256, 0, s>>>(f->n_dir, gx, part, defer ? nullptr : d_psi, d_scale);
         PBSO_CUDA(cudaGetLastError());
     } else if (d_scale) {
         k_fit_fill<<<div_up(n_maps, 256), 256, 0, s>>>(n_maps, 1.0, d_scale);
@@ -394,23 +401,27 @@ int pbso_ffat_fitter_shell(const pbso_ffat_fitter* f, int shell, double* geom32,
 }
 
 int pbso_ffat_fitter_solve_device(pbso_ffat_fitter* f, int n_maps, const double* d_k, const double* d_pressure,
-                                  int power_scaling, double* d_psi, double* d_scale, void* cuda_stream) {
+                                  int flags, double* d_psi, double* d_scale, void* cuda_stream) {
     PBSO_REQUIRE(f && n_maps >= 0, PBSO_ERR_INVALID, "bad argument");
     if (n_maps == 0) return PBSO_OK;
     PBSO_REQUIRE(d_k && d_pressure && d_psi, PBSO_ERR_INVALID, "null argument");
     PBSO_REQUIRE((reinterpret_cast<uintptr_t>(d_pressure) & 15) == 0, PBSO_ERR_INVALID, "pressure must be 16-byte aligned");
     DeviceGuard g(f->device);
-    return launch_solve(f, n_maps, d_k, d_pressure, power_scaling, d_psi, d_scale, cuda_stream ? (cudaStream_t)cuda_stream : f->stream);
+    return launch_solve(f, n_maps, d_k, d_pressure, flags, d_psi, d_scale, cuda_stream ? (cudaStream_t)cuda_stream : f->stream);
 }
 
-int pbso_ffat_fitter_solve(pbso_ffat_fitter* f, int n_maps, const double* k, const double* pressure, int power_scaling,
+int pbso_ffat_fitter_solve(pbso_ffat_fitter* f, int n_maps, const double* k, const double* pressure, int flags,
                            double* psi, double* scale) {
     PBSO_REQUIRE(f && n_maps >= 0, PBSO_ERR_INVALID, "bad argument");
     if (n_maps == 0) return PBSO_OK;
     PBSO_REQUIRE(k && pressure && psi, PBSO_ERR_INVALID, "null argument");
     // Solve asserts _N_directions > 0 (:1012); k == 0 would divide by zero exactly as the reference does (inf/nan out)
     DeviceGuard g(f->device);
-    const size_t per_map = (size_t)4 * f->n_total;                              // doubles: 2 * n_total complex entries (:1013)
+    const size_t per_map = (size_t)((flags & PBSO_FIT_PACKED) ? 2 : 4) * f->n_total;   // doubles: 2 * n_total complex entries (:1013), half of that packed
+    // power scaling on this entry: the device computes the factor, the host multiplies while the data is in its hands
+    // (row * scale, the same FP64 product k_fit_scale does) -- no second pass over Psi on the device
+    const bool host_scale = (flags & PBSO_FIT_POWER_SCALING) && !(flags & PBSO_FIT_DEFER_SCALE);
+    std::vector<double> sc_h;
     const size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)n_maps, ((size_t)256 << 20) / (per_map * sizeof(double))));
     if (chunk > f->cap_maps) {
         cudaFree(f->d_k); cudaFree(f->d_p); cudaFree(f->d_psi); cudaFree(f->d_scale);
@@ -427,11 +438,14 @@ int pbso_ffat_fitter_solve(pbso_ffat_fitter* f, int n_maps, const double* k, con
         PBSO_CUDA(cudaMemcpyAsync(f->d_k, k + m0, n * sizeof(double), cudaMemcpyHostToDevice, f->stream));
         PBSO_CUDA(cudaMemcpyAsync(f->d_p, pressure + m0 * per_map, n * per_map * sizeof(double), cudaMemcpyHostToDevice, f->stream));
         PBSO_CUDA(cudaEventRecord(f->ev0, f->stream));
-        if (int rc = launch_solve(f, n, f->d_k, f->d_p, power_scaling, f->d_psi, f->d_scale, f->stream)) return rc;
+        if (int rc = launch_solve(f, n, f->d_k, f->d_p, host_scale ? (flags | PBSO_FIT_DEFER_SCALE) : flags, f->d_psi, f->d_scale, f->stream)) return rc;
         PBSO_CUDA(cudaEventRecord(f->ev1, f->stream));
         PBSO_CUDA(cudaMemcpyAsync(psi + m0 * f->n_dir, f->d_psi, (size_t)n * f->n_dir * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
         if (scale) PBSO_CUDA(cudaMemcpyAsync(scale + m0, f->d_scale, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+        if (host_scale) { sc_h.resize((size_t)n); PBSO_CUDA(cudaMemcpyAsync(sc_h.data(), f->d_scale, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream)); }
         PBSO_CUDA(cudaStreamSynchronize(f->stream));
+        if (host_scale)
+            for (int m = 0; m < n; ++m) { double* row = psi + (m0 + m) * f->n_dir; const double sc = sc_h[(size_t)m]; for (int d = 0; d < f->n_dir; ++d) row[d] *= sc; }
         float ms = 0.f; cudaEventElapsedTime(&ms, f->ev0, f->ev1); f->last_ms += ms;
     }
     return PBSO_OK;

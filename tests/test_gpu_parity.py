@@ -831,6 +831,17 @@ def test_ffat_fit_many_modes_and_device_entry(pbso, orc):
     ft.solve_device(300, dk.data_ptr(), dp.data_ptr(), dpsi.data_ptr(), True, dscale.data_ptr(), st.cuda_stream)
     st.synchronize()
     assert np.array_equal(dpsi.cpu().numpy(), psi) and np.array_equal(dscale.cpu().numpy(), scale)
+    # packed layout (one complex per quad = the even entries, the only ones Solve reads, ffat_solver.h:1054-1056): same bits,
+    # host and device entries; deferred scale: Psi unscaled + the factor
+    packed = np.ascontiguousarray(w["pressure"][:, 0::2])
+    psi_p, scale_p = ft.Solve(w["k"], packed, True, packed=True)
+    assert np.array_equal(psi_p, psi) and np.array_equal(scale_p, scale)
+    dpp = torch.from_numpy(packed.view(np.float64)).cuda()
+    ft.solve_device(300, dk.data_ptr(), dpp.data_ptr(), dpsi.data_ptr(), True, dscale.data_ptr(), st.cuda_stream, packed=True, defer_scale=True)
+    st.synchronize()
+    psi_u, _ = ft.Solve(w["k"], w["pressure"], False)
+    assert np.array_equal(dpsi.cpu().numpy(), psi_u) and np.array_equal(dscale.cpu().numpy(), scale)
+    assert np.array_equal(psi_u * scale[:, None], psi)
 
 
 def test_ffat_fit_feeds_runtime_map(pbso, orc):
