@@ -143,7 +143,6 @@ k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, co
         }
     }
     const double inv_r0 = st_inv_r0[dc];
-    __shared__ double2 s_red[FIT_THREADS / 32];
     const int m0 = blockIdx.y * maps_per_block, m1 = min(n_maps, m0 + maps_per_block);
     for (int m = m0; m < m1; ++m) {
         const double k = kvec[m];
@@ -188,15 +187,9 @@ k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, co
                 t2.x += __shfl_down_sync(0xffffffffu, t2.x, o);
                 t2.y += __shfl_down_sync(0xffffffffu, t2.y, o);
             }
-            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t2;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double2 t = s_red[0];
-#pragma unroll
-                for (int i = 1; i < FIT_THREADS / 32; ++i) { t.x += s_red[i].x; t.y += s_red[i].y; }
-                partial[(size_t)m * gridDim.x + blockIdx.x] = t;
-            }
-            __syncthreads();
+            // one partial per WARP, straight to global memory: no block barrier inside the mode loop (two __syncthreads per
+            // mode cost 25 % of the kernel); k_fit_scale adds them in a fixed order
+            if ((threadIdx.x & 31) == 0) partial[((size_t)m * gridDim.x + blockIdx.x) * (FIT_THREADS / 32) + (threadIdx.x >> 5)] = t2;
         }
     }
 }
@@ -244,7 +237,7 @@ static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, cons
     const bool defer = (flags & PBSO_FIT_DEFER_SCALE) != 0;
     const int gx = div_up(f->n_dir, FIT_THREADS);
     if (power_scaling) {
-        const size_t need = (size_t)n_maps * gx;
+        const size_t need = (size_t)n_maps * gx * (FIT_THREADS / 32);
         if (need > f->cap_partial) {
             cudaFree(f->d_partial);
             f->d_partial = nullptr; f->cap_partial = 0;
@@ -276,7 +269,7 @@ static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, cons
     PBSO_CUDA(cudaGetLastError());
     if (power_scaling) {
         if (defer) PBSO_REQUIRE(d_scale, PBSO_ERR_INVALID, "PBSO_FIT_DEFER_SCALE needs the scale output");
-        k_fit_scale<<<n_maps, defer ? 32 : 256, 0, s>>>(f->n_dir, gx, part, defer ? nullptr : d_psi, d_scale);
+        k_fit_scale<<<n_maps, defer ? 32 : 256, 0, s>>>(f->n_dir, gx * (FIT_THREADS / 32), part, defer ? nullptr : d_psi, d_scale);
         PBSO_CUDA(cudaGetLastError());
     } else if (d_scale) {
         k_fit_fill<<<div_up(n_maps, 256), 256, 0, s>>>(n_maps, 1.0, d_scale);
