@@ -60,19 +60,7 @@ struct FFAT_Map_Serialize_Double {
         return match;
     }
 private:
-    static void Fill(const std::shared_ptr<pbso_ffat>& set, int id, FFAT_Map<double, 3>& map) {
-        double geom[32]; int igeom[18]; int n = 0, cols = 0, comp = 0;
-        pbso_mirror::check(pbso_ffat_get_map(set.get(), id, geom, igeom, &n, &cols, &comp, nullptr), "FFAT_Map_Serialize");
-        map._Psi.resize(n, cols);
-        pbso_mirror::check(pbso_ffat_get_map(set.get(), id, nullptr, nullptr, nullptr, nullptr, nullptr, map._Psi.data()), "FFAT_Map_Serialize");
-        map._cellSize = geom[0];
-        map._center << geom[28], geom[29], geom[30];
-        map._k = geom[31];
-        map._is_compressed = comp != 0;
-        map.modeId = id;
-        map._set = set;
-        map._single.reset();
-    }
+    static void Fill(const std::shared_ptr<pbso_ffat>& set, int id, FFAT_Map<double, 3>& map) { FFAT_Map<double, 3>::FillFromSet(set, id, map); }
 };
 typedef FFAT_Map_Serialize_Double FFAT_Map_Serialize;
 }  // namespace Gpu_Wavesolver

@@ -85,6 +85,33 @@ public:
         _set = std::shared_ptr<pbso_ffat>(h, [](pbso_ffat* q) { pbso_ffat_destroy(q); });
         _single.reset();
     }
+    // The LEGACY file form: igl::serialize of the whole object (reference :1066-1085; FFAT_Map_Serialize in ffat_map_serialize.h is
+    // the protobuf form that replaced it).  Save writes it (shell 2 three times: GetMapVal reads shell 2 only); Load / LoadAll
+    // read it -- and the protobuf form too, the library tells them apart by the first chunk header.  No libigl involved: the
+    // format is restated in libpbso_b200 (csrc/fatcube_codec.h).
+    static void Save(const char* filename, const FFAT_Map<T, 3>& map) {
+        assert(map._set && "FFAT map is empty");
+        pbso_mirror::check(pbso_ffat_save_legacy_file(map._set.get(), map.modeId, filename), "FFAT_Map::Save");
+    }
+    static void Load(const char* filename, FFAT_Map<T, 3>& map) {
+        pbso_ffat* h = nullptr;
+        pbso_mirror::check(pbso_ffat_load_file(filename, &h), "FFAT_Map::Load");
+        std::shared_ptr<pbso_ffat> set(h, [](pbso_ffat* p) { pbso_ffat_destroy(p); });
+        int id = 0;
+        pbso_mirror::check(pbso_ffat_mode_ids(h, &id), "FFAT_Map::Load");
+        FillFromSet(set, id, map);
+    }
+    static std::map<int, FFAT_Map<T, 3>>* LoadAll(const char* dirname) {
+        std::vector<std::string> filenames;
+        ListDirFiles(dirname, filenames, ".fatcube");
+        auto* map = new std::map<int, FFAT_Map<T, 3>>();
+        for (const auto& filename : filenames) {
+            FFAT_Map<T, 3> map_;
+            Load(filename.c_str(), map_);
+            (*map)[map_.modeId] = map_;
+        }
+        return map;
+    }
     // One line per shell: "Nx Ny" for the six faces (reference :1100-1118).
     static void ReadNElementsFile(const char* filename, std::vector<std::vector<std::pair<int, int>>>& N_elements) {
         std::ifstream stream(filename);
@@ -138,6 +165,22 @@ private:
     std::shared_ptr<pbso_ffat_fitter> _fitter;    // shell geometry, when built from a mesh
     mutable std::shared_ptr<pbso_ffat> _single;   // this map alone, re-keyed to id 0, built on first GetMapVal
 
+    // host copy of one map of a loaded set (what both Load functions fill in)
+    static void FillFromSet(const std::shared_ptr<pbso_ffat>& set, int id, FFAT_Map<T, 3>& map) {
+        double geom[32]; int igeom[18]; int n = 0, cols = 0, comp = 0;
+        pbso_mirror::check(pbso_ffat_get_map(set.get(), id, geom, igeom, &n, &cols, &comp, nullptr), "FFAT_Map");
+        std::vector<double> psi((size_t)n * cols);
+        pbso_mirror::check(pbso_ffat_get_map(set.get(), id, nullptr, nullptr, nullptr, nullptr, nullptr, psi.data()), "FFAT_Map");
+        map._Psi.resize(n, cols);
+        for (int c = 0; c < cols; ++c) for (int r = 0; r < n; ++r) map._Psi(r, c) = (T)psi[(size_t)c * n + r];
+        map._cellSize = (T)geom[0];
+        map._center << (T)geom[28], (T)geom[29], (T)geom[30];
+        map._k = (T)geom[31];
+        map._is_compressed = comp != 0;
+        map.modeId = id;
+        map._set = set;
+        map._single.reset();
+    }
     pbso_ffat* single() const {
         if (!_single) {
             double geom[32]; int igeom[18]; int n = 0, cols = 0, comp = 0;

@@ -126,6 +126,11 @@ int pbso_ffat_get_map(const pbso_ffat* f, int mode_id, double* geom32, int* igeo
                       int* psi_len, int* psi_cols, int* is_compressed, double* psi);
 /* FFAT_Map_Serialize_Double::Save (ffat_map_serialize.h:90-164). */
 int pbso_ffat_save_file(const pbso_ffat* f, int mode_id, const char* filename);
+/* The LEGACY .fatcube form -- libigl's igl::serialize of the FFAT_Map<T,3> object, what FFAT_Map<T,3>::Save / Load / LoadAll
+ * (ffat_solver.h:1066-1085) write and read -- is recognised by pbso_ffat_load_file / pbso_ffat_load_dir by its first chunk
+ * header ("serial_map_ch3") and read without libigl (the format is restated in csrc/fatcube_codec.h); this writes it:
+ * shell 2 three times (GetMapVal reads shell 2 only), g++ type strings. */
+int pbso_ffat_save_legacy_file(const pbso_ffat* f, int mode_id, const char* filename);
 /* ModalSolver::computeTransfer (modal_solver.h:286-315) for L listeners at once (kernel K3):
  * out[l*n_modes + m] = |maps.at(m).GetMapVal(pos_l, use_compressed)|, m in [0, n_modes)
  * (ffat_solver.h:1180-1206 -> Intersect :676-712 -> Interpolate :736-803 -> Reconstruct :899-906).

@@ -74,6 +74,7 @@ def lib():
             "pbso_ffat_mode_ids": [vp, c_ip],
             "pbso_ffat_get_map": [vp, C.c_int, c_dp, c_ip, c_ip, c_ip, c_ip, c_dp],
             "pbso_ffat_save_file": [vp, C.c_int, C.c_char_p],
+            "pbso_ffat_save_legacy_file": [vp, C.c_int, C.c_char_p],
             "pbso_ffat_eval": [vp, C.c_int, c_dp, C.c_int, C.c_int, c_dp],
             "pbso_ffat_eval_device": [vp, C.c_int, vp, C.c_int, vp, vp],
             "pbso_ffat_eval_device_view": [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp],

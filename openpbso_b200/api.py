@@ -236,6 +236,10 @@ class FFATMaps:
     def Save(self, mode_id, filename):
         check(lib().pbso_ffat_save_file(self._h, mode_id, filename.encode()))
 
+    def SaveLegacy(self, mode_id, filename):
+        """FFAT_Map<T,3>::Save (ffat_solver.h:1066-1068): the igl::serialize form; LoadAll / Load read either form."""
+        check(lib().pbso_ffat_save_legacy_file(self._h, mode_id, filename.encode()))
+
     def quantise(self, mode_id):
         """First half of FFAT_Map<T,3>::Compress (ffat_solver.h:1125-1147): per face, Psi * (255/maxAmp) saturated to 8 bits
         the way cv::Mat::convertTo(CV_8U) does -> (q8 [psi_len] uint8, maxAmp[6], maxAmp_global)."""

@@ -168,6 +168,164 @@ void fatcube_encode(const FatcubeMap& m, std::string& out) {
     put_bytes(out, 1, t3);
 }
 
+// ---------------------------------------------------------------------------------------------
+// legacy igl::serialize reader / writer (format notes in fatcube_codec.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Cur {
+    const uint8_t* p = nullptr; const uint8_t* end = nullptr; bool ok = true;
+    Cur() {}
+    Cur(const uint8_t* b, const uint8_t* e) : p(b), end(e) {}
+    bool need(size_t n) { if (!ok || (size_t)(end - p) < n) { ok = false; return false; } return true; }
+    uint64_t u64() { uint64_t v = 0; if (need(8)) { std::memcpy(&v, p, 8); p += 8; } return v; }
+    int32_t i32() { int32_t v = 0; if (need(4)) { std::memcpy(&v, p, 4); p += 4; } return v; }
+    double f64() { double v = 0; if (need(8)) { std::memcpy(&v, p, 8); p += 8; } return v; }
+    std::string str() { const uint64_t n = u64(); std::string s; if (need(n)) { s.assign((const char*)p, (size_t)n); p += n; } return s; }
+    Cur sub(uint64_t n) { if (!need(n)) return Cur(end, end); Cur c(p, p + n); p += n; return c; }
+};
+struct Chunk { std::string name; Cur data; };
+// next chunk of a member stream; false at the end (or on a malformed header: c.ok is cleared)
+bool next_chunk(Cur& c, Chunk& out) {
+    if (!c.ok || c.p >= c.end) return false;
+    out.name = c.str();
+    (void)c.str();                                                   // type: the writer's typeid name, not needed
+    const uint64_t size = c.u64();
+    out.data = c.sub(size);
+    return c.ok;
+}
+bool read_matrix(Cur& c, std::vector<double>& v, int64_t& rows, int64_t& cols) {
+    rows = (int64_t)c.u64(); cols = (int64_t)c.u64();
+    if (!c.ok || rows < 0 || cols < 0 || (rows && cols > (int64_t)((size_t)(c.end - c.p) / 8) / rows)) { c.ok = false; return false; }
+    v.resize((size_t)(rows * cols));
+    for (auto& x : v) x = c.f64();
+    return c.ok;
+}
+bool read_vec3(Cur& c, std::vector<double>& v) { int64_t r, q; return read_matrix(c, v, r, q) && v.size() == 3; }
+
+void lg_put_u64(std::string& o, uint64_t v) { o.append((const char*)&v, 8); }
+void lg_put_i32(std::string& o, int32_t v) { o.append((const char*)&v, 4); }
+void lg_put_f64(std::string& o, double v) { o.append((const char*)&v, 8); }
+void lg_put_str(std::string& o, const std::string& s) { lg_put_u64(o, s.size()); o += s; }
+void lg_put_chunk(std::string& o, const char* name, const char* type, const std::string& data) {
+    lg_put_str(o, name); lg_put_str(o, type); lg_put_u64(o, data.size()); o += data;
+}
+std::string mat_bytes(const std::vector<double>& v, int64_t rows, int64_t cols) {
+    std::string o; lg_put_u64(o, (uint64_t)rows); lg_put_u64(o, (uint64_t)cols);
+    for (double x : v) lg_put_f64(o, x);
+    return o;
+}
+const char* T_INT = "i"; const char* T_DBL = "d"; const char* T_BOOL = "b";
+const char* T_V3 = "N5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEE";
+const char* T_MX = "N5Eigen6MatrixIdLin1ELin1ELi0ELin1ELin1EEE";
+}  // namespace
+
+bool legacy_fatcube_sniff(const uint8_t* data, size_t size) {
+    static const char tag[] = "serial_map_ch3";
+    uint64_t n = 0;
+    if (size < 8 + sizeof(tag) - 1) return false;
+    std::memcpy(&n, data, 8);
+    return n == sizeof(tag) - 1 && std::memcmp(data + 8, tag, sizeof(tag) - 1) == 0;
+}
+
+bool legacy_fatcube_decode(const uint8_t* data, size_t size, FatcubeMap& out, std::string& err) {
+    Cur file(data, data + size);
+    Chunk top; bool found = false; Cur body(data, data);
+    while (next_chunk(file, top))
+        if (top.name == "serial_map_ch3") { body = top.data; found = true; }      // igl::deserialize keeps the LAST match (serialize.h:540-545)
+    if (!file.ok) { err = "legacy .fatcube: truncated chunk header"; return false; }
+    if (!found) { err = "legacy .fatcube: no \"serial_map_ch3\" object"; return false; }
+    Cur members = body.sub(body.u64());
+    if (!body.ok) { err = "legacy .fatcube: truncated object"; return false; }
+    out = FatcubeMap();
+    std::vector<double> psi, cpsi; int64_t pr = 0, pc = 0, cr = 0, cc = 0;
+    bool have_shell = false;
+    Chunk m;
+    while (next_chunk(members, m)) {
+        Cur& d = m.data;
+        if (m.name == "modeId") out.modeid = d.i32();
+        else if (m.name == "k") out.k = d.f64();
+        else if (m.name == "center") read_vec3(d, out.center3);
+        else if (m.name == "Psi") read_matrix(d, psi, pr, pc);
+        else if (m.name == "compressed_Psi") read_matrix(d, cpsi, cr, cc);
+        else if (m.name == "is_compressed") { if (d.need(1)) out.is_compressed = *d.p != 0; }
+        else if (m.name == "maps") {                                  // std::vector<FFAT_Map<T,1>>: GetMapVal reads _shells.at(2)
+            const uint64_t count = d.u64();
+            for (uint64_t s = 0; s < count && d.ok; ++s) {
+                Cur shell = d.sub(d.u64());
+                if (s != 2) continue;
+                have_shell = true;
+                Chunk f;
+                while (next_chunk(shell, f)) {
+                    Cur& e = f.data;
+                    if (f.name == "cellSize") out.cellsize = e.f64();
+                    else if (f.name == "center") read_vec3(e, out.center1);
+                    else if (f.name == "bboxLow") read_vec3(e, out.bboxlow);
+                    else if (f.name == "bboxTop") read_vec3(e, out.bboxtop);
+                    else if (f.name == "lowCorners") {
+                        const uint64_t n = e.u64();
+                        for (uint64_t i = 0; i < n && e.ok; ++i) { std::vector<double> v; if (read_vec3(e, v)) out.lowcorners.push_back(v); }
+                    } else if (f.name == "N_elements") {
+                        const uint64_t n = e.u64();
+                        for (uint64_t i = 0; i < n && e.ok; ++i) { const int a = e.i32(), b = e.i32(); out.n_elements.push_back({a, b}); }
+                    } else if (f.name == "strides") {
+                        const uint64_t n = e.u64();
+                        for (uint64_t i = 0; i < n && e.ok; ++i) out.strides.push_back(e.i32());
+                    }
+                    if (!e.ok) { err = "legacy .fatcube: truncated member \"" + f.name + "\" of shell 2"; return false; }
+                }
+                if (!shell.ok) { err = "legacy .fatcube: truncated shell"; return false; }
+            }
+        }
+        if (!d.ok) { err = "legacy .fatcube: truncated member \"" + m.name + "\""; return false; }
+    }
+    if (!members.ok) { err = "legacy .fatcube: truncated member stream"; return false; }
+    if (!have_shell) { err = "legacy .fatcube: fewer than 3 shells (GetMapVal reads _shells.at(2))"; return false; }
+    // the protobuf form keeps ONE matrix: _compressed_Psi when _is_compressed, else _Psi (ffat_map_serialize.h:147-160)
+    const std::vector<double>& src = out.is_compressed ? cpsi : psi;
+    const int64_t rows = out.is_compressed ? cr : pr, cols = out.is_compressed ? cc : pc;
+    for (int64_t c = 0; c < cols; ++c) out.psi.emplace_back(src.begin() + c * rows, src.begin() + (c + 1) * rows);
+    return true;
+}
+
+void legacy_fatcube_encode(const FatcubeMap& m, std::string& out) {
+    std::string shell;                                               // FFAT_Map<T,1>::InitSerialization (ffat_solver.h:440-452)
+    { std::string d; lg_put_i32(d, m.modeid); lg_put_chunk(shell, "modeId", T_INT, d); }
+    { std::string d; lg_put_f64(d, -1.0); lg_put_chunk(shell, "k", T_DBL, d); }                       // a shell's own _k stays at its default
+    { std::string d; lg_put_f64(d, m.cellsize); lg_put_chunk(shell, "cellSize", T_DBL, d); }
+    { std::string d; lg_put_u64(d, m.lowcorners.size()); for (auto& v : m.lowcorners) d += mat_bytes(v, 3, 1);
+      lg_put_chunk(shell, "lowCorners", "St6vectorIN5Eigen6MatrixIdLi3ELi1ELi0ELi3ELi1EEESaIS2_EE", d); }
+    { std::string d; lg_put_u64(d, m.n_elements.size()); for (auto& v : m.n_elements) { lg_put_i32(d, v[0]); lg_put_i32(d, v[1]); }
+      lg_put_chunk(shell, "N_elements", "St6vectorISt4pairIiiESaIS1_EE", d); }
+    { std::string d; lg_put_u64(d, m.strides.size()); for (int v : m.strides) lg_put_i32(d, v); lg_put_chunk(shell, "strides", "St6vectorIiSaIiEE", d); }
+    int total = 0; for (auto& v : m.n_elements) total += v[0] * v[1];
+    { std::string d; lg_put_i32(d, total); lg_put_chunk(shell, "N_elements_total", T_INT, d); }
+    { std::string d; lg_put_u64(d, 0); lg_put_chunk(shell, "A", "St6vectorIN5Eigen6MatrixISt7complexIdELin1ELi1ELi0ELin1ELi1EEESaIS4_EE", d); }
+    lg_put_chunk(shell, "center", T_V3, mat_bytes(m.center1, 3, 1));
+    lg_put_chunk(shell, "bboxLow", T_V3, mat_bytes(m.bboxlow, 3, 1));
+    lg_put_chunk(shell, "bboxTop", T_V3, mat_bytes(m.bboxtop, 3, 1));
+    std::string body;                                                // FFAT_Map<T,3>::InitSerialization (:978-991)
+    { std::string d; lg_put_i32(d, m.modeid); lg_put_chunk(body, "modeId", T_INT, d); }
+    { std::string d; lg_put_f64(d, m.k); lg_put_chunk(body, "k", T_DBL, d); }
+    { std::string d; lg_put_f64(d, m.cellsize); lg_put_chunk(body, "cellSize", T_DBL, d); }
+    lg_put_chunk(body, "center", T_V3, mat_bytes(m.center3, 3, 1));
+    { std::string d; lg_put_u64(d, 3); for (int s = 0; s < 3; ++s) { lg_put_u64(d, shell.size()); d += shell; }
+      lg_put_chunk(body, "maps", "St6vectorIN14Gpu_Wavesolver8FFAT_MapIdLi1EEESaIS2_EE", d); }
+    { std::string d; lg_put_u64(d, 3); for (int s = 0; s < 3; ++s) { lg_put_u64(d, m.n_elements.size()); for (auto& v : m.n_elements) { lg_put_i32(d, v[0]); lg_put_i32(d, v[1]); } }
+      lg_put_chunk(body, "N_elements", "St6vectorIS_ISt4pairIiiESaIS1_EESaIS3_EE", d); }
+    { std::string d; lg_put_u64(d, 3); lg_put_i32(d, 0); lg_put_i32(d, total); lg_put_i32(d, 2 * total); lg_put_chunk(body, "strides", "St6vectorIiSaIiEE", d); }   // shell offsets (:960-975)
+    std::vector<double> flat; const size_t rows = m.psi.empty() ? 0 : m.psi[0].size();
+    for (auto& c : m.psi) flat.insert(flat.end(), c.begin(), c.end());
+    const std::string mat = mat_bytes(flat, (int64_t)rows, (int64_t)m.psi.size()), none = mat_bytes({}, 0, 0);
+    lg_put_chunk(body, "Psi", T_MX, m.is_compressed ? none : mat);
+    { std::string d; lg_put_i32(d, 3 * total); lg_put_chunk(body, "N_elements_total", T_INT, d); }
+    { std::string d; lg_put_i32(d, total); lg_put_chunk(body, "N_directions", T_INT, d); }
+    { std::string d; d.push_back(m.is_compressed ? 1 : 0); lg_put_chunk(body, "is_compressed", T_BOOL, d); }
+    lg_put_chunk(body, "compressed_Psi", T_MX, m.is_compressed ? mat : none);
+    std::string data; lg_put_u64(data, body.size()); data += body;
+    out.clear();
+    lg_put_chunk(out, "serial_map_ch3", "N14Gpu_Wavesolver8FFAT_MapIdLi3EEE", data);
+}
+
 bool list_dir_files(const char* dirname, std::vector<std::string>& names, const char* contains) {
     DIR* dir = opendir(dirname);
     if (!dir) return false;                                   // reference: perror(""), empty list

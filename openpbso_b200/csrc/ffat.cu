@@ -602,7 +602,11 @@ static int load_one(const char* filename, HostMap& hm) {
     std::stringstream ss; ss << stream.rdbuf();
     const std::string buf = ss.str();
     FatcubeMap fm; std::string err;
-    if (!fatcube_decode((const uint8_t*)buf.data(), buf.size(), fm, err))
+    // both of the reference's loaders read "*.fatcube": FFAT_Map_Serialize::Load the protobuf form (ffat_map_serialize.h:166-254),
+    // FFAT_Map<T,3>::Load the legacy igl::serialize form (ffat_solver.h:1069-1071) -- told apart by the legacy chunk header
+    const bool legacy = legacy_fatcube_sniff((const uint8_t*)buf.data(), buf.size());
+    if (!(legacy ? legacy_fatcube_decode((const uint8_t*)buf.data(), buf.size(), fm, err)
+                 : fatcube_decode((const uint8_t*)buf.data(), buf.size(), fm, err)))
         return set_error(PBSO_ERR_FORMAT, "%s: %s", filename, err.c_str());
     if (int rc = to_host_map(fm, hm, err)) return set_error(rc, "%s: %s", filename, err.c_str());
     return PBSO_OK;
@@ -964,6 +968,18 @@ int pbso_ffat_save_file(const pbso_ffat* f, int mode_id, const char* filename) {
     if (it == f->maps.end()) return set_error(PBSO_ERR_RANGE, "no map with mode id %d", mode_id);
     FatcubeMap fm; from_host_map(it->second, fm);
     std::string bytes; fatcube_encode(fm, bytes);
+    std::ofstream stream(filename, std::ios::binary);
+    if (!stream) return set_error(PBSO_ERR_IO, "cannot open %s for writing", filename);
+    stream.write(bytes.data(), (std::streamsize)bytes.size());
+    return stream.good() ? PBSO_OK : set_error(PBSO_ERR_IO, "short write to %s", filename);
+}
+
+int pbso_ffat_save_legacy_file(const pbso_ffat* f, int mode_id, const char* filename) {
+    PBSO_REQUIRE(f && filename, PBSO_ERR_INVALID, "null argument");
+    auto it = f->maps.find(mode_id);
+    if (it == f->maps.end()) return set_error(PBSO_ERR_RANGE, "no map with mode id %d", mode_id);
+    FatcubeMap fm; from_host_map(it->second, fm);
+    std::string bytes; legacy_fatcube_encode(fm, bytes);
     std::ofstream stream(filename, std::ios::binary);
     if (!stream) return set_error(PBSO_ERR_IO, "cannot open %s for writing", filename);
     stream.write(bytes.data(), (std::streamsize)bytes.size());

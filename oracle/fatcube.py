@@ -126,3 +126,86 @@ def load_all(dirname):
             m = load(full)
             out[m["modeid"]] = m
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# The LEGACY .fatcube form: libigl's igl::serialize of the FFAT_Map<T,3> object (ffat_solver.h:978-991 members,
+# :1066-1085 Save / Load / LoadAll; the format is external/libigl/include/igl/serialize.h:452-480 chunk header,
+# :700-1030 fundamental types / strings / std containers / Eigen matrices, :560-600 nested Serializable objects).
+# [pinned: tests/golden/legacy_fatcube/*.fatcube are written by the reference's own FFAT_Map<double,3>::Save with libigl's own
+#  serialize.h compiled in place (oracle/_ref, tests/golden/make_golden_legacy.py), and tests/test_oracle_vs_ref.py reads files
+#  the reference has just written and compares with what the reference's own LoadAll + GetMapVal gives]
+# ---------------------------------------------------------------------------------------------
+import struct as _struct
+
+
+class _Cur:
+    def __init__(self, b, o=0, end=None):
+        self.b = b; self.o = o; self.end = len(b) if end is None else end
+
+    def take(self, n):
+        if n < 0 or self.o + n > self.end:
+            raise ValueError("legacy .fatcube: truncated")
+        o = self.o; self.o += n
+        return o
+
+    def u64(self): return _struct.unpack_from("<Q", self.b, self.take(8))[0]
+    def i32(self): return _struct.unpack_from("<i", self.b, self.take(4))[0]
+    def f64(self): return _struct.unpack_from("<d", self.b, self.take(8))[0]
+    def string(self): n = self.u64(); o = self.take(n); return self.b[o:o + n].decode("latin1")
+    def sub(self, n): o = self.take(n); return _Cur(self.b, o, o + n)
+    def more(self): return self.o < self.end
+
+    def chunks(self):
+        """[string name][string type][u64 size][data] until the end: yields (name, type, cursor over data)."""
+        while self.more():
+            name = self.string(); typ = self.string(); size = self.u64()
+            yield name, typ, self.sub(size)
+
+    def matrix(self):
+        r = self.u64(); c = self.u64()                     # Eigen::Index = 8 bytes each, then column-major data
+        o = self.take(8 * r * c)
+        return np.frombuffer(self.b, dtype="<f8", count=r * c, offset=o).reshape(c, r).T.copy()
+
+
+def is_legacy(buf):
+    return len(buf) >= 22 and _struct.unpack_from("<Q", buf, 0)[0] == 14 and buf[8:22] == b"serial_map_ch3"
+
+
+def decode_legacy(buf):
+    """bytes -> the same dict decode() gives: shell 2's geometry (the one GetMapVal reads), k, centre, Psi."""
+    body = None
+    for name, _typ, cur in _Cur(buf).chunks():
+        if name == "serial_map_ch3":
+            body = cur                                      # igl::deserialize keeps the last match
+    if body is None:
+        raise ValueError("legacy .fatcube: no serial_map_ch3 object")
+    top = {}; shell = None
+    for name, _typ, d in body.sub(body.u64()).chunks():
+        if name in ("modeId", "N_elements_total", "N_directions"): top[name] = d.i32()
+        elif name in ("k", "cellSize"): top[name] = d.f64()
+        elif name in ("center", "Psi", "compressed_Psi"): top[name] = d.matrix()
+        elif name == "is_compressed": top[name] = d.b[d.take(1)] != 0
+        elif name == "maps":
+            shells = [d.sub(d.u64()) for _ in range(d.u64())]
+            shell = {}
+            for fname, _t, e in shells[2].chunks():         # GetMapVal reads _shells.at(2) (ffat_solver.h:1188-1203)
+                if fname == "cellSize": shell[fname] = e.f64()
+                elif fname in ("center", "bboxLow", "bboxTop"): shell[fname] = e.matrix()[:, 0]
+                elif fname == "lowCorners": shell[fname] = np.array([e.matrix()[:, 0] for _ in range(e.u64())])
+                elif fname == "N_elements": shell[fname] = np.array([[e.i32(), e.i32()] for _ in range(e.u64())], dtype=np.int32)
+                elif fname == "strides": shell[fname] = np.array([e.i32() for _ in range(e.u64())], dtype=np.int32)
+    comp = bool(top.get("is_compressed", False))
+    P = top["compressed_Psi"] if comp else top["Psi"]
+    out = dict(cellsize=shell["cellSize"], lowcorners=shell["lowCorners"], n_elements=shell["N_elements"], strides=shell["strides"],
+               center1=shell["center"], bboxlow=shell["bboxLow"], bboxtop=shell["bboxTop"], k=top["k"], center=top["center"][:, 0],
+               is_compressed=comp, psi_cols=[P[:, c].copy() for c in range(P.shape[1])], modeid=top["modeId"])
+    out["psi"] = out["psi_cols"][0]
+    return out
+
+
+def load_any(path):
+    """Either form of a .fatcube file."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    return decode_legacy(buf) if is_legacy(buf) else decode(buf)

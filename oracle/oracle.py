@@ -144,6 +144,10 @@ def ref():
         R.ref_ffat_free.argtypes = [C.c_void_p]
         R.ref_ffat_eval.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int, c_dp]
         R.ref_ffat_load_save.argtypes = [C.c_char_p, C.c_char_p, c_ip, c_dp]
+        R.ref_ffat_legacy_from_fatcube.argtypes = [C.c_char_p, C.c_char_p]
+        R.ref_ffat_legacy_fit_save.argtypes = [C.c_int, C.c_double, c_dp, C.c_int, c_ip, C.c_int, C.c_double, c_dp, C.c_int, C.c_char_p]
+        R.ref_ffat_legacy_load_all.restype = C.c_void_p
+        R.ref_ffat_legacy_load_all.argtypes = [C.c_char_p, c_ip]
         R.ref_list_dir_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         R.ref_batch_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp]
         R.ref_cubemap_mesh.argtypes = [c_ip, c_ip, C.c_double, c_dp, c_ip, c_dp, C.c_int, c_ip, c_ip]
@@ -313,6 +317,31 @@ def ref_ffat_eval(dirname, pos, use_compressed=False):
     ok = R.ref_ffat_eval(h, _dp(pos), L, int(use_compressed), _dp(out))
     R.ref_ffat_free(h)
     return out if ok else None
+
+
+def ref_ffat_eval_legacy(dirname, pos):
+    """The reference's LEGACY loader -- FFAT_Map<double,3>::LoadAll (igl::deserialize, ffat_solver.h:1069-1085) -- + |GetMapVal|
+    over a directory of legacy .fatcube files -> [L][N] or None."""
+    R = ref(); n = C.c_int()
+    h = R.ref_ffat_legacy_load_all(dirname.encode(), C.byref(n))
+    pos = _f64(pos).reshape(-1, 3); L = len(pos)
+    out = np.empty((L, n.value))
+    ok = R.ref_ffat_eval(h, _dp(pos), L, 0, _dp(out))
+    R.ref_ffat_free(h)
+    return out if ok else None
+
+
+def ref_ffat_legacy_from_fatcube(in_file, out_file):
+    """FFAT_Map_Serialize::Load(protobuf file) -> FFAT_Map<double,3>::Save(legacy file), the reference's own code; returns modeId."""
+    return ref().ref_ffat_legacy_from_fatcube(in_file.encode(), out_file.encode())
+
+
+def ref_ffat_legacy_fit_save(mode_id, cell_size, V, n_elements, k, pressure, power_scaling, out_file):
+    """The reference's constructor + Solve, then FFAT_Map<double,3>::Save(legacy file): a complete legacy map, three shells."""
+    V = _f64(V); ne = np.ascontiguousarray(n_elements, dtype=np.int32)
+    P = np.ascontiguousarray(pressure, dtype=np.complex128).view(np.float64)
+    return ref().ref_ffat_legacy_fit_save(int(mode_id), float(cell_size), _dp(V), len(V), _ip(ne), ne.shape[0], float(k), _dp(P),
+                                          int(power_scaling), out_file.encode())
 
 
 def force_profile(ftype, width_us, BUF, n_buf):

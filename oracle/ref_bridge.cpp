@@ -211,6 +211,40 @@ int ref_ffat_eval(void* h, const double* pos, int L, int use_compressed, double*
     } catch (const std::out_of_range&) { return 0; }
     return 1;
 }
+// The LEGACY .fatcube format (libigl's igl::serialize of the FFAT_Map<T,3> object, ffat_solver.h:978-991, 1066-1085), with the
+// reference's own code and libigl's own serialize.h compiled in place:
+//   ref_ffat_legacy_from_fatcube  FFAT_Map_Serialize::Load(protobuf file) -> FFAT_Map<T,3>::Save(legacy file)
+//   ref_ffat_legacy_fit_save      constructor + Solve (as ref_ffat_fit) -> FFAT_Map<T,3>::Save(legacy file): all three shells inside
+//   ref_ffat_legacy_load_all      FFAT_Map<T,3>::LoadAll(dir) (the legacy loader) -> the same map set handle ref_ffat_eval takes
+int ref_ffat_legacy_from_fatcube(const char* in_file, const char* out_file) {
+    Gpu_Wavesolver::FFAT_Map<double, 3> map;
+    Gpu_Wavesolver::FFAT_Map_Serialize::Load(in_file, map);
+    Gpu_Wavesolver::FFAT_Map<double, 3>::Save(out_file, map);
+    return map.modeId;
+}
+int ref_ffat_legacy_fit_save(int mode_id, double cell_size, const double* V, int n_rows, const int* n_elements, int n_shells,
+                             double k, const double* pressure, int power_scaling, const char* legacy_file) {
+    typedef Gpu_Wavesolver::FFAT_Map<double, 3> Map3;
+    Eigen::Matrix<double, Eigen::Dynamic, 3> Vm; Vm.resize(n_rows, 3);
+    for (int i = 0; i < n_rows; ++i) for (int j = 0; j < 3; ++j) Vm(i, j) = V[(size_t)i * 3 + j];
+    std::vector<std::vector<std::pair<int, int>>> ne(n_shells, std::vector<std::pair<int, int>>(6));
+    int n_total = 0;
+    for (int s = 0; s < n_shells; ++s) for (int f = 0; f < 6; ++f) {
+        ne[s][f] = std::make_pair(n_elements[(s * 6 + f) * 2], n_elements[(s * 6 + f) * 2 + 1]);
+        n_total += ne[s][f].first * ne[s][f].second;
+    }
+    Map3 map(mode_id, cell_size, Vm, ne);
+    Map3::FFAT_VectorXcd P; P.resize(2 * n_total);
+    for (int i = 0; i < 2 * n_total; ++i) P(i) = std::complex<double>(pressure[2 * i], pressure[2 * i + 1]);
+    map.Solve(k, P, power_scaling != 0);
+    Map3::Save(legacy_file, map);
+    return (int)map.GetData().rows();
+}
+void* ref_ffat_legacy_load_all(const char* dir, int* n_maps) {
+    MapSet* m = Gpu_Wavesolver::FFAT_Map<double, 3>::LoadAll(dir);
+    *n_maps = (int)m->size();
+    return m;
+}
 // Load one file and Save it again with the reference's own code (byte-level round trip of the codec).
 int ref_ffat_load_save(const char* in_file, const char* out_file, int* mode_id, double* k_cell) {
     Gpu_Wavesolver::FFAT_Map<double, 3> map;

@@ -5,6 +5,7 @@
 // vertices.f64: rows x 3 doubles (row-major).  Prints GetMapVal(probe) with 17 significant digits.
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <string>
 #include <vector>
 #include "ffat_map_serialize.h"
@@ -47,5 +48,17 @@ int main(int argc, char** argv) {
     FFAT_Map<double, 3> cback;
     FFAT_Map_Serialize::Load(cfile.c_str(), cback);
     printf("%.17g %.17g %.17g %.17g\n", amp, map.GetMapVal(probe, true), cback.GetMapVal(probe, true), map.GetMapVal(probe));
+    // the legacy file form (FFAT_Map<T,3>::Save / Load / LoadAll, reference :1066-1085) next to the protobuf one: the plain map
+    // through LoadAll, the compressed one through Load
+    const std::string ldir = std::string(argv[9]) + ".legacy";
+    if (system(("mkdir -p '" + ldir + "'").c_str()) != 0) return 5;
+    FFAT_Map<double, 3>::Save((ldir + "/m.fatcube").c_str(), back);
+    std::map<int, FFAT_Map<double, 3>>* all = FFAT_Map<double, 3>::LoadAll(ldir.c_str());
+    const std::string lcfile = std::string(argv[9]) + ".legacy-compressed";
+    FFAT_Map<double, 3>::Save(lcfile.c_str(), map);
+    FFAT_Map<double, 3> lback;
+    FFAT_Map<double, 3>::Load(lcfile.c_str(), lback);
+    printf("%d %.17g %.17g\n", (int)all->size(), lback.GetMapVal(probe, true), all->at(modeId).GetMapVal(probe));
+    delete all;
     return 0;
 }

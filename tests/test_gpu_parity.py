@@ -911,8 +911,9 @@ def test_ffat_fit_header_mirror_caller(pbso, orc, tmp_path):
             r = subprocess.run([exe, nfile, vfile, repr(w["cell_size"]), "6", repr(float(w["k"][0])), pfile, str(binary), str(scaling),
                                 out] + [repr(x) for x in probe], capture_output=True, text=True)
             assert r.returncode == 0, r.stderr
-            rows, cols, v1, v2, amp, c1, c2, v3 = r.stdout.split()
+            rows, cols, v1, v2, amp, c1, c2, v3, n_legacy, l1, l2 = r.stdout.split()
             assert (int(rows), int(cols)) == (fit["n_dir"], 1) and v1 == v2 == v3 and c1 == c2
+            assert int(n_legacy) == 1 and l1 == c1 and l2 == v1          # legacy Save / Load / LoadAll: the compressed map survives (both views)
             d = fatcube.load(out)
             assert d["modeid"] == 6 and np.allclose(d["psi"], want[0], rtol=1e-12, atol=0)
             g, ig = fit["geom"][2], fit["igeom"][2]
@@ -939,6 +940,15 @@ def test_ffat_fit_reproduces_the_reference_fixture(pbso, golden_dir):
     for scaling, key in ((False, "psi"), (True, "psi_scaled")):
         psi, _ = ft.Solve(g["k"], g["pressure"], scaling)
         assert np.allclose(psi, g[key], rtol=1e-12, atol=0)
+
+
+def test_legacy_fatcube_directory_evaluates_like_the_reference(pbso, golden_dir):
+    """K3 on maps read from the LEGACY .fatcube form (tests/golden/legacy_fatcube/, written by the reference's own
+    FFAT_Map<double,3>::Save through libigl's own igl::serialize) against |GetMapVal| computed by the reference's own legacy loader
+    (legacy_eval.npz): maps of different sizes, so the per-map kernel."""
+    g = np.load(os.path.join(golden_dir, "legacy_eval.npz"))
+    fm = pbso.FFATMaps.LoadAll(os.path.join(golden_dir, "legacy_fatcube"))
+    assert np.allclose(fm.computeTransfer(g["pos"]), g["out"], rtol=1e-12, atol=0)
 
 
 def test_ffat_compress_reproduces_the_opencv_fixture(pbso, orc, golden_dir, tmp_path):

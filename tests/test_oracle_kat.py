@@ -263,3 +263,15 @@ def test_ffat_compress_oracle_reproduces_the_opencv_fixture(orc, golden_dir):
         assert np.array_equal(q, g["q8_pre"][i])
         assert np.array_equal(amp, g["max_amp"][i]) and gmax == g["max_amp_global"][i]
         assert np.array_equal(orc.ffat_dequantise(m, g["q8_post"][i], amp), g["compressed_psi"][i])
+
+
+def test_legacy_fatcube_oracle_reader_reproduces_the_reference_fixture(orc, golden_dir):
+    """tests/golden/legacy_fatcube/*.fatcube were written by the reference's own FFAT_Map<double,3>::Save through libigl's own
+    igl::serialize, and legacy_eval.npz by its own legacy LoadAll + |GetMapVal| (tests/golden/make_golden_legacy.py): the oracle's
+    reader of that form + the oracle's GetMapVal must reproduce it."""
+    from oracle import fatcube
+    g = np.load(os.path.join(golden_dir, "legacy_eval.npz"))
+    maps = [fatcube.load_any(os.path.join(golden_dir, "legacy_fatcube", "mode-%d.fatcube" % i)) for i in range(4)]
+    assert [m["modeid"] for m in maps] == [0, 1, 2, 3]
+    got = np.concatenate([orc.ffat_eval([m], g["pos"]) for m in maps], axis=1)
+    assert np.isfinite(g["out"]).all() and np.allclose(got, g["out"], rtol=1e-13, atol=0)

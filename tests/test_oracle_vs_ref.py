@@ -398,6 +398,7 @@ def test_projection_matches_the_reference_tool_functions(orc, ref, tmp_path):
     exe = str(tmp_path / "ref_modal_force")
     r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-w", '-DREF_MODAL_FORCE_EXTRACT="%s"' % extract,
                         "-I" + os.path.join(root, "oracle", "ref_stubs"), "-I" + os.path.join(root, "include", "openpbso", "eigen_shim"), "-I" + ref_root,
+                        "-I" + os.path.join(ref_root, "external", "libigl", "include"),
                         os.path.join(root, "tests", "cpp", "ref_modal_force_main.cpp"), os.path.join(ref_root, "io.cpp"), "-o", exe, "-pthread"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     M, V = 23, 40
@@ -420,3 +421,39 @@ def test_projection_matches_the_reference_tool_functions(orc, ref, tmp_path):
         got = np.fromfile(out).reshape(len(cmds), forceDim)
         # same three / nine products; the oracle is built -march=native (FMA contraction), the reference harness is not
         assert np.allclose(got, np.array(want), rtol=1e-13, atol=1e-15)
+
+
+def test_legacy_fatcube_both_directions_against_the_reference(orc, golden_dir, tmp_path):
+    """The legacy .fatcube form against the reference's own code (FFAT_Map<double,3>::Save / LoadAll with libigl's own igl/serialize.h,
+    compiled in place).  (1) The reference writes freshly fitted maps and a re-saved protobuf map; the oracle's reader gets the fields
+    the protobuf form of the same map carries, and oracle reader + oracle GetMapVal equal the reference's legacy LoadAll + GetMapVal.
+    (2) The PRODUCT's legacy writer (host-only code of libpbso_b200, no device needed) produces files the reference's own
+    igl::deserialize accepts -- it matches member names AND typeid strings -- and evaluates identically."""
+    import os
+    from oracle import fatcube
+    from openpbso_b200 import synth
+    import openpbso_b200 as pbso
+    d = str(tmp_path / "legacy"); os.makedirs(d)
+    w = synth.ffat_fit_workload(2, 71, half_cells=((2, 2, 3), (3, 4, 4), (4, 5, 6)), cell_size=0.2)
+    for m in range(2):
+        assert orc.ref_ffat_legacy_fit_save(m, w["cell_size"], w["V"], w["n_elements"], w["k"][m], w["pressure"][m], m == 1,
+                                            os.path.join(d, "mode-%d.fatcube" % m)) > 0
+        pbfile = str(tmp_path / ("pb-%d.fatcube" % m))
+        orc.ref_ffat_fit(m, w["cell_size"], w["V"], w["n_elements"], w["k"][m], w["pressure"][m], m == 1, save_to=pbfile)
+        a, b = fatcube.load_any(os.path.join(d, "mode-%d.fatcube" % m)), fatcube.load(pbfile)
+        for key in ("cellsize", "k", "modeid", "is_compressed"):
+            assert a[key] == b[key], key
+        for key in ("lowcorners", "n_elements", "strides", "center1", "bboxlow", "bboxtop", "center", "psi"):
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), key
+    pos = np.concatenate([synth.listeners(120, 72), 3.0 * np.eye(3), -3.0 * np.eye(3)])
+    want = orc.ref_ffat_eval_legacy(d, pos)
+    maps = [fatcube.load_any(os.path.join(d, "mode-%d.fatcube" % m)) for m in range(2)]
+    got = np.concatenate([orc.ffat_eval([m], pos) for m in maps], axis=1)
+    assert want is not None and np.allclose(got, want, rtol=1e-13, atol=0)
+    # (2) product writer -> reference reader
+    d2 = str(tmp_path / "written"); os.makedirs(d2)
+    fm = pbso.FFATMaps.LoadAll(d)
+    for m in range(2):
+        fm.SaveLegacy(m, os.path.join(d2, "mode-%d.fatcube" % m))
+    back = orc.ref_ffat_eval_legacy(d2, pos)
+    assert back is not None and back.shape == want.shape and np.array_equal(back, want)
