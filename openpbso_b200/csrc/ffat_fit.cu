@@ -253,7 +253,8 @@ static int launch_solve(pbso_ffat_fitter* f, int n_maps, const double* d_k, cons
     // through a shared-memory ring; one thread per (direction, shell) -- 56 registers, 36 resident warps instead of 16, 10 %
     // slower; issuing the y + 1 taps after the y taps so that they hit L1 -- no change.  ncu: L2 sector traffic is 3 x the
     // algorithmic bytes (the four taps and three shells of neighbouring directions re-read sectors that L1 does not hold
-    // long enough), 5.5 TB/s of L2 traffic is what bounds the kernel)
+    // long enough); staging each block's three contiguous runs of quads through shared memory with cp.async, double-buffered
+    // over the modes -- bit-identical, 8 % slower)
     {
         // direct gathers: enough blocks for ~16 resident CTAs on every SM before modes are folded into a block
         int mpb = 1;
