@@ -807,9 +807,14 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             }
             st->ev_ver = a.ev_ver; st->list_state = (a.v0r ? 1 : 0) + (a.d_stems ? 2 : 0); st->list_tiles = n_tiles; st->list_buf = a.buf_size; st->list_obj0 = o0; st->list_nobj = no;
         }
-        if (st->n_units == 0) continue;                               // silence: the mix is already zeroed
         // state blocks: carrier [n_it][no] | impulses of the batch
         const int e0 = a.h_ev_off[o0], ne = a.h_ev_off[o0 + no] - e0;
+        if (st->n_units == 0) {
+            // nothing for the contraction: silence (the mix is already zeroed) -- or impulses that land inside the LAST tile
+            // of the render, whose samples are all head samples
+            if (ne > 0 && a.buf_size % TCB_L != 0) { if (int rc = batch_event_heads(a, e0, ne, st->ev_obj)) return rc; ++*launches; }
+            continue;
+        }
         const size_t vneed = ((size_t)n_it * no + ne + 1) * mp;           // + one zero block: the idle half of a pair
         if (vneed > st->v_cap) {
             cudaFree(st->V); st->V = nullptr; st->v_cap = 0;

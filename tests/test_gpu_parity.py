@@ -617,7 +617,7 @@ def test_batch_tc3x_longer_render_after_shorter(pbso):
         assert_waveform_parity(br.render_mix(256, n_buf, pbso.PREC_TC3X), br.render_mix(256, n_buf, pbso.PREC_F64))
 
 
-@pytest.mark.parametrize("BUF", [513, 100, 129, 640])
+@pytest.mark.parametrize("BUF", [513, 100, 129, 640, 43])
 def test_batch_tc3x_any_buffer_size(pbso, orc, BUF):
     """The tensor-core path at buffer sizes that are not multiples of its 128-sample tiles -- 513 is the reference's
     default FRAMES_PER_BUFFER (modal_solver.h:100): impulses land inside a tile (their first samples come from the
@@ -646,6 +646,13 @@ def test_batch_tc3x_any_buffer_size(pbso, orc, BUF):
     assert_waveform_parity(ytc, want)
     s64 = br.render_stems(BUF, n_buf, pbso.PREC_F64); stc = br.render_stems(BUF, n_buf, pbso.PREC_TC3X)
     assert np.abs(stc - s64).max() <= 3e-6 * np.abs(s64).max()
+    # an impulse that lands inside the LAST tile of the render and is the only one: nothing reaches the contraction, every
+    # sample it produces is a head sample
+    b1 = pbso.BatchRenderer(H, w["a"][:1], w["b"][:1]); b1.set_transfer(w["trans"][:1])
+    for nb in range(2, 7):
+        if ((nb - 1) * BUF) % 128 != 0 and -(-((nb - 1) * BUF) // 128) * 128 >= nb * BUF:
+            b1.set_impulses([0], [nb - 1], space[:1])
+            assert_waveform_parity(b1.render_mix(BUF, nb, pbso.PREC_TC3X), b1.render_mix(BUF, nb, pbso.PREC_F64), rel=1e-9, mx=1e-9)
     n1 = n_buf // 2
     first = buf < n1
     br.set_impulses(obj[first], buf[first], space[first]); y1 = br.render_mix(BUF, n1, pbso.PREC_TC3X)
