@@ -154,6 +154,16 @@ k_fit_solve(int S_rt, int n_dir, int n_total, int n_maps, int maps_per_block, co
             for (int s = 0; s < SR; ++s)
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) v[s][kk] = __ldg(P + idx[s][kk]);       // all gathers in flight first
+            // ... and the next mode's lines are requested now, so that its gathers find them on the way (ncu: half of all stall
+            // samples sit on the first FMA behind the gathers -- the kernel waits for DRAM once per mode and warp)
+            // (measured: 115.7 -> 103.4 us on the same box; two modes ahead or prefetching into L1: no further gain)
+            if (m + 1 < m1) {
+                const double2* Pn = P + (packed ? (size_t)n_total : (size_t)2 * n_total);
+#pragma unroll
+                for (int s = 0; s < SR; ++s)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pn + idx[s][kk]));
+            }
 #pragma unroll
             for (int s = 0; s < SR; ++s) {
                 double pre = 0.0, pim = 0.0;
