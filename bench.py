@@ -518,9 +518,12 @@ def run_ours(args):
         ln, prev = lanes[k & 1], lanes[(k + 1) & 1]
         ln["br"].set_transfer(trans_h, wait=False)
         ln["br"].set_impulses(obj_h, buf_h, space_h, wait=False)
+        if comm:
+            # the previous step's reduce goes first: the render kernel is persistent and fills every SM (registers included), so
+            # an NCCL kernel that becomes ready behind it would wait for the whole render
+            ln["st"].wait_event(prev["red"])
         ln["br"].render_mix_device(BUF, args.buffers, ln["mix"].data_ptr(), prec)
         if comm:
-            ln["st"].wait_event(prev["red"])
             comm.reduce_audio(ln["mix"].data_ptr(), n_samples, 0, ln["st"].cuda_stream)
             ln["red"].record(ln["st"])
         if rank == 0:
