@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_OBJ, N_MODES, BUF, N_BUF = 4096, 512, 256, 1723      # cfg5: 441 088 samples = 10.0 s
-TC3X_DRAM_BYTES_PER_MODE_SAMPLE = 1.222e9 / 9.2504e11    # ncu --set full, cfg5 launch: 1.18 GB read + 0.04 GB written (profiles/r2_k_batch_tc_metrics.txt)
+TC3X_DRAM_BYTES_PER_MODE_SAMPLE = 1.21867e9 / 9.2504e11   # dram__bytes_read + _write of k_batch_tc<2> on a full cfg5 launch (profiles/r2_k_batch_tc_final_metrics.txt)
 FLOP_PER_MODE_SAMPLE = 8.0                              # 4 FMA: 3 in Step (modal_integrator.h:109-110) + 1 in the dot (modal_solver.h:267-269)
 
 
