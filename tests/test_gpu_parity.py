@@ -748,7 +748,7 @@ def test_batch_tc3x_object_batches(pbso, monkeypatch):
     batch; same waveform as the FP64 kernel."""
     n_obj, n_modes, n_buf = 23, 40, 150
     w = synth.batch_workload(n_obj, n_modes, n_buf, 77, "low_damping", first_second_bufs=100)
-    monkeypatch.setenv("PBSO_TC_TABLE_BYTES", str(5 * 3 * 5376))           # room for 5 objects (3 chunks each)
+    monkeypatch.setenv("PBSO_TC_TABLE_BYTES", str(5 * 3 * 5520))           # room for 5 objects (3 chunks of 5520 bytes each)
     br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"])
     br.set_impulses(np.arange(n_obj), w["imp_buf"], w["space"])
     y64 = br.render_mix(256, n_buf, pbso.PREC_F64)
