@@ -79,6 +79,7 @@ constexpr int TCB_SEED_BYTES = 1024;                    // X[8 blk][16 m] float2
 constexpr int TCB_SMEM = TCB_NB * TCB_BT_BYTES + TCB_NT * TCB_TAB_BYTES + TCB_NS * TCB_SEED_BYTES + 512 + 1024;
 constexpr int TCB_WINDOW = 8;              // objects per work item
 constexpr int TCB_FLUSH_UNITS = 8;         // units between FP64 flushes of the register accumulators
+constexpr int TCB_FLUSH_CHUNKS = 256;      // ... and never more K chunks than this in one FP32 running sum (8 units of 512 modes)
 static_assert(TCB_SMEM <= 232448, "shared memory budget");
 static_assert(TCB_NA == TCB_NB, "A and B stages share their full / empty barriers");
 
@@ -268,7 +269,7 @@ template <int PAIR>
 __global__ void __launch_bounds__(TCB_THREADS, 1)
 k_batch_tc(int n_modes, int n_tiles, long long n_samples, const int* __restrict__ cta_first, const Unit* __restrict__ units,
            const uint8_t* __restrict__ tab, const float2* __restrict__ V, int obj0,
-           double* __restrict__ mix, float* __restrict__ stems, double inv_gain, int ablate, unsigned long long* __restrict__ prof) {
+           double* __restrict__ mix, float* __restrict__ stems, double inv_gain, int ablate, unsigned long long* __restrict__ prof, int flush_chunks) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* tabs = smem + TCB_NB * TCB_BT_BYTES;
@@ -459,8 +460,38 @@ k_batch_tc(int n_modes, int n_tiles, long long n_samples, const int* __restrict_
 #pragma unroll
         for (int j = 0; j < TCB_L / 2; ++j) acc[j] = 0ull;
         uint32_t g = 0;
+        int chunks_held = 0;                                                 // K chunks summed in the registers since the last flush
+        // registers -> FP64 mix (and / or the object's float stem), then cleared
+        auto flush = [&](const Unit& un) {
+            const long long tile = ((long long)un.it * PAIR + rank) * TCB_ROWS + row;
+            // the last tile of a render whose length is not a multiple of 128 is cut at n_samples
+            const int lim = tile < n_tiles ? (int)min((long long)TCB_L, n_samples - tile * TCB_L) : 0;
+            if (lim > 0 && mix) {
+                double* dst = mix + tile * TCB_L;
+#pragma unroll
+                for (int j = 0; j < TCB_L / 2; ++j) {
+                    float a, b; upk(acc[j], a, b);
+                    if (2 * j < lim) atomicAdd(dst + 2 * j, (double)a * inv_gain);
+                    if (2 * j + 1 < lim) atomicAdd(dst + 2 * j + 1, (double)b * inv_gain);
+                }
+            }
+            if (lim > 0 && stems) {                                  // per-object stems: the host flushes at every object change
+                float* dst = stems + (size_t)un.obj * n_samples + tile * TCB_L;
+                const float ig = (float)inv_gain;
+#pragma unroll
+                for (int j = 0; j < TCB_L / 2; ++j) {
+                    float a, b; upk(acc[j], a, b);
+                    if (2 * j < lim) atomicAdd(dst + 2 * j, a * ig);
+                    if (2 * j + 1 < lim) atomicAdd(dst + 2 * j + 1, b * ig);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < TCB_L / 2; ++j) acc[j] = 0ull;
+            chunks_held = 0;
+        };
 #pragma unroll 1
         for (int u = u0; u < u1; ++u) {
+            const Unit un = units[u];
 #pragma unroll 1
             for (int ch = 0; ch < cpu; ch += 2, ++g) {
                 const int buf = g & 1;
@@ -473,34 +504,12 @@ k_batch_tc(int n_modes, int n_tiles, long long n_samples, const int* __restrict_
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) PBSO_ARRIVE_LEAD(lead_accempty, buf);
+                // the FP32 running sum is bounded in CHUNKS, not in units: an object with thousands of modes has hundreds of
+                // chunks per unit, and 4096 of them in one FP32 sum cost a factor 2 in max-abs error (1.3e-6 at 8192 modes)
+                chunks_held += 2;
+                if (chunks_held >= flush_chunks && ch + 2 < cpu) flush(un);
             }
-            const Unit un = units[u];
-            if (un.flush) {
-                const long long tile = ((long long)un.it * PAIR + rank) * TCB_ROWS + row;
-                // the last tile of a render whose length is not a multiple of 128 is cut at n_samples
-                const int lim = tile < n_tiles ? (int)min((long long)TCB_L, n_samples - tile * TCB_L) : 0;
-                if (lim > 0 && mix) {
-                    double* dst = mix + tile * TCB_L;
-#pragma unroll
-                    for (int j = 0; j < TCB_L / 2; ++j) {
-                        float a, b; upk(acc[j], a, b);
-                        if (2 * j < lim) atomicAdd(dst + 2 * j, (double)a * inv_gain);
-                        if (2 * j + 1 < lim) atomicAdd(dst + 2 * j + 1, (double)b * inv_gain);
-                    }
-                }
-                if (lim > 0 && stems) {                              // per-object stems: the host flushes at every object change
-                    float* dst = stems + (size_t)un.obj * n_samples + tile * TCB_L;
-                    const float ig = (float)inv_gain;
-#pragma unroll
-                    for (int j = 0; j < TCB_L / 2; ++j) {
-                        float a, b; upk(acc[j], a, b);
-                        if (2 * j < lim) atomicAdd(dst + 2 * j, a * ig);
-                        if (2 * j + 1 < lim) atomicAdd(dst + 2 * j + 1, b * ig);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < TCB_L / 2; ++j) acc[j] = 0ull;
-            }
+            if (un.flush || chunks_held >= flush_chunks) flush(un);
         }
     } else {
         // warps 20-23: the scheduler prefers the highest warp id of a sub-partition, and the MMA issuers are the warps the
@@ -774,6 +783,12 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     }
     if (!st->cta_first) PBSO_CUDA(cudaMalloc(&st->cta_first, sizeof(int) * (a.sm_count + 2)));
     static const int ablate = getenv("PBSO_TC_ABLATE") ? atoi(getenv("PBSO_TC_ABLATE")) : 0;
+    // FP32 running sums of the epilogue: at most 256 K chunks (8 units of 512 modes) -- 128 for objects with more than 1024 modes,
+    // whose chunks all belong to one impulse response and add coherently (measured, 3 objects x 8192 modes, max-abs of full scale:
+    // 8.1e-7 at 256, 5.7e-7 at 128, 4.3e-7 at 64; the flush is 128 FP64 reductions per thread: 128 instead of 256 costs 7 % of the
+    // render, 64 costs 18 %)
+    static const int flush_env = getenv("PBSO_TC_FLUSH_CHUNKS") ? std::max(2, atoi(getenv("PBSO_TC_FLUSH_CHUNKS"))) : 0;
+    const int flush_chunks = flush_env ? flush_env : (cpu > 64 ? TCB_FLUSH_CHUNKS / 2 : TCB_FLUSH_CHUNKS);
     static bool attr[64] = {};            // per device: function attributes do not carry across devices
     if (!attr[dev & 63]) {
         PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
@@ -851,10 +866,10 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
             cfg.attrs = at; cfg.numAttrs = 1;
             if (st->pair == 2)
                 PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<2>, a.n_modes, n_tiles, n_samples, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
-                                             (const float2*)st->V, o0, a.d_mix, a.d_stems, inv_gain, ablate, d_prof));
+                                             (const float2*)st->V, o0, a.d_mix, a.d_stems, inv_gain, ablate, d_prof, flush_chunks));
             else
                 PBSO_CUDA(cudaLaunchKernelEx(&cfg, k_batch_tc<1>, a.n_modes, n_tiles, n_samples, (const int*)st->cta_first, (const Unit*)st->units, (const uint8_t*)st->tab,
-                                             (const float2*)st->V, o0, a.d_mix, a.d_stems, inv_gain, ablate, d_prof));
+                                             (const float2*)st->V, o0, a.d_mix, a.d_stems, inv_gain, ablate, d_prof, flush_chunks));
         }
         if (d_prof) {
             unsigned long long h[24 * 8];

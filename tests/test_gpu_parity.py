@@ -743,6 +743,20 @@ def test_batch_stateful_ranges(pbso, orc):
     assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
 
 
+def test_batch_tc3x_objects_with_thousands_of_modes(pbso):
+    """An object with 8192 modes is 512 K chunks per unit: the FP32 register sums of the epilogue are flushed to the FP64 mix every
+    128 chunks, inside a unit too (flushing per unit only cost a factor 2 in max-abs error at this size: 1.3e-6 in the bench at
+    64 x 8192)."""
+    n_obj, n_modes, n_buf = 3, 8192, 200
+    w = synth.batch_workload(n_obj, n_modes, n_buf, 41, "low_damping", first_second_bufs=120)
+    br = pbso.BatchRenderer(H, w["a"], w["b"]); br.set_transfer(w["trans"])
+    br.set_impulses(np.arange(n_obj), w["imp_buf"], w["space"])
+    rel, mx = assert_waveform_parity(br.render_mix(256, n_buf, pbso.PREC_TC3X), br.render_mix(256, n_buf, pbso.PREC_F64))
+    assert mx <= 7e-7, mx
+    stems = br.render_stems(256, n_buf, pbso.PREC_TC3X); s64 = br.render_stems(256, n_buf, pbso.PREC_F64)
+    assert np.abs(stems - s64).max() <= 3e-6 * np.abs(s64).max()
+
+
 def test_batch_tc3x_object_batches(pbso, monkeypatch):
     """Operand tables larger than the table budget: the renderer walks the objects in batches and rebuilds the tables per
     batch; same waveform as the FP64 kernel."""
