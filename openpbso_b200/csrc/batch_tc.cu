@@ -676,15 +676,19 @@ void tc_free(TcState* st) {
 // round-robin to the CTAs (clusters) in (window, M-tile) order -- the CTAs rendering the M-tiles of one window run at about the same time, so a
 // window's table blocks are read from HBM once and from L2 by the rest; a CTA keeps one M-tile's partial mix in
 // registers across the units of an item.
-static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tiles, int n_it) {
+static void build_units(TcState* st, const TcArgs& a, int o0, int no, int n_tiles, int n_it, int cpu) {
     // an impulse joins the contraction at the first tile boundary at or after its sample (row = ceil(t_e / 128))
     auto ev_row = [&](int e) { return ((long long)a.h_ev_buf[e] * a.buf_size + TCB_L - 1) / TCB_L; };
     const int PAIR = st->pair, ncl = st->grid / PAIR, n_grp = div_up(n_it, PAIR);
     const unsigned imp_blk0 = (unsigned)((size_t)n_it * no);
     const int e_base = a.h_ev_off[o0];
     const unsigned zero_blk = imp_blk0 + (unsigned)(a.h_ev_off[o0 + no] - e_base);          // idle half of a pair
-    static const int window = getenv("PBSO_TC_WINDOW") ? std::max(1, atoi(getenv("PBSO_TC_WINDOW"))) : TCB_WINDOW;
-    static const int flush_units = getenv("PBSO_TC_FLUSH") ? std::max(1, atoi(getenv("PBSO_TC_FLUSH"))) : TCB_FLUSH_UNITS;
+    // objects per work item and units per flush: 8 for objects of 512 modes (32 K chunks each) and more; objects with fewer modes
+    // are windowed so that a flush still closes ~256 chunks (a flush stalls the pipeline for ~10 us whatever the unit length)
+    static const int window_env = getenv("PBSO_TC_WINDOW") ? std::max(1, atoi(getenv("PBSO_TC_WINDOW"))) : 0;
+    static const int flush_env = getenv("PBSO_TC_FLUSH") ? std::max(1, atoi(getenv("PBSO_TC_FLUSH"))) : 0;
+    const int window = window_env ? window_env : std::min(64, std::max(TCB_WINDOW, TCB_FLUSH_CHUNKS / std::max(cpu, 1)));
+    const int flush_units = flush_env ? flush_env : std::max(TCB_FLUSH_UNITS, window);
     std::vector<std::vector<Unit>> per(ncl);
     std::vector<int> cur(no);
     long long item = 0;
@@ -807,7 +811,7 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
         // unit list (depends on the impulse script, the render length and the batch)
         const bool relist = st->ev_ver != a.ev_ver || st->list_state != (a.v0r ? 1 : 0) + (a.d_stems ? 2 : 0) || st->list_tiles != n_tiles || st->list_buf != a.buf_size || st->list_obj0 != o0 || st->list_nobj != no;
         if (relist) {
-            build_units(st, a, o0, no, n_tiles, n_it);
+            build_units(st, a, o0, no, n_tiles, n_it, cpu);
             if ((size_t)st->n_units > st->unit_cap) {
                 cudaFree(st->units); st->units = nullptr; st->unit_cap = 0;
                 PBSO_CUDA(cudaMalloc(&st->units, sizeof(Unit) * st->n_units)); st->unit_cap = st->n_units;
