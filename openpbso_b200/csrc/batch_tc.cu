@@ -22,7 +22,7 @@
 //    .release.cluster / .acquire.cluster forms compile to GPU-scope fences and L1 invalidations and cost 30 %.
 //    (Streaming precomputed B tiles from L2 with multicast bulk copies was built and measured first: correct, but
 //    no faster than generating -- the per-SM ingest of bulk copies (~35 B/clk) and L2 bandwidth bound it.)
-//    Work items are (window of 8 objects, M-tile pair), dealt round-robin to the clusters, so the clusters rendering
+//    Work items are (window of 12 objects for cfg5, M-tile pair), dealt round-robin to the clusters, so the clusters rendering
 //    the M-tile pairs of one object window read the same 5.4 KB table blocks at about the same time: HBM sees every
 //    block about once per render (1.2 GB for cfg5 in total), L2 serves the rest.
 //  * Operand A (tile-start states) is generated on the SM straight into TMEM (tcgen05.st, MMA in TS mode):
@@ -77,9 +77,9 @@ constexpr int TCB_TAB_R = 1024, TCB_TAB_B = 1024 + 17 * TCB_RSTRIDE;
 constexpr int TCB_TAB_BYTES = TCB_TABG_BYTES + 128;     // + the chunk's 16 tile-start states
 constexpr int TCB_SEED_BYTES = 1024;                    // X[8 blk][16 m] float2: v W^(16 blk)
 constexpr int TCB_SMEM = TCB_NB * TCB_BT_BYTES + TCB_NT * TCB_TAB_BYTES + TCB_NS * TCB_SEED_BYTES + 512 + 1024;
-constexpr int TCB_WINDOW = 8;              // objects per work item
-constexpr int TCB_FLUSH_UNITS = 8;         // units between FP64 flushes of the register accumulators
-constexpr int TCB_FLUSH_CHUNKS = 256;      // ... and never more K chunks than this in one FP32 running sum (8 units of 512 modes)
+constexpr int TCB_WINDOW = 8;              // objects per work item, at least (build_units: TCB_FLUSH_CHUNKS / chunks per unit, 12 for 512 modes)
+constexpr int TCB_FLUSH_UNITS = 8;         // units between FP64 flushes of the register accumulators, at least (= the window)
+constexpr int TCB_FLUSH_CHUNKS = 384;      // ... and never more K chunks than this in one FP32 running sum (12 units of 512 modes)
 static_assert(TCB_SMEM <= 232448, "shared memory budget");
 static_assert(TCB_NA == TCB_NB, "A and B stages share their full / empty barriers");
 
@@ -787,12 +787,12 @@ int tc_render(TcState** pst, const TcArgs& a, int* launches) {
     }
     if (!st->cta_first) PBSO_CUDA(cudaMalloc(&st->cta_first, sizeof(int) * (a.sm_count + 2)));
     static const int ablate = getenv("PBSO_TC_ABLATE") ? atoi(getenv("PBSO_TC_ABLATE")) : 0;
-    // FP32 running sums of the epilogue: at most 256 K chunks (8 units of 512 modes) -- 128 for objects with more than 1024 modes,
+    // FP32 running sums of the epilogue: at most 384 K chunks (12 units of 512 modes: cfg5 measured at 256 / 384 / 512 chunks per
+    // flush, same box: 14.95 / 14.41 / 14.58 ms, max-abs 4.58e-7 / 4.50e-7 / 5.05e-7) -- 128 for objects with more than 1024 modes,
     // whose chunks all belong to one impulse response and add coherently (measured, 3 objects x 8192 modes, max-abs of full scale:
-    // 8.1e-7 at 256, 5.7e-7 at 128, 4.3e-7 at 64; the flush is 128 FP64 reductions per thread: 128 instead of 256 costs 7 % of the
-    // render, 64 costs 18 %)
+    // 8.1e-7 at 256, 5.7e-7 at 128, 4.3e-7 at 64).  A flush is 128 FP64 reductions per thread and stalls the pipeline ~10 us.
     static const int flush_env = getenv("PBSO_TC_FLUSH_CHUNKS") ? std::max(2, atoi(getenv("PBSO_TC_FLUSH_CHUNKS"))) : 0;
-    const int flush_chunks = flush_env ? flush_env : (cpu > 64 ? TCB_FLUSH_CHUNKS / 2 : TCB_FLUSH_CHUNKS);
+    const int flush_chunks = flush_env ? flush_env : (cpu > 64 ? 128 : TCB_FLUSH_CHUNKS);
     static bool attr[64] = {};            // per device: function attributes do not carry across devices
     if (!attr[dev & 63]) {
         PBSO_CUDA(cudaFuncSetAttribute(k_batch_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM));
