@@ -260,3 +260,72 @@ def test_message_queue_matches_the_reference_queue(tmp_path):
         assert r.returncode == 0
         outs.append(r.stdout)
     assert outs[0] == outs[1] and "maxSize 1023 capacity 1023" in outs[0]
+
+
+def test_offline_planner_matches_the_oracle_solver(orc, tmp_path):
+    """tools/offline_render.h restates ModalSolver::step's message handling (one force message per buffer, the active-force list and
+    its (sum of loads) x (sum of profiles) rank-1 force, sustained / autoregressive forces and their parameter messages, clearAllForces,
+    the transfer queue of capacity 1, the unit transfer) to PLAN a script for the batch path.  Host-only: a random script is played
+    through the planner (tests/cpp/planner_main.cpp, no device) and through the oracle's solver, and every buffer must be given
+    the same rank-1 force and the same transfer."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include", "openpbso"); libdir = os.path.join(root, "openpbso_b200")
+    exe = str(tmp_path / "planner_main")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(inc, "eigen_shim"), "-I" + inc, "-I" + os.path.join(root, "tools"),
+                        os.path.join(root, "tests", "cpp", "planner_main.cpp"), "-L" + libdir, "-lpbso_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    N, BUF = 7, 64
+    rng = np.random.default_rng(314)
+    a, b = synth.ab_from_material(synth.mode_frequencies(N, 9), synth.MATERIALS["low_damping"])
+    sv = orc.Solver(orc.Integrator(synth.H, a, b), BUF)
+    lines = []; want = []
+    fmt = lambda v: " ".join("%.17g" % x for x in v)
+    def run(k):
+        lines.append("run %d" % k)
+        for _ in range(k):
+            if sv.step() is not None:
+                sp, tm = sv.last_force()
+                want.append((np.outer(sp, tm), sv.latest_transfer().copy()))
+    for _ in range(60):
+        c = rng.integers(0, 12)
+        v = rng.standard_normal(N)
+        if c <= 2: lines.append("point " + fmt(v)); assert sv.enqueue_force(v)
+        elif c == 3:
+            w = float(rng.choice([200.0, 900.0, 2500.0])); lines.append("gauss %.17g " % w + fmt(v)); assert sv.enqueue_force(v, orc.GAUSSIAN, w)
+        elif c == 4:
+            lines.append("ar_start " + fmt(v)); assert sv.enqueue_force(v, orc.AR, 0.0, orc.F_SUSTAIN_START)
+            run(int(rng.integers(1, 4)))
+            if rng.random() < 0.5:
+                p = (0.7, 0.2, 0.002, 0.1); lines.append("arprm %.17g %.17g %.17g %.17g" % p); sv.enqueue_arprm(*p)
+            lines.append("ar_data " + fmt(2 * v)); assert sv.enqueue_force(2 * v, orc.AR)
+            run(int(rng.integers(1, 4)))
+            lines.append("ar_end"); assert sv.enqueue_force(np.zeros(N), orc.AR, 0.0, orc.F_SUSTAIN_END)
+        elif c == 5: lines.append("clear"); assert sv.enqueue_force(np.zeros(N), orc.POINT, 0.0, orc.F_CLEAR)
+        elif c == 6:
+            t = np.abs(rng.standard_normal(N)) + 0.1
+            lines.append("trans " + fmt(t)); sv.enqueue_trans(t)               # capacity 1: a second one before a step is dropped by both
+        elif c == 7: lines.append("unit_transfer"); sv.set_use_transfer(False)
+        elif c == 8: lines.append("use_transfer"); sv.set_use_transfer(True)
+        else: run(int(rng.integers(1, 5)))
+    run(6)
+    script = tmp_path / "s.txt"; script.write_text("\n".join(lines) + "\n")
+    out = tmp_path / "plan.bin"
+    r = subprocess.run([exe, str(N), str(script), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = out.read_bytes()
+    nb, nt = np.frombuffer(raw, dtype=np.int32, count=2)
+    assert nb == len(want) and nb > 40
+    rec = 8 + 8 * (N + BUF); off = 8
+    trans = np.frombuffer(raw, dtype=np.float64, offset=8 + nb * rec).reshape(nt, N)
+    kinds = set()
+    for i in range(nb):
+        kind, ti = np.frombuffer(raw, dtype=np.int32, count=2, offset=off)
+        sp = np.frombuffer(raw, dtype=np.float64, count=N, offset=off + 8); tm = np.frombuffer(raw, dtype=np.float64, count=BUF, offset=off + 8 + 8 * N)
+        off += rec
+        kinds.add(int(kind))
+        # the same rank-1 force (the oracle is built with -march=native: its autoregressive recurrence contracts to FMAs, hence 1e-13)
+        assert np.allclose(np.outer(sp, tm), want[i][0], rtol=1e-13, atol=0), i
+        assert np.array_equal(trans[ti], want[i][1]), i
+    assert kinds == {0, 1, 2}                                                     # silent, impulse and general buffers all occurred
