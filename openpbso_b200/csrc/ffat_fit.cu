@@ -422,10 +422,6 @@ int pbso_ffat_fitter_solve(pbso_ffat_fitter* f, int n_maps, const double* k, con
     // Solve asserts _N_directions > 0 (:1012); k == 0 would divide by zero exactly as the reference does (inf/nan out)
     DeviceGuard g(f->device);
     const size_t per_map = (size_t)((flags & PBSO_FIT_PACKED) ? 2 : 4) * f->n_total;   // doubles: 2 * n_total complex entries (:1013), half of that packed
-    // power scaling on this entry: the device computes the factor, the host multiplies while the data is in its hands
-    // (row * scale, the same FP64 product k_fit_scale does) -- no second pass over Psi on the device
-    const bool host_scale = (flags & PBSO_FIT_POWER_SCALING) && !(flags & PBSO_FIT_DEFER_SCALE);
-    std::vector<double> sc_h;
     const size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)n_maps, ((size_t)256 << 20) / (per_map * sizeof(double))));
     if (chunk > f->cap_maps) {
         cudaFree(f->d_k); cudaFree(f->d_p); cudaFree(f->d_psi); cudaFree(f->d_scale);
@@ -442,14 +438,11 @@ int pbso_ffat_fitter_solve(pbso_ffat_fitter* f, int n_maps, const double* k, con
         PBSO_CUDA(cudaMemcpyAsync(f->d_k, k + m0, n * sizeof(double), cudaMemcpyHostToDevice, f->stream));
         PBSO_CUDA(cudaMemcpyAsync(f->d_p, pressure + m0 * per_map, n * per_map * sizeof(double), cudaMemcpyHostToDevice, f->stream));
         PBSO_CUDA(cudaEventRecord(f->ev0, f->stream));
-        if (int rc = launch_solve(f, n, f->d_k, f->d_p, host_scale ? (flags | PBSO_FIT_DEFER_SCALE) : flags, f->d_psi, f->d_scale, f->stream)) return rc;
+        if (int rc = launch_solve(f, n, f->d_k, f->d_p, flags, f->d_psi, f->d_scale, f->stream)) return rc;
         PBSO_CUDA(cudaEventRecord(f->ev1, f->stream));
         PBSO_CUDA(cudaMemcpyAsync(psi + m0 * f->n_dir, f->d_psi, (size_t)n * f->n_dir * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
         if (scale) PBSO_CUDA(cudaMemcpyAsync(scale + m0, f->d_scale, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
-        if (host_scale) { sc_h.resize((size_t)n); PBSO_CUDA(cudaMemcpyAsync(sc_h.data(), f->d_scale, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream)); }
         PBSO_CUDA(cudaStreamSynchronize(f->stream));
-        if (host_scale)
-            for (int m = 0; m < n; ++m) { double* row = psi + (m0 + m) * f->n_dir; const double sc = sc_h[(size_t)m]; for (int d = 0; d < f->n_dir; ++d) row[d] *= sc; }
         float ms = 0.f; cudaEventElapsedTime(&ms, f->ev0, f->ev1); f->last_ms += ms;
     }
     return PBSO_OK;
