@@ -97,6 +97,19 @@ def test_fit_tool_writes_the_maps_the_oracle_fits(pbso, orc, fit_exe, tmp_path, 
         g, ig = fit["geom"][2], fit["igeom"][2]
         assert np.array_equal(np.asarray(d["lowcorners"]).ravel(), g[1:19]) and np.array_equal(d["bboxlow"], g[22:25])
         assert np.array_equal(d["strides"], ig[12:]) and np.array_equal(np.asarray(d["n_elements"]).ravel(), ig[:12])
+    # -compress -legacy: the same maps through FFAT_Map::Compress, written in the igl::serialize form; the oracle's independent
+    # reader finds _compressed_Psi = its own quantisation of the fitted Psi
+    from oracle import fatcube
+    out2 = str(tmp_path / "maps_cl")
+    r = subprocess.run(cmd[:cmd.index("-o") + 1] + [out2] + cmd[cmd.index("-o") + 2:] + ["-compress", "-legacy"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for m in range(4):
+        raw = open(os.path.join(out2, "%d.fatcube" % (3 + m)), "rb").read()
+        assert fatcube.is_legacy(raw)
+        d = fatcube.decode_legacy(raw)
+        plain = fm.get_map(3 + m)
+        q, amp, _ = orc.ffat_quantise(plain)
+        assert d["is_compressed"] and d["modeid"] == 3 + m and np.array_equal(d["psi"], orc.ffat_dequantise(plain, q, amp))
     short = str(tmp_path / ("p-3." + ("bin" if binary else "txt")))
     with open(short, "wb") as f:                                  # a truncated pressure file: Solve's size assert
         f.write(np.int32(0).tobytes() if binary else b"")

@@ -4,7 +4,7 @@
 // of an object fitted in one launch on the B200 (kernel K6) through libpbso_b200.so.
 //
 //   pbso_fit_ffat -n N_ELEMENTS.txt -v VERTICES.f64 -c CELL_SIZE -k WAVENUMBERS.txt -p PRESSURE_TEMPLATE -o OUT_DIR
-//                 [-b] [-s] [-first ID]
+//                 [-b] [-s] [-first ID] [-compress] [-legacy]
 //
 //   -n   one line per shell: "Nx Ny" for the six faces +x,-x,+y,-y,+z,-z   (FFAT_Map<T,3>::ReadNElementsFile, :1100-1118)
 //   -v   raw doubles, rows x 3: the cube-map mesh vertices, 4 per quad, shells back to back (CubemapMesh order, :334-397)
@@ -14,6 +14,9 @@
 //        then count doubles), default text ("re im" per line)
 //   -s   power scaling (Solve's powerScaling, :909-929)
 //   -o   output directory: OUT_DIR/<mode id>.fatcube for every mode (FFAT_Map_Serialize::Save, ffat_map_serialize.h:90-164)
+//   -compress   FFAT_Map<T,3>::Compress every map before saving (8-bit per-face quantisation, ffat_solver.h:1125-1178, without the
+//               JPEG file round trip): the files carry _compressed_Psi and is_compressed
+//   -legacy     write the legacy igl::serialize form (FFAT_Map<T,3>::Save, ffat_solver.h:1066-1068) instead of the protobuf one
 #include <sys/stat.h>
 #include <cstdio>
 #include <cstdlib>
@@ -35,18 +38,20 @@ static int fail(const char* what) {
 
 int main(int argc, char** argv) {
     std::map<std::string, std::string> opt;
-    bool binary = false, scaling = false;
+    bool binary = false, scaling = false, compress = false, legacy = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "-b") binary = true;
         else if (a == "-s") scaling = true;
+        else if (a == "-compress") compress = true;
+        else if (a == "-legacy") legacy = true;
         else if (a.size() > 1 && a[0] == '-' && i + 1 < argc) opt[a.substr(1)] = argv[++i];
         else { fprintf(stderr, "pbso_fit_ffat: unexpected argument %s\n", a.c_str()); return 2; }
     }
     for (const char* need : {"n", "v", "c", "k", "p", "o"})
         if (!opt.count(need)) {
             fprintf(stderr, "usage: pbso_fit_ffat -n N_ELEMENTS.txt -v VERTICES.f64 -c CELL_SIZE -k WAVENUMBERS.txt -p PRESSURE_TEMPLATE "
-                            "-o OUT_DIR [-b] [-s] [-first ID]\n");
+                            "-o OUT_DIR [-b] [-s] [-first ID] [-compress] [-legacy]\n");
             return 2;
         }
     const double cell = atof(opt["c"].c_str());
@@ -109,10 +114,11 @@ int main(int argc, char** argv) {
     }
     pbso_ffat* maps = nullptr;
     if (pbso_ffat_create(n_maps, ids.data(), geom.data(), igeom.data(), psi.data(), n_dir, nullptr, &maps)) return fail("maps");
+    if (compress && pbso_ffat_compress(maps, -1, nullptr)) return fail("compress");
     mkdir(opt["o"].c_str(), 0777);
     for (int m = 0; m < n_maps; ++m) {
         const std::string out = opt["o"] + "/" + std::to_string(ids[m]) + ".fatcube";
-        if (pbso_ffat_save_file(maps, ids[m], out.c_str())) return fail("save");
+        if (legacy ? pbso_ffat_save_legacy_file(maps, ids[m], out.c_str()) : pbso_ffat_save_file(maps, ids[m], out.c_str())) return fail("save");
     }
     printf("pbso_fit_ffat: %d modes, %d shells, %d quads, %d directions, fit kernels %.3f ms -> %s/*.fatcube\n", n_maps,
            (int)N_elements.size(), n_total, n_dir, kernel_ms, opt["o"].c_str());
