@@ -329,3 +329,31 @@ def test_offline_planner_matches_the_oracle_solver(orc, tmp_path):
         assert np.allclose(np.outer(sp, tm), want[i][0], rtol=1e-13, atol=0), i
         assert np.array_equal(trans[ti], want[i][1]), i
     assert kinds == {0, 1, 2}                                                     # silent, impulse and general buffers all occurred
+
+
+def test_compress_host_side_reproduces_the_opencv_fixture(pbso, golden_dir, tmp_path):
+    """The host half of FFAT_Map<T,3>::Compress in the product (pbso_ffat_quantise / pbso_ffat_set_compressed_u8 / pbso_ffat_compress: a
+    format conversion next to the file codecs, no device involved) against tests/golden/ffat_compress.npz, made with OpenCV's own cast
+    and JPEG codec: OpenCV's bytes out, _compressed_Psi bit for bit from the post-JPEG bytes, Save writing it in both file forms."""
+    from oracle import fatcube
+    g = np.load(os.path.join(golden_dir, "ffat_compress.npz"))
+    maps = synth.ffat_maps(g["freqs"], 2000, n=8)
+    for i, m in enumerate(maps):
+        m["psi"] = g["psi"][i]
+    fm = pbso.FFATMaps.from_dicts(maps)
+    for i in range(3):
+        q, amp, gmax = fm.quantise(i)
+        assert np.array_equal(q, g["q8_pre"][i]) and np.array_equal(amp, g["max_amp"][i]) and gmax == g["max_amp_global"][i]
+        fm.set_compressed_u8(i, g["q8_post"][i], amp)
+        q2, amp2, c = fm.get_compressed(i)
+        assert np.array_equal(q2, g["q8_post"][i]) and np.array_equal(amp2, amp) and np.array_equal(c, g["compressed_psi"][i])
+        for legacy in (False, True):
+            fn = str(tmp_path / ("c%d%d.fatcube" % (i, legacy)))
+            (fm.SaveLegacy if legacy else fm.Save)(i, fn)
+            d = fatcube.load_any(fn)
+            assert d["is_compressed"] and np.array_equal(d["psi"], g["compressed_psi"][i])
+    with pytest.raises(pbso.PbsoError):
+        fm.set_compressed_u8(0, g["q8_post"][0][:-1], g["max_amp"][0])                      # one byte per texel
+    back = pbso.FFATMaps.Load(str(tmp_path / "c10.fatcube"))
+    with pytest.raises(pbso.PbsoError):
+        back.quantise(1)                                                                    # loaded compressed: no _Psi to compress
